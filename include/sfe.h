@@ -1,0 +1,174 @@
+/*
+ * sfe.h — C ABI of the B200-native speech frontend ("sfe") library, libsfe.so.
+ *
+ * This is the drop-in boundary for the on-the-fly acoustic frontend of bagustris/speechain
+ * (SURVEY.md §8b).  The reference is pure Python: its "FFI" for this path is the module API
+ * of speechain/module/{frontend,norm,augment}; each entry point below names the reference
+ * code whose arithmetic it replaces.  Plain C types and raw device pointers only — no torch
+ * types cross this boundary, and the library owns no per-call memory: every buffer is
+ * allocated by the caller (PyTorch's caching allocator in the shipped host layer).
+ *
+ * Conventions
+ *   - All array pointers are DEVICE pointers unless the name ends in _host.
+ *   - All calls are asynchronous on `stream` (a cudaStream_t passed as void*); nothing
+ *     synchronises the host.  A plan is immutable after creation and may be used from any
+ *     thread that has the plan's device current.
+ *   - Return value 0 = success; non-zero = sfe_status.  No C++ exception crosses the ABI;
+ *     sfe_last_error() returns a thread-local message for the last failing call.
+ *   - Features are fp32, lengths int64, mask descriptors int32.
+ */
+#ifndef SFE_H_
+#define SFE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFE_ABI_VERSION 1
+
+typedef enum sfe_status {
+  SFE_OK = 0,
+  SFE_ERR_BAD_CONFIG = 1,       /* inconsistent sfe_config                                  */
+  SFE_ERR_UNSUPPORTED_NFFT = 2, /* no FFT plan compiled for this n_fft                      */
+  SFE_ERR_BAD_ARG = 3,          /* NULL / misaligned pointer, negative size, D too large …  */
+  SFE_ERR_CUDA = 4              /* a CUDA runtime call or kernel launch failed              */
+} sfe_status;
+
+/* Constructor arguments of Speech2LinearSpec + LinearSpec2MelSpec, already resolved by the host
+ * layer (seconds -> samples, n_fft default, fmax default): speech2linear.py:85-140,
+ * linear2mel.py:117-161, speech2mel.py:107-151. */
+typedef struct sfe_config {
+  int32_t n_fft;          /* even; must have a compiled plan (see sfe_supported_nfft)          */
+  int32_t win_length;     /* 1..n_fft                                                          */
+  int32_t hop_length;     /* >= 1                                                              */
+  int32_t center;         /* torch.stft(center=...): batch-level reflect padding by n_fft/2    */
+  int32_t has_preemphasis;
+  float   preemphasis;    /* y[n] = x[n] - a*x[n-1], y[0]=x[0], y[>=len]=0  (s2l.py:167-173)   */
+  int32_t mag_spec;       /* sqrt of the power spectrum before the mel bank (s2l.py:236-237)   */
+  /* linear-spectrogram output transform (Speech2LinearSpec standalone, s2l.py:240-245) */
+  int32_t lin_logging;
+  float   lin_clamp;
+  float   lin_log_div;    /* ln(log_base), or 1.0f for natural log                             */
+  /* mel stage (linear2mel.py:177-187); n_mels == 0 => plan without a mel stage */
+  int32_t n_mels;
+  int32_t mel_logging;
+  float   mel_clamp;
+  float   mel_log_div;
+  const float* window_host;     /* win_length floats (already * n_fft^-0.5 if normalized=True)  */
+  const float* mel_weight_host; /* (n_mels, n_fft/2+1) row-major, rows banded; NULL if n_mels==0 */
+} sfe_config;
+
+typedef struct sfe_plan sfe_plan;
+
+/* SpecAugment masks drawn by the host with the reference's torch.randint sequence
+ * (specaug.py:145-199).  All device pointers, int32, shape (B, n_freq) / (B, n_time). */
+typedef struct sfe_masks {
+  const int32_t* freq_pos;
+  const int32_t* freq_len;
+  int32_t n_freq;
+  const int32_t* time_pos;
+  const int32_t* time_len;
+  int32_t n_time;
+  float fill;              /* 0.0 when feat_norm=True (specaug.py:203)                         */
+  const float* fill_dev;   /* if non-NULL, the fill value is read from device (feat.mean())    */
+} sfe_masks;
+
+/* Batch-shared SpecAugment time warp (specaug.py:96-124): rows [0,center) are resampled to
+ * [0,pos) and [center,minlen) to [pos,minlen) by cubic convolution (A=-0.75, align_corners). */
+typedef struct sfe_warp {
+  int32_t enabled;
+  int32_t center;
+  int32_t pos;
+  int32_t minlen;
+} sfe_warp;
+
+int  sfe_abi_version(void);
+const char* sfe_last_error(void);
+/* writes up to cap supported n_fft values, returns how many exist */
+int  sfe_supported_nfft(int32_t* out, int cap);
+
+int  sfe_plan_create(const sfe_config* cfg, sfe_plan** out);
+void sfe_plan_destroy(sfe_plan* plan);
+/* frames torch.stft yields for a padded batch of T_max samples (s2l.py:198) */
+int64_t sfe_plan_num_frames(const sfe_plan* plan, int64_t T_max);
+/* dynamic shared memory per CTA and CTAs per SM of the fused kernel (for reports) */
+int  sfe_plan_query(const sfe_plan* plan, int32_t* smem_bytes, int32_t* ctas_per_sm, int32_t* n_sm);
+
+/* Fused waveform -> (log-)mel / linear spectrogram / energy (+ per-utterance sums).
+ * Replaces Speech2LinearSpec.forward + LinearSpec2MelSpec.forward (= Speech2MelSpec.forward),
+ * speech2linear.py:142-250, linear2mel.py:163-189.
+ *   wav        (B, T_max) fp32, row pitch `wav_pitch` samples, zero beyond each length
+ *   wav_len    (B,) int64 device
+ *   mel        (B, F, n_mels) or NULL        F = sfe_plan_num_frames(T_max)
+ *   lin        (B, F, n_fft/2+1) or NULL
+ *   energy     (B, F) or NULL                (s2l.py:216-219,230-233)
+ *   feat_len   (B,) int64 or NULL: len//hop+1 (s2l.py:201-212); wav_len is NOT mutated
+ *   stats      (B, n_mels, 2) fp64 or NULL: sum and sum of squares of `mel` over valid frames
+ *              (zeroed by this call); input of sfe_stats_finalize / sfe_normalize
+ *   norm_mean/norm_std (n_mels,) or NULL: fused global normalisation (x-mean)/std in the
+ *              epilogue (feat_norm.py:327-336, frozen/eval statistics)
+ *   masks      NULL or SpecAugment masks applied in the epilogue (needs min over feat_len
+ *              already folded into the drawn positions)
+ *   skip_pad   if non-zero, mel rows t >= feat_len are left unwritten (a following
+ *              sfe_normalize call synthesises them) */
+int sfe_frontend_forward(const sfe_plan* plan, const float* wav, int64_t wav_pitch,
+                         const int64_t* wav_len, int32_t B, int64_t T_max, float* mel, float* lin,
+                         float* energy, int64_t* feat_len, double* stats, const float* norm_mean,
+                         const float* norm_std, const sfe_masks* masks, int32_t skip_pad,
+                         void* stream);
+
+/* LinearSpec2MelSpec.forward on an existing linear spectrogram (linear2mel.py:163-189).
+ * lin (B*F, n_fft/2+1) -> mel (B*F, n_mels). */
+int sfe_linear2mel_forward(const sfe_plan* plan, const float* lin, int64_t n_rows, float* mel,
+                           void* stream);
+
+/* Sum / sum of squares over valid frames of an arbitrary (B, F, D) tensor
+ * (feat_norm.py:115-133 first half).  stats (B, D, 2) fp64 is zeroed by this call. */
+int sfe_stats_accumulate(const float* feat, const int64_t* feat_len, int32_t B, int64_t F,
+                         int32_t D, double* stats, void* stream);
+
+/* Per-utterance mean and unbiased std (clamped) from the sums (feat_norm.py:115-133), and
+ * the packed local sums for batch/global statistics (feat_norm.py:239-266):
+ *   mean, std   (B, D) fp32 (either may be NULL)
+ *   packed      (2*D+1,) fp32 = [sum_i mean_i | sum_i std_i | B] or NULL */
+int sfe_stats_finalize(const double* stats, const int64_t* feat_len, int32_t B, int32_t D,
+                       float clamp, float* mean, float* std, float* packed, void* stream);
+
+/* Batch statistics from (all-reduced) packed sums and the running-average update of
+ * register_mean_std_batch (feat_norm.py:250,265,483-508):
+ *   batch_mean = packed[0:D]/packed[2D], batch_std = packed[D:2D]/packed[2D]
+ *   if update: run = first ? batch : w*batch + (1-w)*run          (w = 1/global_batch)
+ *   batch_mean_out / batch_std_out (D,) optional copies of the batch statistics. */
+int sfe_running_update(const float* packed, int32_t D, float weight, int32_t first,
+                       int32_t update, float* run_mean, float* run_std, float* batch_mean_out,
+                       float* batch_std_out, void* stream);
+
+/* (x - mean)/std, optional time warp, optional SpecAugment masking, one read + one write.
+ * Replaces feat_norm.py:137-139 / 283-299 / 327-336 and specaug.py:111-124,202-204.
+ *   src, dst   (B, F, D); may alias when warp is NULL/disabled
+ *   stats      if non-NULL: per-utterance statistics are derived from these sums
+ *              (utterance mode) and written to mean_out/std_out (B, D) when non-NULL
+ *   mean, std  if stats is NULL: vectors of shape (D,) when per_utt == 0 (batch/global
+ *              mode) or (B, D) when per_utt != 0; either may be NULL (mean_norm/std_norm off)
+ *   use_mean/use_std: the mean_norm / std_norm switches when stats != NULL
+ *   pad_value  value of unwritten rows t >= feat_len when src_has_pad == 0 */
+int sfe_normalize(const float* src, float* dst, const int64_t* feat_len, int32_t B, int64_t F,
+                  int32_t D, const double* stats, float clamp, int32_t use_mean, int32_t use_std,
+                  const float* mean, const float* std, int32_t per_utt, float* mean_out,
+                  float* std_out, int32_t src_has_pad, float pad_value, const sfe_warp* warp,
+                  const sfe_masks* masks, void* stream);
+
+/* DeltaFeature.forward (delta_feat.py:57-81): (B, F, D) -> (B, F, D*(order+1)). */
+int sfe_delta(const float* feat, int32_t B, int64_t F, int32_t D, int32_t order, int32_t N,
+              float* out, void* stream);
+
+/* mean over all elements of a tensor into out[0] (fill value of specaug.py:203 when
+ * feat_norm=False). */
+int sfe_mean_all(const float* x, int64_t n, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFE_H_ */

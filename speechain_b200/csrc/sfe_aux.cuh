@@ -1,0 +1,391 @@
+// Light kernels around the fused frontend: statistics, normalise (+warp +mask), delta, standalone
+// mel projection.  All HBM-bound streaming passes with coalesced, vectorised accesses.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sfe_fused.cuh"
+
+namespace sfe {
+
+// ---------------------------------------------------------------------------------------------
+// per-utterance sums over valid frames of an arbitrary (B, F, D) tensor      feat_norm.py:115-133
+// grid (chunks, B); each CTA reduces FR frames of one utterance, then fp64 atomics
+// ---------------------------------------------------------------------------------------------
+constexpr int STATS_FR = 64;
+
+__global__ void __launch_bounds__(256) stats_accumulate_kernel(const float* __restrict__ feat,
+                                                               const long long* __restrict__ flen, long long F, int D,
+                                                               double* __restrict__ stats) {
+  const int b = blockIdx.y;
+  const long long n = min(flen[b], F);
+  const long long t0 = static_cast<long long>(blockIdx.x) * STATS_FR;
+  if (t0 >= n) return;
+  const long long t1 = min(n, t0 + STATS_FR);
+  const float* src = feat + (static_cast<long long>(b) * F) * D;
+  // thread -> (row group, dim): consecutive threads walk consecutive dims (coalesced)
+  extern __shared__ double sred[];  // [rows][D][2]
+  const int rows = max(1, 256 / D);
+  const int r = threadIdx.x / D, d = threadIdx.x % D;
+  double s1 = 0.0, s2 = 0.0;
+  if (r < rows) {
+    for (long long t = t0 + r; t < t1; t += rows) {
+      const double x = static_cast<double>(__ldg(src + t * D + d));
+      s1 += x;
+      s2 = fma(x, x, s2);
+    }
+    sred[(r * D + d) * 2] = s1;
+    sred[(r * D + d) * 2 + 1] = s2;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) {
+    double s = 0.0;
+    for (int q = 0; q < rows; ++q) s += sred[q * D * 2 + i];
+    atomicAdd(stats + static_cast<long long>(b) * D * 2 + i, s);
+  }
+}
+
+// wide-D variant (D > 256): one thread per dim, loop
+__global__ void __launch_bounds__(256) stats_accumulate_wide_kernel(const float* __restrict__ feat,
+                                                                    const long long* __restrict__ flen, long long F,
+                                                                    int D, double* __restrict__ stats) {
+  const int b = blockIdx.y;
+  const long long n = min(flen[b], F);
+  const long long t0 = static_cast<long long>(blockIdx.x) * STATS_FR;
+  if (t0 >= n) return;
+  const long long t1 = min(n, t0 + STATS_FR);
+  const float* src = feat + (static_cast<long long>(b) * F) * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    double s1 = 0.0, s2 = 0.0;
+    for (long long t = t0; t < t1; ++t) {
+      const double x = static_cast<double>(__ldg(src + t * D + d));
+      s1 += x;
+      s2 = fma(x, x, s2);
+    }
+    atomicAdd(stats + (static_cast<long long>(b) * D + d) * 2, s1);
+    atomicAdd(stats + (static_cast<long long>(b) * D + d) * 2 + 1, s2);
+  }
+}
+
+__device__ __forceinline__ void moments_to_mean_std(double s1, double s2, long long n, float clamp, float& mean,
+                                                    float& sd) {
+  const double dn = static_cast<double>(n);
+  const double m = s1 / dn;
+  // unbiased variance; n == 1 gives 0/0 = NaN like torch.std
+  double var = (s2 - s1 * m) / (dn - 1.0);
+  if (var < 0.0) var = 0.0;
+  float s = static_cast<float>(sqrt(var));
+  if (s < clamp) s = clamp;  // NaN stays NaN, like torch.clamp
+  mean = static_cast<float>(m);
+  sd = s;
+}
+
+// mean/std (B, D) and packed [sum mean | sum std | B]                      feat_norm.py:115-133,239-266
+__global__ void stats_finalize_kernel(const double* __restrict__ stats, const long long* __restrict__ flen, int B, int D,
+                                      float clamp, float* __restrict__ mean, float* __restrict__ sd,
+                                      float* __restrict__ packed) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  float sm = 0.f, ss = 0.f;
+  for (int b = 0; b < B; ++b) {  // rank-local sums in utterance order, like curr_means.sum(dim=0)
+    float m, s;
+    moments_to_mean_std(stats[(static_cast<long long>(b) * D + d) * 2], stats[(static_cast<long long>(b) * D + d) * 2 + 1],
+                        flen[b], clamp, m, s);
+    if (mean) mean[static_cast<long long>(b) * D + d] = m;
+    if (sd) sd[static_cast<long long>(b) * D + d] = s;
+    sm += m;
+    ss += s;
+  }
+  if (packed) {
+    packed[d] = sm;
+    packed[D + d] = ss;
+    if (d == 0) packed[2 * D] = static_cast<float>(B);
+  }
+}
+
+// batch statistics + running average                                       feat_norm.py:250,265,483-508
+__global__ void running_update_kernel(const float* __restrict__ packed, int D, float w, int first, int update,
+                                      float* __restrict__ run_mean, float* __restrict__ run_std,
+                                      float* __restrict__ bmean, float* __restrict__ bstd) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  const float n = packed[2 * D];
+  const float m = packed[d] / n, s = packed[D + d] / n;
+  if (bmean) bmean[d] = m;
+  if (bstd) bstd[d] = s;
+  if (update) {
+    if (run_mean) run_mean[d] = first ? m : w * m + (1.f - w) * run_mean[d];
+    if (run_std) run_std[d] = first ? s : w * s + (1.f - w) * run_std[d];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// normalise (+ time warp) (+ SpecAugment masks): one read, one write
+// ---------------------------------------------------------------------------------------------
+struct NormParams {
+  const float* src;
+  float* dst;
+  const long long* flen;
+  int B;
+  long long F;
+  int D;
+  const double* stats;
+  float clamp;
+  int use_mean, use_std;
+  const float* mean;
+  const float* sd;
+  int per_utt;
+  float* mean_out;
+  float* std_out;
+  int src_has_pad;
+  float pad_value;
+  int warp_on, warp_center, warp_pos, warp_minlen;
+  const int* fpos;
+  const int* flen_m;
+  int n_fmask;
+  const int* tpos;
+  const int* tlen;
+  int n_tmask;
+  float fill;
+  const float* fill_dev;
+  int frames_per_cta;
+};
+
+__device__ __forceinline__ void cubic_w(float t, float (&w)[4]) {
+  const float A = -0.75f;
+  const float x0 = t + 1.f, x1 = t, x2 = 1.f - t, x3 = 2.f - t;
+  w[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+  w[1] = ((A + 2.f) * x1 - (A + 3.f)) * x1 * x1 + 1.f;
+  w[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+  w[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+}
+
+__global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ NormParams p) {
+  extern __shared__ float nsm[];  // mean[D] | sd[D] | fmask[D]
+  const int b = blockIdx.y, D = p.D;
+  float* s_mean = nsm;
+  float* s_sd = nsm + D;
+  float* s_fm = nsm + 2 * D;
+  const long long n_valid = min(p.flen[b], p.F);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float m = 0.f, s = 1.f;
+    if (p.stats) {
+      moments_to_mean_std(p.stats[(static_cast<long long>(b) * D + d) * 2],
+                          p.stats[(static_cast<long long>(b) * D + d) * 2 + 1], p.flen[b], p.clamp, m, s);
+      if (blockIdx.x == 0) {
+        if (p.mean_out) p.mean_out[static_cast<long long>(b) * D + d] = m;
+        if (p.std_out) p.std_out[static_cast<long long>(b) * D + d] = s;
+      }
+      if (!p.use_mean) m = 0.f;
+      if (!p.use_std) s = 1.f;
+    } else {
+      if (p.mean) m = p.per_utt ? p.mean[static_cast<long long>(b) * D + d] : p.mean[d];
+      if (p.sd) s = p.per_utt ? p.sd[static_cast<long long>(b) * D + d] : p.sd[d];
+    }
+    s_mean[d] = m;
+    s_sd[d] = s;
+    bool fm = false;
+    for (int q = 0; q < p.n_fmask; ++q) {
+      const int ps = p.fpos[b * p.n_fmask + q], ln = p.flen_m[b * p.n_fmask + q];
+      fm |= (d >= ps) && (d < ps + ln);
+    }
+    s_fm[d] = fm ? 1.f : 0.f;
+  }
+  __syncthreads();
+  const bool do_mean = p.stats ? (p.use_mean != 0) : (p.mean != nullptr);
+  const bool do_std = p.stats ? (p.use_std != 0) : (p.sd != nullptr);
+  const float fillv = p.fill_dev ? *p.fill_dev : p.fill;
+  const long long t0 = static_cast<long long>(blockIdx.x) * p.frames_per_cta;
+  const long long t1 = min(p.F, t0 + p.frames_per_cta);
+  const float* src = p.src + static_cast<long long>(b) * p.F * D;
+  float* dst = p.dst + static_cast<long long>(b) * p.F * D;
+  const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.src) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(p.dst) & 15) == 0);
+  const int W = vec ? D / 4 : D;  // work items per frame
+  const long long items = (t1 - t0) * W;
+  for (long long it = threadIdx.x; it < items; it += blockDim.x) {
+    const long long t = t0 + it / W;
+    const int c = static_cast<int>(it % W);
+    bool tmask = false;
+    for (int q = 0; q < p.n_tmask; ++q) {
+      const int ps = p.tpos[b * p.n_tmask + q], ln = p.tlen[b * p.n_tmask + q];
+      tmask |= (t >= ps) && (t < ps + ln);
+    }
+    // source taps (time warp) --------------------------------------------------------------
+    int idx[4];
+    float cw[4];
+    bool warped = false;
+    if (p.warp_on && t < p.warp_minlen) {
+      warped = true;
+      int lo, in_len, out_len, tt;
+      if (t < p.warp_pos) { lo = 0; in_len = p.warp_center; out_len = p.warp_pos; tt = static_cast<int>(t); }
+      else { lo = p.warp_center; in_len = p.warp_minlen - p.warp_center; out_len = p.warp_minlen - p.warp_pos; tt = static_cast<int>(t) - p.warp_pos; }
+      const float scale = out_len > 1 ? static_cast<float>(in_len - 1) / static_cast<float>(out_len - 1) : 0.f;
+      const float real = scale * static_cast<float>(tt);
+      const int i0 = static_cast<int>(floorf(real));
+      cubic_w(real - static_cast<float>(i0), cw);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) idx[q] = lo + min(max(i0 - 1 + q, 0), in_len - 1);
+    }
+    const bool is_pad = (t >= n_valid) && !p.src_has_pad;
+    if (vec) {
+      float4 x;
+      if (is_pad) x = make_float4(p.pad_value, p.pad_value, p.pad_value, p.pad_value);
+      else if (warped) {
+        x = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(src + static_cast<long long>(idx[q]) * D) + c);
+          x.x = fmaf(cw[q], v.x, x.x); x.y = fmaf(cw[q], v.y, x.y); x.z = fmaf(cw[q], v.z, x.z); x.w = fmaf(cw[q], v.w, x.w);
+        }
+      } else x = *(reinterpret_cast<const float4*>(src + t * D) + c);
+      float* xv = reinterpret_cast<float*>(&x);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int d = c * 4 + e;
+        float v = xv[e];
+        if (do_mean) v -= s_mean[d];
+        if (do_std) v /= s_sd[d];
+        if (tmask || s_fm[d] != 0.f) v = fillv;
+        xv[e] = v;
+      }
+      *(reinterpret_cast<float4*>(dst + t * D) + c) = x;
+    } else {
+      const int d = c;
+      float v;
+      if (is_pad) v = p.pad_value;
+      else if (warped) {
+        v = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v = fmaf(cw[q], __ldg(src + static_cast<long long>(idx[q]) * D + d), v);
+      } else v = src[t * D + d];
+      if (do_mean) v -= s_mean[d];
+      if (do_std) v /= s_sd[d];
+      if (tmask || s_fm[d] != 0.f) v = fillv;
+      dst[t * D + d] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// delta / delta-delta                                                      delta_feat.py:57-81
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) delta_kernel(const float* __restrict__ x, int B, long long F, int D, int order,
+                                                    int N, float denom, float* __restrict__ out) {
+  const long long total = static_cast<long long>(B) * F * D;
+  const int OD = D * (order + 1);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int d = static_cast<int>(i % D);
+    const long long bt = i / D;
+    const long long t = bt % F, b = bt / F;
+    const float* row = x + b * F * D + d;
+    float* o = out + bt * OD;
+    o[d] = row[t * D];
+    // first order at time u (zero outside [0,F))
+    auto delta1 = [&](long long u) -> float {
+      if (u < 0 || u >= F) return 0.f;
+      float acc = 0.f;
+      for (int j = -N; j <= N; ++j) {
+        const long long v = u + j;
+        if (v >= 0 && v < F) acc = fmaf(static_cast<float>(j) / denom, __ldg(row + v * D), acc);
+      }
+      return acc;
+    };
+    o[D + d] = delta1(t);
+    if (order == 2) {
+      float acc = 0.f;
+      for (int j = -N; j <= N; ++j) acc = fmaf(static_cast<float>(j) / denom, delta1(t + j), acc);
+      o[2 * D + d] = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// mean of all elements (two-stage, fp64 accumulate)                         specaug.py:203
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sum_all_kernel(const float* __restrict__ x, long long n, double* __restrict__ acc) {
+  double s = 0.0;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    s += static_cast<double>(__ldg(x + i));
+  __shared__ double sh[256];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(acc, sh[0]);
+}
+__global__ void mean_finish_kernel(double* acc, long long n, float* out) {
+  out[0] = static_cast<float>(acc[0] / static_cast<double>(n));
+  acc[0] = 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// standalone banded mel projection of an existing linear spectrogram      linear2mel.py:163-189
+// each warp converts FPW rows per iteration through the same banded tables as the fused kernel
+// ---------------------------------------------------------------------------------------------
+struct L2MParams {
+  const float* lin;
+  float* mel;
+  long long n_rows;
+  int K, D;
+  int mel_log;
+  float mel_clamp, mel_div;
+  const float* tables;
+  int tab_floats, o_mstart, o_mw, mel_rounds, mel_tail;
+  int mel_taps[MAX_MEL_ROUNDS];
+  int sm_warp, sm_warp_bytes;
+};
+
+__global__ void __launch_bounds__(NTHREADS) linear2mel_kernel(const __grid_constant__ L2MParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  float* tab = reinterpret_cast<float*>(smem);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* P2 = reinterpret_cast<float*>(smem + p.sm_warp + warp * p.sm_warp_bytes);
+  for (int i = tid; i < p.tab_floats; i += NTHREADS) tab[i] = __ldg(p.tables + i);
+  const int p2_floats = (p.K + p.mel_tail + 2) * FPW;
+  for (int i = lane; i < p2_floats; i += 32) P2[i] = 0.f;
+  __syncthreads();
+  const int* mstart = reinterpret_cast<const int*>(tab + p.o_mstart);
+  const float* mw = tab + p.o_mw;
+  const float2* P2v = reinterpret_cast<const float2*>(P2);
+  const long long pairs = (p.n_rows + FPW - 1) / FPW;
+  for (long long pr = static_cast<long long>(blockIdx.x) * NWARPS + warp; pr < pairs;
+       pr += static_cast<long long>(gridDim.x) * NWARPS) {
+    const long long r0 = pr * FPW;
+#pragma unroll
+    for (int s = 0; s < FPW; ++s) {
+      const long long r = r0 + s;
+      for (int k = lane; k < p.K; k += 32) P2[k * FPW + s] = (r < p.n_rows) ? __ldg(p.lin + r * p.K + k) : 0.f;
+    }
+    __syncwarp();
+    int wofs = 0;
+    for (int rd = 0; rd < p.mel_rounds; ++rd) {
+      const int d = rd * 32 + lane;
+      const int st = mstart[d];
+      const int nt = p.mel_taps[rd];
+      float a0 = 0.f, a1 = 0.f;
+      for (int q = 0; q < nt; ++q) {
+        const float wgt = mw[wofs + q * 32 + lane];
+        const float2 pv = P2v[st + q];
+        a0 = fmaf(wgt, pv.x, a0);
+        a1 = fmaf(wgt, pv.y, a1);
+      }
+      wofs += nt * 32;
+      if (d < p.D) {
+        if (p.mel_log) {
+          a0 = logf(fmaxf(a0, p.mel_clamp)) / p.mel_div;
+          a1 = logf(fmaxf(a1, p.mel_clamp)) / p.mel_div;
+        }
+        if (r0 < p.n_rows) p.mel[r0 * p.D + d] = a0;
+        if (r0 + 1 < p.n_rows) p.mel[(r0 + 1) * p.D + d] = a1;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace sfe

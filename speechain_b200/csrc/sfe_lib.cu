@@ -1,0 +1,526 @@
+// libsfe.so — C ABI (include/sfe.h) over the sm_100a kernels.  No torch, no exceptions across
+// the boundary, no per-call allocation: a plan owns its constant tables and two scheduler words.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/sfe.h"
+#include "sfe_aux.cuh"
+#include "sfe_fused.cuh"
+
+using namespace sfe;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define SFE_CUDA(expr)                                                                                 \
+  do {                                                                                                 \
+    cudaError_t e_ = (expr);                                                                           \
+    if (e_ != cudaSuccess) return fail(SFE_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// FFT plan registry: n_fft -> template instance
+// ---------------------------------------------------------------------------------------------
+typedef void (*fused_fn)(const FwdParams);
+
+struct FftEntry {
+  int n_fft, M, G, R1, R2, R3, MP, C;
+  fused_fn fn;
+};
+
+template <int M, int G, int R1, int R2, int R3>
+static FftEntry make_entry() {
+  typedef FftPlan<M, G, R1, R2, R3> PL;
+  return FftEntry{2 * M, M, G, R1, R2, R3, PL::MP, PL::C, &fused_frontend_kernel<PL>};
+}
+
+static const std::vector<FftEntry>& registry() {
+  static const std::vector<FftEntry> r = {
+      make_entry<64, 16, 8, 8, 1>(),      // n_fft 128
+      make_entry<100, 16, 4, 5, 5>(),     // n_fft 200
+      make_entry<128, 16, 8, 16, 1>(),    // n_fft 256
+      make_entry<160, 16, 8, 5, 4>(),     // n_fft 320  (20 ms @ 16 kHz)
+      make_entry<200, 16, 8, 5, 5>(),     // n_fft 400  (25 ms @ 16 kHz: the ASR recipes' default)
+      make_entry<240, 16, 16, 5, 3>(),    // n_fft 480
+      make_entry<256, 16, 16, 16, 1>(),   // n_fft 512
+      make_entry<320, 32, 16, 5, 4>(),    // n_fft 640
+      make_entry<400, 32, 16, 5, 5>(),    // n_fft 800
+      make_entry<512, 32, 8, 8, 8>(),     // n_fft 1024 (TTS recipes)
+      make_entry<1024, 32, 16, 8, 8>(),   // n_fft 2048
+  };
+  return r;
+}
+
+struct sfe_plan {
+  sfe_config cfg;
+  const FftEntry* fft;
+  int device;
+  int n_sm;
+  float* d_tables;
+  unsigned int* d_sched;
+  double* d_acc;  // one fp64 scratch word for sfe_mean_all
+  FwdParams proto;  // everything that does not change per call
+  int smem_bytes;
+  int ctas_per_sm;
+  // standalone mel kernel
+  int l2m_smem;
+  int l2m_sm_warp, l2m_warp_bytes;
+};
+
+extern "C" int sfe_abi_version(void) { return SFE_ABI_VERSION; }
+extern "C" const char* sfe_last_error(void) { return g_err.c_str(); }
+
+extern "C" int sfe_supported_nfft(int32_t* out, int cap) {
+  const auto& r = registry();
+  for (int i = 0; i < static_cast<int>(r.size()) && i < cap; ++i) out[i] = r[i].n_fft;
+  return static_cast<int>(r.size());
+}
+
+static int round_up(int x, int a) { return (x + a - 1) / a * a; }
+
+extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
+  if (!cfg || !out) return fail(SFE_ERR_BAD_ARG, "sfe_plan_create: NULL argument");
+  *out = nullptr;
+  if (cfg->n_fft <= 0 || (cfg->n_fft & 1)) return fail(SFE_ERR_BAD_CONFIG, "n_fft must be positive and even");
+  if (cfg->win_length < 1 || cfg->win_length > cfg->n_fft)
+    return fail(SFE_ERR_BAD_CONFIG, "win_length must be in [1, n_fft]");
+  if (cfg->hop_length < 1) return fail(SFE_ERR_BAD_CONFIG, "hop_length must be >= 1");
+  if (!cfg->window_host) return fail(SFE_ERR_BAD_CONFIG, "window_host is NULL");
+  if (cfg->n_mels < 0 || cfg->n_mels > 32 * MAX_MEL_ROUNDS)
+    return fail(SFE_ERR_BAD_CONFIG, "n_mels must be in [0, 256]");
+  if (cfg->n_mels > 0 && !cfg->mel_weight_host) return fail(SFE_ERR_BAD_CONFIG, "mel_weight_host is NULL");
+  const FftEntry* fe = nullptr;
+  for (const auto& e : registry())
+    if (e.n_fft == cfg->n_fft) fe = &e;
+  if (!fe) {
+    std::string s = "unsupported n_fft " + std::to_string(cfg->n_fft) + "; compiled plans:";
+    for (const auto& e : registry()) s += " " + std::to_string(e.n_fft);
+    return fail(SFE_ERR_UNSUPPORTED_NFFT, s);
+  }
+
+  sfe_plan* pl = new sfe_plan();
+  memset(&pl->proto, 0, sizeof(FwdParams));
+  pl->cfg = *cfg;
+  pl->cfg.window_host = nullptr;
+  pl->cfg.mel_weight_host = nullptr;
+  pl->fft = fe;
+  const int M = fe->M, K = M + 1, D = cfg->n_mels, win = cfg->win_length;
+  const double PI = 3.14159265358979323846;
+
+  // ---- constant tables (fp64 -> fp32) ----
+  std::vector<float> tab;
+  auto align4 = [&]() { while (tab.size() % 4) tab.push_back(0.f); };
+  FwdParams& P = pl->proto;
+  // window, pre-scaled by 1/2 (the real-FFT unpack then needs no halving)
+  P.o_win = static_cast<int>(tab.size());
+  for (int i = 0; i < win; ++i) tab.push_back(0.5f * cfg->window_host[i]);
+  tab.push_back(0.f);
+  tab.push_back(0.f);
+  align4();
+  // Stockham twiddles of pass 2 and 3: tw[(r-1)*T + j] = exp(-2 pi i r (j % P) / (P R))
+  auto push_tw = [&](int R, int Pp) {
+    const int T = M / R;
+    for (int r = 1; r < R; ++r)
+      for (int j = 0; j < T; ++j) {
+        const double a = -2.0 * PI * static_cast<double>(r) * static_cast<double>(j % Pp) / (static_cast<double>(Pp) * R);
+        tab.push_back(static_cast<float>(cos(a)));
+        tab.push_back(static_cast<float>(sin(a)));
+      }
+  };
+  P.o_tw2 = static_cast<int>(tab.size());
+  push_tw(fe->R2, fe->R1);
+  align4();
+  P.o_tw3 = static_cast<int>(tab.size());
+  if (fe->R3 > 1) push_tw(fe->R3, fe->R1 * fe->R2);
+  align4();
+  // real-FFT unpack twiddles W_N^k, k = 0..M/2
+  P.o_wpost = static_cast<int>(tab.size());
+  for (int k = 0; k <= M / 2; ++k) {
+    const double a = -2.0 * PI * k / (2.0 * M);
+    tab.push_back(static_cast<float>(cos(a)));
+    tab.push_back(static_cast<float>(sin(a)));
+  }
+  align4();
+  // banded mel filter: per bin first tap + taps, lane-major weights per round of 32 bins
+  P.mel_rounds = (D + 31) / 32;
+  P.mel_tail = 0;
+  std::vector<int> mst(P.mel_rounds * 32, 0), mnt(P.mel_rounds * 32, 0);
+  for (int d = 0; d < D; ++d) {
+    const float* row = cfg->mel_weight_host + static_cast<size_t>(d) * K;
+    int first = -1, last = -1;
+    for (int k = 0; k < K; ++k)
+      if (row[k] != 0.f) {
+        if (first < 0) first = k;
+        last = k;
+      }
+    if (first >= 0) {
+      mst[d] = first;
+      mnt[d] = last - first + 1;
+    }
+    if (mnt[d] > P.mel_tail) P.mel_tail = mnt[d];
+  }
+  P.o_mstart = static_cast<int>(tab.size());
+  for (int v : mst) {
+    float f;
+    memcpy(&f, &v, 4);
+    tab.push_back(f);
+  }
+  align4();
+  P.o_mw = static_cast<int>(tab.size());
+  for (int rd = 0; rd < P.mel_rounds; ++rd) {
+    int nt = 0;
+    for (int l = 0; l < 32; ++l) nt = mnt[rd * 32 + l] > nt ? mnt[rd * 32 + l] : nt;
+    P.mel_taps[rd] = nt;
+    for (int q = 0; q < nt; ++q)
+      for (int l = 0; l < 32; ++l) {
+        const int d = rd * 32 + l;
+        float w = 0.f;
+        if (d < D && q < mnt[d]) w = cfg->mel_weight_host[static_cast<size_t>(d) * K + mst[d] + q];
+        tab.push_back(w);
+      }
+  }
+  align4();
+  P.tab_floats = static_cast<int>(tab.size());
+
+  // ---- shared-memory carve-up ----
+  const int stage_floats = round_up((TILE_F - 1) * cfg->hop_length + win + 16, 4);
+  const int z_bytes = round_up(fe->C * fe->MP * 8, 16);
+  const int p2_bytes = round_up((K + P.mel_tail + 2) * FPW * 4, 16);
+  int o = round_up(P.tab_floats * 4, 16);
+  P.sm_stage = o;
+  P.sm_stage_floats = stage_floats;
+  o += stage_floats * 4;
+  P.sm_warp = o;
+  P.sm_z_bytes = z_bytes;
+  P.sm_warp_bytes = z_bytes + p2_bytes;
+  o += NWARPS * P.sm_warp_bytes;
+  P.sm_red = round_up(o, 16);
+  o = P.sm_red + NWARPS * (D > 0 ? D : 1) * 2 * 8;
+  P.sm_bar = round_up(o, 16);
+  pl->smem_bytes = P.sm_bar + 16;
+  // standalone mel kernel: tables + per-warp P2
+  pl->l2m_sm_warp = round_up(P.tab_floats * 4, 16);
+  pl->l2m_warp_bytes = p2_bytes;
+  pl->l2m_smem = pl->l2m_sm_warp + NWARPS * p2_bytes;
+
+  // ---- static part of the launch parameters ----
+  P.n_fft = cfg->n_fft;
+  P.win = win;
+  P.hop = cfg->hop_length;
+  P.K = K;
+  P.D = D;
+  P.center = cfg->center ? 1 : 0;
+  P.off = (cfg->n_fft - win) / 2 - (cfg->center ? cfg->n_fft / 2 : 0);
+  P.has_pre = cfg->has_preemphasis ? 1 : 0;
+  P.pre = cfg->preemphasis;
+  P.mag = cfg->mag_spec ? 1 : 0;
+  P.lin_log = cfg->lin_logging ? 1 : 0;
+  P.lin_clamp = cfg->lin_clamp;
+  P.lin_div = cfg->lin_log_div;
+  P.mel_log = cfg->mel_logging ? 1 : 0;
+  P.mel_clamp = cfg->mel_clamp;
+  P.mel_div = cfg->mel_log_div;
+  P.pad_mel = cfg->mel_logging ? logf(cfg->mel_clamp) / cfg->mel_log_div : 0.f;
+  P.pad_lin = cfg->lin_logging ? logf(cfg->lin_clamp) / cfg->lin_log_div : 0.f;
+
+  // ---- device resources ----
+  cudaError_t e = cudaGetDevice(&pl->device);
+  cudaDeviceProp prop;
+  if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, pl->device);
+  if (e == cudaSuccess && pl->smem_bytes > static_cast<int>(prop.sharedMemPerBlockOptin)) {
+    delete pl;
+    return fail(SFE_ERR_BAD_CONFIG, "configuration needs more shared memory per CTA than the device offers");
+  }
+  if (e == cudaSuccess) e = cudaMalloc(&pl->d_tables, tab.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(pl->d_tables, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&pl->d_sched, 2 * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(pl->d_sched, 0, 2 * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMalloc(&pl->d_acc, sizeof(double));
+  if (e == cudaSuccess) e = cudaMemset(pl->d_acc, 0, sizeof(double));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fe->fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             pl->smem_bytes);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(reinterpret_cast<const void*>(&linear2mel_kernel),
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, pl->l2m_smem);
+  int occ = 0;
+  if (e == cudaSuccess)
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void*>(fe->fn), NTHREADS,
+                                                      pl->smem_bytes);
+  if (e != cudaSuccess) {
+    std::string msg = std::string("sfe_plan_create: ") + cudaGetErrorString(e);
+    cudaFree(pl->d_tables);
+    cudaFree(pl->d_sched);
+    cudaFree(pl->d_acc);
+    delete pl;
+    return fail(SFE_ERR_CUDA, msg);
+  }
+  pl->n_sm = prop.multiProcessorCount;
+  pl->ctas_per_sm = occ < 1 ? 1 : occ;
+  P.tables = pl->d_tables;
+  P.sched = pl->d_sched;
+  *out = pl;
+  return SFE_OK;
+}
+
+extern "C" void sfe_plan_destroy(sfe_plan* pl) {
+  if (!pl) return;
+  cudaFree(pl->d_tables);
+  cudaFree(pl->d_sched);
+  cudaFree(pl->d_acc);
+  delete pl;
+}
+
+extern "C" int64_t sfe_plan_num_frames(const sfe_plan* pl, int64_t T_max) {
+  if (!pl) return -1;
+  const int64_t T = pl->cfg.center ? T_max + 2 * (pl->cfg.n_fft / 2) : T_max;
+  if (T < pl->cfg.n_fft) return 0;
+  return 1 + (T - pl->cfg.n_fft) / pl->cfg.hop_length;
+}
+
+extern "C" int sfe_plan_query(const sfe_plan* pl, int32_t* smem_bytes, int32_t* ctas_per_sm, int32_t* n_sm) {
+  if (!pl) return fail(SFE_ERR_BAD_ARG, "sfe_plan_query: NULL plan");
+  if (smem_bytes) *smem_bytes = pl->smem_bytes;
+  if (ctas_per_sm) *ctas_per_sm = pl->ctas_per_sm;
+  if (n_sm) *n_sm = pl->n_sm;
+  return SFE_OK;
+}
+
+static int check_masks(const sfe_masks* m) {
+  if (!m) return SFE_OK;
+  if (m->n_freq < 0 || m->n_time < 0 || m->n_freq > 64 || m->n_time > 64)
+    return fail(SFE_ERR_BAD_ARG, "mask counts must be in [0, 64]");
+  if ((m->n_freq > 0 && (!m->freq_pos || !m->freq_len)) || (m->n_time > 0 && (!m->time_pos || !m->time_len)))
+    return fail(SFE_ERR_BAD_ARG, "mask descriptor pointers are NULL");
+  return SFE_OK;
+}
+
+extern "C" int sfe_frontend_forward(const sfe_plan* pl, const float* wav, int64_t wav_pitch, const int64_t* wav_len,
+                                    int32_t B, int64_t T_max, float* mel, float* lin, float* energy, int64_t* feat_len,
+                                    double* stats, const float* norm_mean, const float* norm_std,
+                                    const sfe_masks* masks, int32_t skip_pad, void* stream) {
+  if (!pl) return fail(SFE_ERR_BAD_ARG, "sfe_frontend_forward: NULL plan");
+  if (!wav || !wav_len) return fail(SFE_ERR_BAD_ARG, "sfe_frontend_forward: wav / wav_len is NULL");
+  if (B <= 0 || T_max <= 0 || wav_pitch < T_max) return fail(SFE_ERR_BAD_ARG, "sfe_frontend_forward: bad B / T_max / pitch");
+  if (reinterpret_cast<uintptr_t>(wav) & 3) return fail(SFE_ERR_BAD_ARG, "wav must be 4-byte aligned");
+  if (mel && pl->cfg.n_mels == 0) return fail(SFE_ERR_BAD_ARG, "plan has no mel stage but mel output requested");
+  if (!mel && (stats || norm_mean || norm_std || masks))
+    return fail(SFE_ERR_BAD_ARG, "stats / normalisation / masks need the mel output");
+  if (!mel && !lin && !energy) return fail(SFE_ERR_BAD_ARG, "no output requested");
+  if (pl->cfg.center && T_max <= pl->cfg.n_fft / 2)
+    return fail(SFE_ERR_BAD_ARG, "reflect padding needs T_max > n_fft/2 (torch.stft raises here too)");
+  if (int rc = check_masks(masks)) return rc;
+  const int64_t F = sfe_plan_num_frames(pl, T_max);
+  if (F <= 0) return fail(SFE_ERR_BAD_ARG, "input shorter than one frame");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  FwdParams P = pl->proto;
+  P.wav = wav;
+  P.pitch = wav_pitch;
+  P.total_floats = static_cast<long long>(B - 1) * wav_pitch + T_max;
+  P.len = reinterpret_cast<const long long*>(wav_len);
+  P.B = B;
+  P.T_max = T_max;
+  P.F = static_cast<int>(F);
+  P.tiles_per_utt = static_cast<int>((F + TILE_F - 1) / TILE_F);
+  const long long nt = static_cast<long long>(P.tiles_per_utt) * B;
+  if (nt > 0x7fffffffLL) return fail(SFE_ERR_BAD_ARG, "batch too large");
+  P.num_tiles = static_cast<int>(nt);
+  P.mel = mel;
+  P.lin = lin;
+  P.energy = energy;
+  P.feat_len = reinterpret_cast<long long*>(feat_len);
+  P.stats = stats;
+  P.norm_mean = norm_mean;
+  P.norm_std = norm_std;
+  P.skip_pad = skip_pad;
+  if (masks) {
+    P.fpos = masks->freq_pos;
+    P.flen = masks->freq_len;
+    P.n_fmask = masks->n_freq;
+    P.tpos = masks->time_pos;
+    P.tlen = masks->time_len;
+    P.n_tmask = masks->n_time;
+    P.fill = masks->fill;
+    P.fill_dev = masks->fill_dev;
+  }
+  if (stats) SFE_CUDA(cudaMemsetAsync(stats, 0, static_cast<size_t>(B) * pl->cfg.n_mels * 2 * sizeof(double), st));
+  int grid = pl->n_sm * pl->ctas_per_sm;
+  if (grid > P.num_tiles) grid = P.num_tiles;
+  pl->fft->fn<<<grid, NTHREADS, pl->smem_bytes, st>>>(P);
+  SFE_CUDA(cudaGetLastError());
+  return SFE_OK;
+}
+
+extern "C" int sfe_linear2mel_forward(const sfe_plan* pl, const float* lin, int64_t n_rows, float* mel, void* stream) {
+  if (!pl || !lin || !mel) return fail(SFE_ERR_BAD_ARG, "sfe_linear2mel_forward: NULL argument");
+  if (pl->cfg.n_mels == 0) return fail(SFE_ERR_BAD_ARG, "plan has no mel stage");
+  if (n_rows <= 0) return SFE_OK;
+  L2MParams P;
+  memset(&P, 0, sizeof(P));
+  P.lin = lin;
+  P.mel = mel;
+  P.n_rows = n_rows;
+  P.K = pl->proto.K;
+  P.D = pl->proto.D;
+  P.mel_log = pl->proto.mel_log;
+  P.mel_clamp = pl->proto.mel_clamp;
+  P.mel_div = pl->proto.mel_div;
+  P.tables = pl->d_tables;
+  P.tab_floats = pl->proto.tab_floats;
+  P.o_mstart = pl->proto.o_mstart;
+  P.o_mw = pl->proto.o_mw;
+  P.mel_rounds = pl->proto.mel_rounds;
+  P.mel_tail = pl->proto.mel_tail;
+  for (int i = 0; i < MAX_MEL_ROUNDS; ++i) P.mel_taps[i] = pl->proto.mel_taps[i];
+  P.sm_warp = pl->l2m_sm_warp;
+  P.sm_warp_bytes = pl->l2m_warp_bytes;
+  long long pairs = (n_rows + FPW - 1) / FPW;
+  long long want = (pairs + NWARPS - 1) / NWARPS;
+  int grid = static_cast<int>(want < pl->n_sm * 4LL ? want : pl->n_sm * 4LL);
+  linear2mel_kernel<<<grid, NTHREADS, pl->l2m_smem, static_cast<cudaStream_t>(stream)>>>(P);
+  SFE_CUDA(cudaGetLastError());
+  return SFE_OK;
+}
+
+extern "C" int sfe_stats_accumulate(const float* feat, const int64_t* feat_len, int32_t B, int64_t F, int32_t D,
+                                    double* stats, void* stream) {
+  if (!feat || !feat_len || !stats) return fail(SFE_ERR_BAD_ARG, "sfe_stats_accumulate: NULL argument");
+  if (B <= 0 || F <= 0 || D <= 0) return fail(SFE_ERR_BAD_ARG, "sfe_stats_accumulate: bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SFE_CUDA(cudaMemsetAsync(stats, 0, static_cast<size_t>(B) * D * 2 * sizeof(double), st));
+  dim3 grid(static_cast<unsigned>((F + STATS_FR - 1) / STATS_FR), static_cast<unsigned>(B));
+  if (D <= 256) {
+    const int rows = 256 / D > 0 ? 256 / D : 1;
+    stats_accumulate_kernel<<<grid, 256, rows * D * 2 * sizeof(double), st>>>(
+        feat, reinterpret_cast<const long long*>(feat_len), F, D, stats);
+  } else {
+    stats_accumulate_wide_kernel<<<grid, 256, 0, st>>>(feat, reinterpret_cast<const long long*>(feat_len), F, D, stats);
+  }
+  SFE_CUDA(cudaGetLastError());
+  return SFE_OK;
+}
+
+extern "C" int sfe_stats_finalize(const double* stats, const int64_t* feat_len, int32_t B, int32_t D, float clamp,
+                                  float* mean, float* std, float* packed, void* stream) {
+  if (!stats || !feat_len) return fail(SFE_ERR_BAD_ARG, "sfe_stats_finalize: NULL argument");
+  if (B <= 0 || D <= 0) return fail(SFE_ERR_BAD_ARG, "sfe_stats_finalize: bad shape");
+  stats_finalize_kernel<<<(D + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      stats, reinterpret_cast<const long long*>(feat_len), B, D, clamp, mean, std, packed);
+  SFE_CUDA(cudaGetLastError());
+  return SFE_OK;
+}
+
+extern "C" int sfe_running_update(const float* packed, int32_t D, float weight, int32_t first, int32_t update,
+                                  float* run_mean, float* run_std, float* batch_mean_out, float* batch_std_out,
+                                  void* stream) {
+  if (!packed || D <= 0) return fail(SFE_ERR_BAD_ARG, "sfe_running_update: bad argument");
+  running_update_kernel<<<(D + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      packed, D, weight, first, update, run_mean, run_std, batch_mean_out, batch_std_out);
+  SFE_CUDA(cudaGetLastError());
+  return SFE_OK;
+}
+
+extern "C" int sfe_normalize(const float* src, float* dst, const int64_t* feat_len, int32_t B, int64_t F, int32_t D,
+                             const double* stats, float clamp, int32_t use_mean, int32_t use_std, const float* mean,
+                             const float* std, int32_t per_utt, float* mean_out, float* std_out, int32_t src_has_pad,
+                             float pad_value, const sfe_warp* warp, const sfe_masks* masks, void* stream) {
+  if (!src || !dst || !feat_len) return fail(SFE_ERR_BAD_ARG, "sfe_normalize: NULL argument");
+  if (B <= 0 || F <= 0 || D <= 0 || D > 4096) return fail(SFE_ERR_BAD_ARG, "sfe_normalize: bad shape");
+  if (int rc = check_masks(masks)) return rc;
+  const bool warp_on = warp && warp->enabled;
+  if (warp_on) {
+    if (src == dst) return fail(SFE_ERR_BAD_ARG, "sfe_normalize: the time warp cannot run in place");
+    if (!(warp->center > 0 && warp->center < warp->minlen && warp->pos > 0 && warp->pos < warp->minlen &&
+          warp->minlen <= F))
+      return fail(SFE_ERR_BAD_ARG, "sfe_normalize: inconsistent warp descriptor");
+  }
+  NormParams P;
+  memset(&P, 0, sizeof(P));
+  P.src = src;
+  P.dst = dst;
+  P.flen = reinterpret_cast<const long long*>(feat_len);
+  P.B = B;
+  P.F = F;
+  P.D = D;
+  P.stats = stats;
+  P.clamp = clamp;
+  P.use_mean = use_mean;
+  P.use_std = use_std;
+  P.mean = mean;
+  P.sd = std;
+  P.per_utt = per_utt;
+  P.mean_out = mean_out;
+  P.std_out = std_out;
+  P.src_has_pad = src_has_pad;
+  P.pad_value = pad_value;
+  if (warp_on) {
+    P.warp_on = 1;
+    P.warp_center = warp->center;
+    P.warp_pos = warp->pos;
+    P.warp_minlen = warp->minlen;
+  }
+  if (masks) {
+    P.fpos = masks->freq_pos;
+    P.flen_m = masks->freq_len;
+    P.n_fmask = masks->n_freq;
+    P.tpos = masks->time_pos;
+    P.tlen = masks->time_len;
+    P.n_tmask = masks->n_time;
+    P.fill = masks->fill;
+    P.fill_dev = masks->fill_dev;
+  }
+  // ~32 KB of features per CTA
+  int fpc = 8192 / D;
+  if (fpc < 1) fpc = 1;
+  if (fpc > 128) fpc = 128;
+  P.frames_per_cta = fpc;
+  dim3 grid(static_cast<unsigned>((F + fpc - 1) / fpc), static_cast<unsigned>(B));
+  normalize_kernel<<<grid, 256, 3 * D * sizeof(float), static_cast<cudaStream_t>(stream)>>>(P);
+  SFE_CUDA(cudaGetLastError());
+  return SFE_OK;
+}
+
+extern "C" int sfe_delta(const float* feat, int32_t B, int64_t F, int32_t D, int32_t order, int32_t N, float* out,
+                         void* stream) {
+  if (!feat || !out) return fail(SFE_ERR_BAD_ARG, "sfe_delta: NULL argument");
+  if (B <= 0 || F <= 0 || D <= 0 || (order != 1 && order != 2) || N < 1) return fail(SFE_ERR_BAD_ARG, "sfe_delta: bad argument");
+  int denom = 0;
+  for (int i = 1; i <= N; ++i) denom += i * i;
+  const long long total = static_cast<long long>(B) * F * D;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  delta_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      feat, B, F, D, order, N, static_cast<float>(2 * denom), out);
+  SFE_CUDA(cudaGetLastError());
+  return SFE_OK;
+}
+
+// scratch accumulator for sfe_mean_all lives with the library (one word per device context)
+extern "C" int sfe_mean_all(const float* x, int64_t n, float* out, void* stream) {
+  if (!x || !out || n <= 0) return fail(SFE_ERR_BAD_ARG, "sfe_mean_all: bad argument");
+  static thread_local double* acc = nullptr;
+  static thread_local int acc_dev = -1;
+  int dev = 0;
+  SFE_CUDA(cudaGetDevice(&dev));
+  if (!acc || acc_dev != dev) {
+    SFE_CUDA(cudaMalloc(&acc, sizeof(double)));
+    SFE_CUDA(cudaMemset(acc, 0, sizeof(double)));
+    acc_dev = dev;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  long long blocks = (n + 256 * 8 - 1) / (256 * 8);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  sum_all_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, n, acc);
+  mean_finish_kernel<<<1, 1, 0, st>>>(acc, n, out);
+  SFE_CUDA(cudaGetLastError());
+  return SFE_OK;
+}

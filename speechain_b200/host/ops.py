@@ -1,0 +1,274 @@
+"""Torch-tensor facade over the C ABI (speechain_b200/_lib.py).
+
+PyTorch is plumbing here: it owns device memory and streams, this file turns tensors into raw
+pointers and calls libsfe on the current CUDA stream.  No arithmetic on the hot path happens in
+torch ops, and nothing here falls back to torch when the library is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{name} must live on a CUDA device: the speechain_b200 frontend has no CPU path "
+            f"(got device={t.device}).")
+
+
+class HostLengths:
+    """Remembers the host copy of a device length tensor so that the next module in the chain
+    (normalise, SpecAugment) does not pay a device->host sync to learn min/max lengths.
+
+    Entries are keyed by tensor identity + version; a tensor that was modified in place or is
+    simply unknown falls back to one ``.cpu()`` copy."""
+
+    _cache: Dict[int, tuple] = {}
+
+    @classmethod
+    def remember(cls, dev: torch.Tensor, host: torch.Tensor):
+        if len(cls._cache) > 64:
+            cls._cache.clear()
+        cls._cache[id(dev)] = (dev._version, dev.data_ptr(), host)
+
+    @classmethod
+    def get(cls, t: torch.Tensor) -> torch.Tensor:
+        if not t.is_cuda:
+            return t
+        hit = cls._cache.get(id(t))
+        if hit is not None and hit[0] == t._version and hit[1] == t.data_ptr():
+            return hit[2]
+        host = t.cpu()
+        cls.remember(t, host)
+        return host
+
+
+class DeviceMasks:
+    """SpecAugment interval descriptors on the device: one pinned staging buffer, one async copy."""
+
+    def __init__(self, device, freq_pos=None, freq_len=None, time_pos=None, time_len=None, fill: float = 0.0,
+                 fill_dev: Optional[torch.Tensor] = None):
+        parts, self.n_freq, self.n_time = [], 0, 0
+        if freq_pos is not None:
+            self.n_freq = int(freq_pos.shape[1])
+            parts += [np.ascontiguousarray(freq_pos, dtype=np.int32).ravel(),
+                      np.ascontiguousarray(freq_len, dtype=np.int32).ravel()]
+        if time_pos is not None:
+            self.n_time = int(time_pos.shape[1])
+            parts += [np.ascontiguousarray(time_pos, dtype=np.int32).ravel(),
+                      np.ascontiguousarray(time_len, dtype=np.int32).ravel()]
+        self.fill = float(fill)
+        self.fill_dev = fill_dev
+        self.buf = None
+        if parts:
+            flat = torch.from_numpy(np.concatenate(parts))
+            self.buf = flat.pin_memory().to(device, non_blocking=True)
+        self._sizes = [p.size for p in parts]
+
+    def struct(self) -> _lib.SfeMasks:
+        m = _lib.SfeMasks()
+        base = self.buf.data_ptr() if self.buf is not None else 0
+        off = 0
+        if self.n_freq:
+            m.freq_pos, m.freq_len = base + off, base + off + 4 * self._sizes[0]
+            off += 8 * self._sizes[0]
+        m.n_freq = self.n_freq
+        if self.n_time:
+            m.time_pos, m.time_len = base + off, base + off + 4 * self._sizes[-1]
+        m.n_time = self.n_time
+        m.fill = self.fill
+        m.fill_dev = self.fill_dev.data_ptr() if self.fill_dev is not None else None
+        return m
+
+
+class FrontendPlan:
+    """Owns one ``sfe_plan`` (constant tables on one device)."""
+
+    def __init__(self, *, n_fft: int, win_length: int, hop_length: int, center: bool = True,
+                 preemphasis: Optional[float] = None, mag_spec: bool = False, lin_logging: bool = False,
+                 lin_clamp: float = 1e-10, lin_log_base: Optional[float] = None, n_mels: int = 0,
+                 mel_logging: bool = True, mel_clamp: float = 1e-10, mel_log_base: Optional[float] = 10.0,
+                 window: torch.Tensor = None, mel_weight: Optional[torch.Tensor] = None, device=None):
+        lib = _lib.load()
+        self.device = torch.device(device if device is not None else "cuda")
+        cfg = _lib.SfeConfig()
+        cfg.n_fft, cfg.win_length, cfg.hop_length, cfg.center = int(n_fft), int(win_length), int(hop_length), int(center)
+        cfg.has_preemphasis = int(preemphasis is not None)
+        cfg.preemphasis = float(preemphasis or 0.0)
+        cfg.mag_spec = int(mag_spec)
+        cfg.lin_logging, cfg.lin_clamp = int(lin_logging), float(lin_clamp)
+        cfg.lin_log_div = float(math.log(lin_log_base)) if lin_log_base is not None else 1.0
+        cfg.n_mels, cfg.mel_logging, cfg.mel_clamp = int(n_mels), int(mel_logging), float(mel_clamp)
+        cfg.mel_log_div = float(math.log(mel_log_base)) if mel_log_base is not None else 1.0
+        win = window.detach().to("cpu", torch.float32).contiguous()
+        if win.numel() != win_length:
+            raise ValueError(f"window has {win.numel()} taps, expected win_length={win_length}")
+        cfg.window_host = win.data_ptr()
+        mw = None
+        if n_mels:
+            mw = mel_weight.detach().to("cpu", torch.float32).contiguous()
+            if tuple(mw.shape) != (n_mels, n_fft // 2 + 1):
+                raise ValueError(f"mel_weight has shape {tuple(mw.shape)}, expected {(n_mels, n_fft // 2 + 1)}")
+            cfg.mel_weight_host = mw.data_ptr()
+        self.n_fft, self.win_length, self.hop_length, self.center = int(n_fft), int(win_length), int(hop_length), bool(center)
+        self.n_mels, self.n_bins = int(n_mels), n_fft // 2 + 1
+        self.pad_mel = (np.log(np.float32(mel_clamp)) / np.float32(cfg.mel_log_div)).astype(np.float32).item() \
+            if mel_logging else 0.0
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.sfe_plan_create(C.byref(cfg), C.byref(handle)))
+        self._h = handle
+        self._lib = lib
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self._lib.sfe_plan_destroy(h)
+            except Exception:
+                pass
+
+    def num_frames(self, T_max: int) -> int:
+        return int(self._lib.sfe_plan_num_frames(self._h, int(T_max)))
+
+    def query(self):
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        _lib.check(self._lib.sfe_plan_query(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(smem_bytes=a.value, ctas_per_sm=b.value, n_sm=c.value)
+
+    def forward(self, wav: torch.Tensor, wav_len: torch.Tensor, *, want_mel=True, want_lin=False, want_energy=False,
+                want_stats=False, norm_mean=None, norm_std=None, masks: Optional[DeviceMasks] = None,
+                skip_pad=False, out_mel=None, out_stats=None):
+        """wav (B, T) fp32 CUDA (any row pitch), wav_len (B,) int64 CUDA."""
+        _need_cuda(wav, "speech")
+        B, T = wav.shape
+        if wav.dtype != torch.float32:
+            raise TypeError(f"speech must be float32, got {wav.dtype}")
+        if wav.stride(1) != 1:
+            wav = wav.contiguous()
+        F = self.num_frames(T)
+        dev = wav.device
+        out = {}
+        mel = lin = energy = stats = None
+        if want_mel:
+            mel = out_mel if out_mel is not None else torch.empty((B, F, self.n_mels), dtype=torch.float32, device=dev)
+        if want_lin:
+            lin = torch.empty((B, F, self.n_bins), dtype=torch.float32, device=dev)
+        if want_energy:
+            energy = torch.empty((B, F), dtype=torch.float32, device=dev)
+        if want_stats:
+            stats = out_stats if out_stats is not None else torch.empty((B, self.n_mels, 2), dtype=torch.float64, device=dev)
+        feat_len = torch.empty((B,), dtype=torch.int64, device=dev)
+        ms = masks.struct() if masks is not None else None
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.sfe_frontend_forward(
+                self._h, _ptr(wav), int(wav.stride(0)), _ptr(wav_len), B, T, _ptr(mel), _ptr(lin), _ptr(energy),
+                _ptr(feat_len), _ptr(stats), _ptr(norm_mean), _ptr(norm_std),
+                C.byref(ms) if ms is not None else None, int(skip_pad), _stream()))
+        out.update(mel=mel, lin=lin, energy=energy, stats=stats, feat_len=feat_len)
+        return out
+
+    def linear2mel(self, lin: torch.Tensor) -> torch.Tensor:
+        _need_cuda(lin, "feat")
+        lin = lin.contiguous()
+        rows = lin.numel() // self.n_bins
+        mel = torch.empty(lin.shape[:-1] + (self.n_mels,), dtype=torch.float32, device=lin.device)
+        with torch.cuda.device(lin.device):
+            _lib.check(self._lib.sfe_linear2mel_forward(self._h, _ptr(lin), rows, _ptr(mel), _stream()))
+        return mel
+
+
+# ----------------------------------------------------------------------------------------------
+# plan-free entry points
+# ----------------------------------------------------------------------------------------------
+
+def stats_accumulate(feat: torch.Tensor, feat_len: torch.Tensor) -> torch.Tensor:
+    _need_cuda(feat, "feat")
+    B, F, D = feat.shape
+    stats = torch.empty((B, D, 2), dtype=torch.float64, device=feat.device)
+    with torch.cuda.device(feat.device):
+        _lib.check(_lib.load().sfe_stats_accumulate(_ptr(feat), _ptr(feat_len), B, F, D, _ptr(stats), _stream()))
+    return stats
+
+
+def stats_finalize(stats: torch.Tensor, feat_len: torch.Tensor, clamp: float, want_packed: bool):
+    B, D, _ = stats.shape
+    dev = stats.device
+    mean = torch.empty((B, D), dtype=torch.float32, device=dev)
+    std = torch.empty((B, D), dtype=torch.float32, device=dev)
+    packed = torch.empty((2 * D + 1,), dtype=torch.float32, device=dev) if want_packed else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().sfe_stats_finalize(_ptr(stats), _ptr(feat_len), B, D, float(clamp), _ptr(mean), _ptr(std),
+                                                  _ptr(packed), _stream()))
+    return mean, std, packed
+
+
+def running_update(packed: torch.Tensor, D: int, weight: float, first: bool, update: bool, run_mean, run_std,
+                   want_batch: bool = False):
+    dev = packed.device
+    bm = torch.empty((D,), dtype=torch.float32, device=dev) if want_batch else None
+    bs = torch.empty((D,), dtype=torch.float32, device=dev) if want_batch else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().sfe_running_update(_ptr(packed), D, float(weight), int(first), int(update), _ptr(run_mean),
+                                                  _ptr(run_std), _ptr(bm), _ptr(bs), _stream()))
+    return bm, bs
+
+
+def normalize(src: torch.Tensor, feat_len: torch.Tensor, *, dst: Optional[torch.Tensor] = None, stats=None,
+              clamp: float = 1e-10, use_mean=True, use_std=True, mean=None, std=None, per_utt=False,
+              want_utt_stats=False, src_has_pad=True, pad_value=0.0, warp=None, masks: Optional[DeviceMasks] = None):
+    """(x-mean)/std [+ warp] [+ masks]; in place unless ``dst`` is given or a warp is requested."""
+    _need_cuda(src, "feat")
+    B, F, D = src.shape
+    if warp is not None and dst is None:
+        dst = torch.empty_like(src)
+    if dst is None:
+        dst = src
+    mo = so = None
+    if want_utt_stats and stats is not None:
+        mo = torch.empty((B, D), dtype=torch.float32, device=src.device)
+        so = torch.empty((B, D), dtype=torch.float32, device=src.device)
+    w = None
+    if warp is not None:
+        w = _lib.SfeWarp(1, int(warp[0]), int(warp[1]), int(warp[2]))
+    ms = masks.struct() if masks is not None else None
+    with torch.cuda.device(src.device):
+        _lib.check(_lib.load().sfe_normalize(
+            _ptr(src), _ptr(dst), _ptr(feat_len), B, F, D, _ptr(stats), float(clamp), int(use_mean), int(use_std),
+            _ptr(mean), _ptr(std), int(per_utt), _ptr(mo), _ptr(so), int(src_has_pad), float(pad_value),
+            C.byref(w) if w is not None else None, C.byref(ms) if ms is not None else None, _stream()))
+    return dst, mo, so
+
+
+def delta(feat: torch.Tensor, order: int, N: int) -> torch.Tensor:
+    _need_cuda(feat, "feat")
+    feat = feat.contiguous()
+    B, F, D = feat.shape
+    out = torch.empty((B, F, D * (order + 1)), dtype=torch.float32, device=feat.device)
+    with torch.cuda.device(feat.device):
+        _lib.check(_lib.load().sfe_delta(_ptr(feat), B, F, D, int(order), int(N), _ptr(out), _stream()))
+    return out
+
+
+def mean_all(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x, "feat")
+    x = x.contiguous()
+    out = torch.empty((1,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().sfe_mean_all(_ptr(x), x.numel(), _ptr(out), _stream()))
+    return out

@@ -1,0 +1,127 @@
+"""Batch-level SpecAugment.  API mirror of speechain/module/augment/specaug.py (`SpecAugment`).
+
+The random draws are made on the HOST with the reference's exact ``torch.randint`` call sequence
+on torch's CPU generator (specaug.py:98-108,145-158,178-191), so masks are bit-identical to the
+reference CPU path under the same ``torch.manual_seed``; only interval descriptors (a few hundred
+bytes) go to the device, where one kernel applies the time warp (4-tap cubic gather) and the
+masks in a single read + write."""
+from typing import List, Optional, Union
+
+import numpy as np
+import torch
+
+from ...host import ops
+from ...host.ops import DeviceMasks, HostLengths
+from ..abs import Module
+
+
+class SpecAugment(Module):
+    def module_init(self, time_warp: bool = True, time_warp_window: int = 5, time_warp_mode: str = "bicubic",
+                    freq_mask: bool = True, freq_mask_width: Union[int, List[int]] = 30, freq_mask_num: int = 2,
+                    time_mask: bool = True, time_mask_width: Union[int, float, List] = 0.05, time_mask_num: int = 2,
+                    time_mask_ratio: float = 1.0, feat_norm: bool = True):
+        assert time_warp or freq_mask or time_mask, "You must specify at least one type of augmentation in SpecAugment!"
+        self.feat_dim = None
+        if self.input_size is not None:
+            self.feat_dim = self.input_size
+            self.output_size = self.input_size
+        self.time_warp = time_warp
+        self.time_warp_window = time_warp_window
+        self.time_warp_mode = time_warp_mode
+        if time_warp and time_warp_mode != "bicubic":
+            raise NotImplementedError("only time_warp_mode='bicubic' (the reference default) is implemented")
+        self.freq_mask = freq_mask
+        if isinstance(freq_mask_width, int):
+            freq_mask_width = [0, freq_mask_width]
+        elif not isinstance(freq_mask_width, (list, tuple)):
+            raise ValueError
+        if self.feat_dim is not None:
+            assert freq_mask_width[1] < self.feat_dim, (
+                "The number of maximum frequency masking bins cannot be larger than the feature dimension! "
+                f"freq_mask_width[1]={freq_mask_width[1]} and self.feat_dim={self.feat_dim}.")
+        self.freq_mask_width = list(freq_mask_width)
+        self.freq_mask_num = freq_mask_num
+        self.time_mask = time_mask
+        if isinstance(time_mask_width, (int, float)):
+            time_mask_width = [0, time_mask_width]
+        elif not isinstance(time_mask_width, (list, tuple)):
+            raise ValueError
+        self.time_mask_width = list(time_mask_width)
+        self.time_mask_num = time_mask_num
+        self.feat_norm = feat_norm
+
+    # ------------------------------------------------------------------------------------
+    def draw(self, batch_size: int, feat_dim: int, time_minlen: int, generator: Optional[torch.Generator] = None):
+        """The reference's draw sequence on the CPU generator.  Returns
+        (warp or None, freq_pos, freq_len, time_pos, time_len) with numpy int64 arrays / None."""
+        kw = {} if generator is None else {"generator": generator}
+        warp = None
+        if self.time_warp and time_minlen > 2 * self.time_warp_window + 1:
+            w = self.time_warp_window
+            center = torch.randint(low=w + 1, high=time_minlen - w, size=(1,), **kw)[0].item()
+            pos = torch.randint(low=center - w, high=center + w, size=(1,), **kw)[0].item()
+            warp = (center, pos, time_minlen)
+        fpos = flen = tpos = tlen = None
+        if self.freq_mask:
+            if self.feat_dim is None:
+                # latent bug of specaug.py:135-141, kept as the same error: feat_dim is never set lazily
+                assert self.feat_dim == feat_dim and self.freq_mask_width[1] < feat_dim, (
+                    "The number of maximum frequency masking bins cannot be larger than the feature dimension! "
+                    f"self.freq_mask_width[1]={self.freq_mask_width[1]} and feat_dim={feat_dim}.")
+            flen = torch.randint(self.freq_mask_width[0], self.freq_mask_width[1] + 1,
+                                 size=(batch_size, self.freq_mask_num), **kw)
+            fpos = torch.randint(0, max(1, feat_dim - flen.max().item()), size=(batch_size, self.freq_mask_num), **kw)
+            fpos, flen = fpos.numpy(), flen.numpy()
+        if self.time_mask:
+            lo, hi = self.time_mask_width
+            if isinstance(lo, float):
+                lo = int(lo * time_minlen)
+            if isinstance(hi, float):
+                hi = int(hi * time_minlen)
+            hi = min(hi, time_minlen)
+            tlen = torch.randint(lo, hi + 1, size=(batch_size, self.time_mask_num), **kw)
+            tpos = torch.randint(0, max(1, time_minlen - tlen.max().item()), size=(batch_size, self.time_mask_num), **kw)
+            tpos, tlen = tpos.numpy(), tlen.numpy()
+        return warp, fpos, flen, tpos, tlen
+
+    def draw_device(self, batch_size, feat_dim, feat_len_host, device, generator=None):
+        """Draw and upload: returns (warp, DeviceMasks or None)."""
+        minlen = int(feat_len_host.min().item())
+        warp, fpos, flen, tpos, tlen = self.draw(batch_size, feat_dim, minlen, generator)
+        masks = None
+        if fpos is not None or tpos is not None:
+            masks = DeviceMasks(device, fpos, flen, tpos, tlen, fill=0.0)
+        return warp, masks
+
+    def forward(self, feat: torch.Tensor, feat_len: torch.Tensor):
+        """feat (batch, F, D) fp32 CUDA, feat_len (batch,).  Returns (augmented feat, feat_len);
+        the input tensor is not modified (the reference writes the warp in place, specaug.py:123-124)."""
+        if not feat.is_cuda:
+            raise RuntimeError("speechain_b200 SpecAugment: `feat` must be a CUDA tensor — there is no CPU path.")
+        if feat.dtype != torch.float32 or not feat.is_contiguous():
+            feat = feat.float().contiguous()
+        B, _, D = feat.shape
+        len_host = HostLengths.get(feat_len)
+        if not feat_len.is_cuda:
+            feat_len = feat_len.to(feat.device, non_blocking=True)
+        warp, masks = self.draw_device(B, D, len_host, feat.device)
+        if masks is None and warp is None:
+            return feat, feat_len
+        if masks is not None and not self.feat_norm:
+            # fill = mean of the (warped) features (specaug.py:203): warp first, then reduce, then mask
+            if warp is not None:
+                feat, _, _ = ops.normalize(feat, feat_len, warp=warp)
+                warp = None
+            masks.fill_dev = ops.mean_all(feat)
+        out, _, _ = ops.normalize(feat, feat_len, dst=torch.empty_like(feat), warp=warp, masks=masks)
+        return out, feat_len
+
+    def extra_repr(self) -> str:
+        out = ""
+        if self.time_warp:
+            out += f"time_warp_window={self.time_warp_window}, time_warp_mode={self.time_warp_mode}, "
+        if self.freq_mask:
+            out += f"\nfreq_mask_width={self.freq_mask_width}, freq_mask_num={self.freq_mask_num}, "
+        if self.time_mask:
+            out += f"\ntime_mask_width={self.time_mask_width}, time_mask_num={self.time_mask_num}"
+        return out

@@ -1,0 +1,131 @@
+"""Speech -> linear spectrogram.  API mirror of speechain/module/frontend/speech2linear.py
+(`Speech2LinearSpec`); the arithmetic is the fused sm_100a kernel behind ``sfe_frontend_forward``."""
+from typing import Optional
+
+import torch
+
+from ...host.ops import FrontendPlan, HostLengths
+from ..abs import Module
+from ._common import ConstHolder, as_float, lengths_pair, make_window, squeeze_speech, to_samples
+
+
+class Speech2LinearSpec(Module):
+    """Waveform -> linear (energy or magnitude) spectrogram, optionally log-compressed.
+
+    Same constructor keys and defaults as the reference (speech2linear.py:20-37).  Differences,
+    all deliberate (SURVEY.md §8b "Ownership"): the caller's ``speech_len`` is not modified in
+    place (speech2linear.py:202 does), the input waveform is never written to, and a 2-D
+    ``(batch, time)`` input also works with pre-emphasis.
+    """
+
+    def module_init(self, hop_length, win_length, sr: int = 16000, n_fft: int = None, preemphasis: float = None,
+                    pre_stft_norm: str = None, window: str = "hann", center: bool = True, normalized: bool = False,
+                    onesided: bool = True, mag_spec: bool = False, return_energy: bool = False, clamp: float = 1e-10,
+                    logging: bool = False, log_base: float = None):
+        hop_length = to_samples(hop_length, sr)
+        win_length = to_samples(win_length, sr)
+        if n_fft is None:
+            n_fft = win_length  # speech2linear.py:93-94
+        if not onesided:
+            raise NotImplementedError("onesided=False is not supported by the B200 frontend (no recipe uses it; "
+                                      "LinearSpec2MelSpec needs n_fft//2+1 bins anyway).")
+        if pre_stft_norm not in (None, "mean_std", "min_max"):
+            raise ValueError(f"pre_stft_norm must be None, 'mean_std' or 'min_max', got {pre_stft_norm!r}")
+        self.output_size = n_fft // 2 + 1
+        self.win_length, self.hop_length, self.n_fft, self.sr = win_length, hop_length, n_fft, sr
+        self.preemphasis = as_float(preemphasis, "preemphasis")
+        if self.preemphasis is not None:
+            self.preemph_filter = ConstHolder(torch.tensor([-self.preemphasis, 1.0]).reshape(1, 1, 2))
+        self.pre_stft_norm = pre_stft_norm
+        self.stft_config = dict(n_fft=n_fft, hop_length=hop_length, win_length=win_length, window=window,
+                                center=center, normalized=normalized, onesided=onesided, return_complex=True)
+        self.mag_spec = mag_spec
+        self.return_energy = return_energy
+        self.clamp = as_float(clamp, "clamp")
+        self.logging = logging
+        self.log_base = as_float(log_base, "log_base")
+        self._plans = {}
+
+    # ------------------------------------------------------------------------------------
+    def _plan(self, device, preemph: bool = True, mel: Optional[dict] = None) -> FrontendPlan:
+        key = (str(device), preemph, None if mel is None else id(mel["weight"]))
+        plan = self._plans.get(key)
+        if plan is None:
+            c = self.stft_config
+            win = make_window(c["window"], self.win_length, self.n_fft, c["normalized"])
+            kw = dict(n_fft=self.n_fft, win_length=self.win_length, hop_length=self.hop_length, center=c["center"],
+                      preemphasis=self.preemphasis if preemph else None, mag_spec=self.mag_spec,
+                      lin_logging=self.logging, lin_clamp=self.clamp, lin_log_base=self.log_base, window=win,
+                      device=device)
+            if mel is not None:
+                kw.update(n_mels=mel["n_mels"], mel_logging=mel["logging"], mel_clamp=mel["clamp"],
+                          mel_log_base=mel["log_base"], mel_weight=mel["weight"])
+            plan = FrontendPlan(**kw)
+            self._plans[key] = plan
+        return plan
+
+    def _prepare(self, speech: torch.Tensor, speech_len: torch.Tensor):
+        """Shared by Speech2LinearSpec and Speech2MelSpec: shape checks, optional waveform
+        pre-normalisation, device lengths.  Returns (wav (B,T), len_dev, len_host, preemph_in_kernel)."""
+        wav = squeeze_speech(speech)
+        if not wav.is_cuda:
+            raise RuntimeError("speechain_b200 frontend: `speech` must be a CUDA tensor — there is no CPU path.")
+        len_dev, len_host = lengths_pair(speech_len, wav.device)
+        in_kernel = True
+        if self.pre_stft_norm is not None:
+            # Rare path (no shipped recipe sets it): the statistics need the pre-emphasised signal
+            # including padding (speech2linear.py:177-187), so this one is done with tensor ops.
+            in_kernel = False
+            if self.preemphasis is not None:
+                y = wav.clone()
+                y[:, 1:] -= self.preemphasis * wav[:, :-1]
+                idx = torch.arange(wav.size(1), device=wav.device)[None, :]
+                wav = y.masked_fill(idx >= len_dev[:, None], 0.0)
+            if self.pre_stft_norm == "mean_std":
+                if wav.size(0) != 1:
+                    raise RuntimeError("pre_stft_norm='mean_std' only broadcasts for batch size 1 "
+                                       "(speech2linear.py:179 has no keepdim)")
+                wav = (wav - wav.mean(dim=1, keepdim=True)) / wav.std(dim=1, keepdim=True)
+            else:
+                lo, hi = wav.amin(dim=1, keepdim=True), wav.amax(dim=1, keepdim=True)
+                wav = (wav - lo) / (hi - lo) * 2 - 1
+        return wav, len_dev, len_host, in_kernel
+
+    def _feat_len_host(self, len_host: torch.Tensor) -> torch.Tensor:
+        n = len_host + 2 * (self.n_fft // 2) if self.stft_config["center"] else len_host
+        return torch.div(n - self.n_fft, self.hop_length, rounding_mode="floor") + 1
+
+    def __getstate__(self):
+        # compiled plans hold raw library handles: never pickle / deepcopy them
+        d = self.__dict__.copy()
+        d["_plans"] = {}
+        return d
+
+    def forward(self, speech: torch.Tensor, speech_len: torch.Tensor):
+        """speech (batch, T, 1) or (batch, T) fp32 CUDA; speech_len (batch,) int64.
+        Returns (linear_spec (batch, F, n_fft//2+1), feat_len) or, with ``return_energy``,
+        (linear_spec, feat_len, energy (batch, F), energy_len)."""
+        wav, len_dev, len_host, in_kernel = self._prepare(speech, speech_len)
+        plan = self._plan(wav.device, preemph=in_kernel)
+        out = plan.forward(wav, len_dev, want_mel=False, want_lin=True, want_energy=self.return_energy)
+        feat_len = out["feat_len"]
+        HostLengths.remember(feat_len, self._feat_len_host(len_host))
+        if self.return_energy:
+            return out["lin"], feat_len, out["energy"], feat_len
+        return out["lin"], feat_len
+
+    def recover(self, feat: torch.Tensor, feat_len: torch.Tensor, inv_preemph_winlen: int = 100):
+        raise NotImplementedError("Griffin-Lim recovery (speech2linear.py:252-351) is a later row of the scope table "
+                                  "(SURVEY.md §8 f4); it is not part of the accelerated forward path.")
+
+    def get_sample_rate(self):
+        return self.sr
+
+    def __repr__(self) -> str:
+        s = (f"{self.__class__.__name__}(\n"
+             f"win_length={self.win_length}, hop_length={self.hop_length}, n_fft={self.n_fft}, mag_spec={self.mag_spec}, ")
+        if self.preemphasis is not None:
+            s += f"preemphasis={self.preemphasis}, "
+        if self.pre_stft_norm is not None:
+            s += f"pre_stft_norm={self.pre_stft_norm}, "
+        return s + "\n)"

@@ -1,0 +1,286 @@
+"""Feature normalisation.  API mirror of speechain/module/norm/feat_norm.py
+(`FeatureNormalization`): per-utterance statistics come from fp64 sums accumulated on the GPU
+(by the fused frontend kernel when it produced ``feat``, else by one streaming pass), the
+normalisation is one read + one write, and the DDP exchange is ONE all-reduce of a packed
+(2·D+1)-float buffer instead of the reference's three all_gathers (feat_norm.py:146-266)."""
+from typing import Dict, Optional
+
+import torch
+
+from ...host import ops
+from ...host.ops import DeviceMasks, HostLengths
+from ..abs import Module
+
+
+class FeatureNormalization(Module):
+    """Same constructor keys, defaults and lazily registered buffers as the reference
+    (feat_norm.py:44-51, 455-531): ``global_mean/global_std/global_batch``, ``{gid}_mean/…``,
+    ``aver_mean/aver_std``."""
+
+    def module_init(self, norm_type: str = "global", mean_norm: bool = True, std_norm: bool = True,
+                    clamp: float = 1e-10, max_epoch_num: int = 4):
+        self.norm_type = norm_type
+        self.mean_norm = mean_norm
+        self.std_norm = std_norm
+        self.clamp = float(clamp)
+        self.max_epoch_num = max_epoch_num
+        if self.input_size is not None:
+            self.output_size = self.input_size
+        self._batch_host: Dict[str, int] = {}  # host mirror of the {prefix}_batch counters (no sync per step)
+
+    # ------------------------------------------------------------------------------------
+    # statistics
+    # ------------------------------------------------------------------------------------
+    @staticmethod
+    def _sums(feat: torch.Tensor, feat_len: torch.Tensor) -> torch.Tensor:
+        """(B, D, 2) fp64 [sum, sum of squares] over the valid frames of each utterance."""
+        stash = getattr(feat, "_sfe_stats", None)
+        if stash is not None and stash[0] == feat._version:
+            return stash[1]
+        return ops.stats_accumulate(feat, feat_len)
+
+    def _all_reduce(self, packed: torch.Tensor) -> torch.Tensor:
+        if self.distributed and torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.all_reduce(packed, op=torch.distributed.ReduceOp.SUM)
+        return packed
+
+    def _counter(self, prefix: str) -> Optional[int]:
+        if prefix in self._batch_host:
+            return self._batch_host[prefix]
+        if hasattr(self, f"{prefix}_batch"):  # restored from a checkpoint: one sync, once
+            self._batch_host[prefix] = int(self.get_buffer(f"{prefix}_batch").item())
+            return self._batch_host[prefix]
+        return None
+
+    def register_mean_std_batch(self, packed: torch.Tensor, D: int, prefix: str, epoch: Optional[int]):
+        """Running average of feat_norm.py:455-508 from the packed [sum mean | sum std | N] sums."""
+        dev = packed.device
+        count = self._counter(prefix)
+        if epoch is None or count is None:
+            count = 1
+        elif epoch <= self.max_epoch_num:
+            count += 1
+        self._batch_host[prefix] = count
+        self.register_buffer(f"{prefix}_batch", torch.full((1,), count, dtype=torch.int64, device=dev))
+        if not (epoch is None or epoch <= self.max_epoch_num):
+            return  # frozen: like the reference, buffers that do not exist yet stay missing
+        first_m = self.mean_norm and not hasattr(self, f"{prefix}_mean")
+        first_s = self.std_norm and not hasattr(self, f"{prefix}_std")
+        if first_m:
+            self.register_buffer(f"{prefix}_mean", torch.empty(D, dtype=torch.float32, device=dev))
+        if first_s:
+            self.register_buffer(f"{prefix}_std", torch.empty(D, dtype=torch.float32, device=dev))
+        weight = float(torch.tensor(1.0) / torch.tensor(count))  # fp32 1/count like `1 / LongTensor`
+        run_mean = self.get_buffer(f"{prefix}_mean") if self.mean_norm else None
+        run_std = self.get_buffer(f"{prefix}_std") if self.std_norm else None
+        if first_m == first_s or run_mean is None or run_std is None:
+            first = first_m if self.mean_norm else first_s
+            ops.running_update(packed, D, weight, first, True, run_mean, run_std)
+        else:  # one of the two buffers pre-exists (partial checkpoint)
+            ops.running_update(packed, D, weight, first_m, True, run_mean, None)
+            ops.running_update(packed, D, weight, first_s, True, None, run_std)
+
+    # ------------------------------------------------------------------------------------
+    def forward(self, feat: torch.Tensor, feat_len: torch.Tensor, group_ids=None, epoch: int = None,
+                masks: Optional[DeviceMasks] = None, inplace: bool = False, src_has_pad: bool = True,
+                pad_value: float = 0.0):
+        """feat (batch, length, channel) or (batch, length) fp32 CUDA; feat_len (batch,).
+        ``masks`` / ``inplace`` / ``src_has_pad`` are extensions used by AcousticFrontend to fuse the
+        SpecAugment masking into the same pass; the reference signature is the first four."""
+        if self.norm_type == "group":
+            assert group_ids is not None, (
+                "You are using group-level feature normalization, but group_ids is not given. "
+                "Please check 'data_cfg' in your configuration.")
+        squeeze = False
+        if feat.dim() == 2:
+            feat, squeeze = feat.unsqueeze(-1), True
+        elif feat.dim() != 3:
+            raise RuntimeError(f"{self.__class__.__name__} only accepts the input vectors in the shape of "
+                               f"(batch, length, channel) or (batch, length), but got shape={feat.shape}!")
+        if not feat.is_cuda:
+            raise RuntimeError("speechain_b200 FeatureNormalization: `feat` must be a CUDA tensor — no CPU path.")
+        stash = getattr(feat, "_sfe_stats", None)
+        if feat.dtype != torch.float32 or not feat.is_contiguous():
+            feat = feat.float().contiguous()
+            stash = None
+        if stash is not None:
+            feat._sfe_stats = stash
+        if feat_len.dtype != torch.int64:
+            feat_len = feat_len.long()
+        if not feat_len.is_cuda:
+            host = feat_len
+            feat_len = feat_len.to(feat.device, non_blocking=True)
+            HostLengths.remember(feat_len, host)
+        B, _, D = feat.shape
+        dst = feat if inplace else None
+        common = dict(masks=masks, src_has_pad=src_has_pad, pad_value=pad_value)
+        if dst is None:
+            dst = torch.empty_like(feat)
+        if not (self.mean_norm or self.std_norm):
+            out, _, _ = ops.normalize(feat, feat_len, dst=dst, **common)
+            return (out.squeeze(-1) if squeeze else out), feat_len
+
+        sums = self._sums(feat, feat_len)
+        if self.norm_type == "utterance" or (self.norm_type == "batch" and not self.training):
+            # feat_norm.py:137-139, 288-299: statistics are resolved inside the normalise kernel
+            out, _, _ = ops.normalize(feat, feat_len, dst=dst, stats=sums, clamp=self.clamp, use_mean=self.mean_norm,
+                                      use_std=self.std_norm, **common)
+        elif self.norm_type == "group" and isinstance(group_ids, torch.Tensor):
+            out = self._forward_group_tensor(feat, feat_len, dst, sums, group_ids, epoch, common)
+        elif self.norm_type in ("batch", "global", "group"):
+            if self.norm_type == "group":
+                assert isinstance(group_ids, (str, int)), (
+                    f"If all the utterances in a single batch belong to the same group, "
+                    f"you should give group_ids as a string or integer. But got type(group_ids)={type(group_ids)}.")
+            mean = std = None
+            if self.training:
+                _, _, packed = ops.stats_finalize(sums, feat_len, self.clamp, want_packed=True)
+                packed = self._all_reduce(packed)
+                if self.norm_type == "batch":
+                    mean, std = ops.running_update(packed, D, 1.0, False, False, None, None, want_batch=True)
+                    mean = mean if self.mean_norm else None
+                    std = std if self.std_norm else None
+            if self.norm_type != "batch":
+                prefix = "global" if self.norm_type == "global" else group_ids
+                if self.training:
+                    self.register_mean_std_batch(packed, D, str(prefix), epoch)
+                mean = self.get_buffer(f"{prefix}_mean") if self.mean_norm else None
+                std = self.get_buffer(f"{prefix}_std") if self.std_norm else None
+            out, _, _ = ops.normalize(feat, feat_len, dst=dst, mean=mean, std=std, per_utt=False, **common)
+        else:
+            raise AssertionError(f"norm_type can only be one of 'utterance', 'batch', 'group', 'global', "
+                                 f"but got norm_type={self.norm_type}!")
+        return (out.squeeze(-1) if squeeze else out), feat_len
+
+    # ------------------------------------------------------------------------------------
+    # group-level normalisation with tensor ids (speaker-wise statistics, feat_norm.py:153-230)
+    # ------------------------------------------------------------------------------------
+    def _forward_group_tensor(self, feat, feat_len, dst, sums, group_ids, epoch, common):
+        B, _, D = feat.shape
+        ids_host = [int(g) for g in group_ids.tolist()]
+        if self.training:
+            mean, std, _ = ops.stats_finalize(sums, feat_len, self.clamp, want_packed=False)
+            if self.distributed and torch.distributed.is_available() and torch.distributed.is_initialized():
+                mean, std, ids_host = self._gather_group(mean, std, ids_host)
+            # bookkeeping on (n_groups, D)-sized tensors; the per-group mean of per-utterance stats
+            order = []
+            for g in ids_host:
+                if g not in order:
+                    order.append(g)
+            for g in order:
+                sel = torch.tensor([i for i, x in enumerate(ids_host) if x == g], device=feat.device)
+                gm = mean.index_select(0, sel).mean(dim=0) if self.mean_norm else None
+                gs = std.index_select(0, sel).mean(dim=0) if self.std_norm else None
+                self._register_group(str(g), gm, gs, epoch)
+            self.update_aver_mean_std(epoch)
+            ids_host = [int(g) for g in group_ids.tolist()]  # back to the local utterances
+        rows_m, rows_s = [], []
+        for g in ids_host:
+            if self.mean_norm:
+                rows_m.append(self.get_buffer(f"{g}_mean") if hasattr(self, f"{g}_mean") else self.get_buffer("aver_mean"))
+            if self.std_norm:
+                rows_s.append(self.get_buffer(f"{g}_std") if hasattr(self, f"{g}_std") else self.get_buffer("aver_std"))
+        m = torch.stack(rows_m).contiguous() if rows_m else None
+        s = torch.stack(rows_s).contiguous() if rows_s else None
+        out, _, _ = ops.normalize(feat, feat_len, dst=dst, mean=m, std=s, per_utt=True, **common)
+        return out
+
+    def _gather_group(self, mean, std, ids_host):
+        """all_gather of per-utterance statistics + ids (feat_norm.py:157-171), padded to the
+        largest local batch."""
+        world = torch.distributed.get_world_size()
+        dev = mean.device
+        n = torch.tensor([len(ids_host)], dtype=torch.int64, device=dev)
+        sizes = [torch.zeros_like(n) for _ in range(world)]
+        torch.distributed.all_gather(sizes, n)
+        sizes = [int(x.item()) for x in sizes]
+        mx = max(sizes)
+        D = mean.size(1)
+        pack = torch.zeros((mx, 2 * D + 1), dtype=torch.float32, device=dev)
+        pack[: len(ids_host), :D] = mean
+        pack[: len(ids_host), D:2 * D] = std
+        pack[: len(ids_host), 2 * D] = torch.tensor(ids_host, dtype=torch.float32, device=dev)
+        allp = [torch.zeros_like(pack) for _ in range(world)]
+        torch.distributed.all_gather(allp, pack)
+        cat = torch.cat([p[:k] for p, k in zip(allp, sizes)])
+        return cat[:, :D].contiguous(), cat[:, D:2 * D].contiguous(), [int(v) for v in cat[:, 2 * D].tolist()]
+
+    def _register_group(self, prefix: str, cur_mean, cur_std, epoch):
+        dev = (cur_mean if cur_mean is not None else cur_std).device
+        count = self._counter(prefix)
+        if epoch is None or count is None:
+            count = 1
+        elif epoch <= self.max_epoch_num:
+            count += 1
+        self._batch_host[prefix] = count
+        self.register_buffer(f"{prefix}_batch", torch.full((1,), count, dtype=torch.int64, device=dev))
+        if epoch is None or epoch <= self.max_epoch_num:
+            w = torch.tensor(1.0, device=dev) / count
+            for name, cur, on in ((f"{prefix}_mean", cur_mean, self.mean_norm), (f"{prefix}_std", cur_std, self.std_norm)):
+                if not on:
+                    continue
+                if not hasattr(self, name):
+                    self.register_buffer(name, cur)
+                else:
+                    self.register_buffer(name, w * cur + (1 - w) * self.get_buffer(name))
+
+    def update_aver_mean_std(self, epoch: int):
+        """feat_norm.py:510-531 (iterates *all* buffers ending in _mean/_std, aver_* included)."""
+        if epoch is None or epoch <= self.max_epoch_num:
+            n_m = n_s = 0
+            a_m = a_s = None
+            for name, buff in self.named_buffers():
+                if name.endswith("_mean"):
+                    n_m += 1
+                    a_m = buff.clone() if a_m is None else a_m + buff
+                elif name.endswith("_std"):
+                    n_s += 1
+                    a_s = buff.clone() if a_s is None else a_s + buff
+            if a_m is not None:
+                self.register_buffer("aver_mean", a_m / n_m)
+            if a_s is not None:
+                self.register_buffer("aver_std", a_s / n_s)
+
+    # ------------------------------------------------------------------------------------
+    def recover(self, feat: torch.Tensor, group_ids=None):
+        """Inverse of the global / group normalisation (feat_norm.py:533-607); a (D,)-broadcast on
+        tiny statistics, not part of the accelerated forward path."""
+        assert self.norm_type not in ["utterance", "batch"], \
+            "If norm_type is either 'utterance' or 'batch', the normalized features cannot be recovered."
+        if self.norm_type == "global" or (self.norm_type == "group" and isinstance(group_ids, (str, int))):
+            prefix = "global" if self.norm_type == "global" else str(group_ids)
+            feat = feat * self.get_buffer(f"{prefix}_std") if self.std_norm else feat
+            feat = feat + self.get_buffer(f"{prefix}_mean") if self.mean_norm else feat
+        elif self.norm_type == "group" and isinstance(group_ids, torch.Tensor):
+            ids = [int(g) for g in group_ids.tolist()]
+            if self.std_norm:
+                feat = feat * torch.stack([self.get_buffer(f"{g}_std") if hasattr(self, f"{g}_std")
+                                           else self.get_buffer("aver_std") for g in ids]).unsqueeze(1)
+            if self.mean_norm:
+                feat = feat + torch.stack([self.get_buffer(f"{g}_mean") if hasattr(self, f"{g}_mean")
+                                           else self.get_buffer("aver_mean") for g in ids]).unsqueeze(1)
+        elif self.norm_type == "group" and group_ids is None:
+            feat = feat * self.get_buffer("aver_std").expand(1, 1, -1) if self.std_norm else feat
+            feat = feat + self.get_buffer("aver_mean").expand(1, 1, -1) if self.mean_norm else feat
+        else:
+            raise RuntimeError
+        return feat
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        """Lazily register every buffer ending in _batch/_std/_mean found in the checkpoint
+        (feat_norm.py:609-632)."""
+        self._batch_host.clear()
+        for key in state_dict.keys():
+            if key.startswith(prefix):
+                name = key[len(prefix):].split(".", 1)[0]
+                if "_" in name and name.split("_")[-1] in ["batch", "std", "mean"]:
+                    self.register_buffer(name, state_dict[key])
+                else:
+                    unexpected_keys.append(key)
+
+    def __getstate__(self):
+        return self.__dict__.copy()
+
+    def extra_repr(self) -> str:
+        return f"norm_type={self.norm_type}, mean_norm={self.mean_norm}, std_norm={self.std_norm}"
