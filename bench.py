@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""Benchmark of the acoustic-frontend hot path (BASELINE.json metric: log-Mel audio-seconds per
+second; HBM GB/s vs the measured peak; reference CPU path timed beside it).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3] [--impl reference]
+
+One "step" = one pass of the hot path over one synthetic batch of the named workload.
+  value  : audio-s/s with the waveforms already resident in HBM (CUDA events, max over ranks)
+  e2e    : same metric through the public module API with PINNED HOST waveforms — the H2D copy
+           of every step's batch and the D2H read of its result lengths are inside the timed region
+  roofline / cpu_baseline : see DESIGN.md §Measurement
+Inputs cycle through a ring of distinct batches whose total footprint exceeds 3x the 126 MB L2,
+so no step finds its input or output lines in cache.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+L2_BYTES = 126e6
+
+WORKLOADS = {
+    # BASELINE.json configs[0]
+    "c1": dict(desc="C1: 16 kHz 80-Mel log10 Speech2MelSpec, 32 x 15 s (n_fft 512, win 400, hop 160)",
+               sr=16000, B=32, fixed_len=240000, seed=1235,
+               frontend=dict(n_mels=80, n_fft=512, win_length=0.025, hop_length=0.010, sr=16000),
+               normalize=None, specaug=None),
+    # BASELINE.json configs[1] — the configuration the metric is quoted on
+    "c2": dict(desc="C2: ASR training batch, 64 x 2-20 s @16 kHz, 80-Mel (n_fft 512) + pre-emphasis 0.97 + "
+                    "utterance norm + SpecAugment (2 freq / 2 time masks)",
+               sr=16000, B=64, len_range=(32000, 320001), seed=1236,
+               frontend=dict(n_mels=80, n_fft=512, win_length=0.025, hop_length=0.010, sr=16000, preemphasis=0.97),
+               normalize=dict(norm_type="utterance"),
+               specaug=dict(time_warp=False, freq_mask_width=30, freq_mask_num=2, time_mask_width=0.05,
+                            time_mask_num=2)),
+    # BASELINE.json configs[2]
+    "c3": dict(desc="C3: TTS 22.05 kHz 80-Mel (n_fft 1024, hop 256, magnitude, ln, clamp 1e-5, energy), 128 x 10 s",
+               sr=22050, B=128, fixed_len=220500, seed=1237,
+               frontend=dict(sr=22050, n_mels=80, win_length=1024, hop_length=256, mag_spec=True, fmin=0, fmax=8000,
+                             log_base=None, clamp=1e-5, return_energy=True),
+               normalize=None, specaug=None),
+}
+
+
+def workload_lengths(w, world=1, rank=0):
+    """Lengths of this rank's utterances.  The global batch has B*world utterances sorted
+    descending; rank r takes [world-1-r :: world] (iterator/abs.py:226-236) -> B per rank (weak scaling)."""
+    n = w["B"] * world
+    if "fixed_len" in w:
+        lens = [w["fixed_len"]] * n
+    else:
+        g = torch.Generator().manual_seed(w["seed"])
+        lo, hi = w["len_range"]
+        lens = sorted(torch.randint(lo, hi, (n,), generator=g).tolist(), reverse=True)
+        lens[0] = hi - 1  # the padded length is the nominal maximum
+    return lens[world - 1 - rank::world]
+
+
+def make_batch(w, lens, seed, device):
+    """(B, T_max, 1) fp32 = 0.1*randn, zero beyond each length."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    T = max(lens)
+    wav = 0.1 * torch.randn(len(lens), T, 1, generator=g, device=device)
+    idx = torch.arange(T, device=device)[None, :, None]
+    wav.masked_fill_(idx >= torch.tensor(lens, device=device)[:, None, None], 0.0)
+    return wav
+
+
+class ClockSampler:
+    """SM clock / throttle reasons sampled through NVML while the timed regions run."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.nv = None
+            self.err = repr(e)
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline: the reference's op sequence on torch CPU tensors (oracle/ref_port_torch.py)
+# ----------------------------------------------------------------------------------------------
+def cpu_pass(w, wav, wl, weight, port):
+    fc = w["frontend"]
+    sr = fc.get("sr", 16000)
+    hop = int(fc["hop_length"] * sr) if isinstance(fc["hop_length"], float) else fc["hop_length"]
+    win = int(fc["win_length"] * sr) if isinstance(fc["win_length"], float) else fc["win_length"]
+    n_fft = fc.get("n_fft") or win
+    spec, fl, en = port.speech2linear(wav, wl, n_fft=n_fft, hop=hop, win=win, preemphasis=fc.get("preemphasis"),
+                                      mag_spec=fc.get("mag_spec", False), return_energy=fc.get("return_energy", False))
+    feat = port.linear2mel(spec, weight, clamp=fc.get("clamp", 1e-10), logging=True, log_base=fc.get("log_base", 10.0))
+    if w["normalize"] is not None:
+        feat = port.norm_utterance(feat, fl)
+    if w["specaug"] is not None:
+        s = w["specaug"]
+        feat = port.specaug(feat, fl, freq_mask_width=(0, s["freq_mask_width"]), freq_mask_num=s["freq_mask_num"],
+                            time_mask_width=(0, s["time_mask_width"]), time_mask_num=s["time_mask_num"])
+    return feat
+
+
+def time_cpu(w, steps, warmup):
+    from oracle import ref_port_torch as port
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    lens = workload_lengths(w)
+    wav = make_batch(w, lens, w["seed"], "cpu")
+    wl = torch.tensor(lens, dtype=torch.int64)
+    fc = w["frontend"]
+    sr = fc.get("sr", 16000)
+    win = int(fc["win_length"] * sr) if isinstance(fc["win_length"], float) else fc["win_length"]
+    weight = port.mel_weight(sr, fc.get("n_fft") or win, fc["n_mels"], fc.get("fmin", 0.0), fc.get("fmax"))
+    torch.manual_seed(1234)
+    for _ in range(warmup):
+        cpu_pass(w, wav.clone(), wl.clone(), weight, port)
+    ts = []
+    for _ in range(steps):
+        x, l = wav.clone(), wl.clone()
+        t0 = time.perf_counter()
+        cpu_pass(w, x, l, weight, port)
+        ts.append(time.perf_counter() - t0)
+    audio_s = sum(lens) / w["sr"]
+    return audio_s, ts, threads
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_reference(args, w, rank, world):
+    if rank != 0:
+        return
+    audio_s, ts, threads = time_cpu(w, args.steps, max(args.warmup, 1))
+    total = sum(ts)
+    val = audio_s * len(ts) / total
+    line = {
+        "impl": "reference", "metric": "log-Mel audio-seconds per second", "value": val, "unit": "audio-s/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1),
+        "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "note": "reference op sequence on torch CPU (oracle/ref_port_torch.py); "
+                   "/root/reference itself does not travel to the GPU box"},
+        "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": threads, "kind": "port",
+                         "sample": f"{len(ts)} full passes over one batch ({audio_s:.0f} audio-s each), {cpu_model()}"},
+        "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, w, rank, world)
+        return
+
+    from speechain_b200.host import ops
+    from speechain_b200.module.acoustic_frontend import AcousticFrontend
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    steps, warmup = args.steps, max(args.warmup, 3)
+    lens = workload_lengths(w, world, rank)
+    B, T = len(lens), max(lens)
+    audio_s = sum(lens) / w["sr"]
+
+    chain = AcousticFrontend(frontend=dict(conf=w["frontend"]), normalize=w["normalize"], specaug=w["specaug"],
+                             distributed=world > 1).to(dev)
+    chain.train()
+    fe = chain.frontend
+    D, hop = fe.output_size, fe.speech2linear.hop_length
+    F = 1 + T // hop
+    flen = [n // hop + 1 for n in lens]
+    out_bytes = 4 * B * F * D + (4 * B * F if fe.return_energy else 0)
+    in_bytes_padded = 4 * B * T
+    ring = max(2, int(np.ceil(3 * L2_BYTES / (in_bytes_padded + out_bytes))) + 1)
+    batches = [make_batch(w, lens, w["seed"] + 100 * i + rank, dev) for i in range(ring)]
+    wl_dev = torch.tensor(lens, dtype=torch.int64, device=dev)
+    wl_host = torch.tensor(lens, dtype=torch.int64)
+    ops.HostLengths.remember(wl_dev, wl_host)
+
+    def step(i):
+        return chain(batches[i % ring], wl_dev)
+
+    torch.manual_seed(1234 + rank)
+    sampler = ClockSampler(local)
+    # spin the clocks up before anything is timed
+    t_end = time.time() + (0.0 if os.environ.get("SFE_BENCH_NOSPIN") else 0.5)
+    i = 0
+    while time.time() < t_end:
+        step(i)
+        i += 1
+        if i % 64 == 0:
+            torch.cuda.synchronize()
+    for i in range(warmup):
+        step(i)
+    barrier()
+    sampler.start()
+
+    # ---- (1) device-resident timing: exactly `steps` steps between two events ----
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+
+    # ---- (2) the dominant kernel alone (fused frontend), same arguments as inside the step ----
+    two_pass = w["normalize"] is not None
+    kw = dict(want_stats=True, skip_pad=True) if two_pass else {}
+    for i in range(3):
+        fe.run(batches[i % ring], wl_dev, **kw)
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for i in range(steps):
+        fe.run(batches[i % ring], wl_dev, **kw)
+    k1.record()
+    torch.cuda.synchronize()
+    kern_ms = k0.elapsed_time(k1) / steps
+
+    # ---- (3) end to end: pinned host waveforms -> H2D -> chain -> D2H of the result lengths ----
+    host = [b.cpu().pin_memory() for b in batches[:2]]
+    dbuf = [torch.empty_like(batches[0]) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
+    res_host = torch.empty(B, dtype=torch.int64).pin_memory()
+    main_stream = torch.cuda.current_stream()
+
+    def e2e_loop(n):
+        # double-buffered: the copy of step i+1 overlaps the kernels of step i
+        for s in range(2):
+            free[s].record(main_stream)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(free[0])
+            dbuf[0].copy_(host[0], non_blocking=True)
+            ready[0].record(copy_stream)
+        for i in range(n):
+            s = i % 2
+            if i + 1 < n:
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(free[1 - s])
+                    dbuf[1 - s].copy_(host[(i + 1) % 2], non_blocking=True)
+                    ready[1 - s].record(copy_stream)
+            main_stream.wait_event(ready[s])
+            ylen = chain(dbuf[s], wl_host)[1]       # lengths arrive on the host, like a collated batch
+            free[s].record(main_stream)
+            res_host.copy_(ylen, non_blocking=True)
+        main_stream.synchronize()
+
+    e2e_steps = max(8, min(steps, 64))
+    e2e_loop(4)
+    barrier()
+    t0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    e2e_loop(e2e_steps)
+    g1.record()
+    barrier()
+    e2e_ms = g0.elapsed_time(g1)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    clocks = sampler.stop()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = load_peaks()
+    S = sum(lens)
+    valid_frames = sum(min(f, F) for f in flen)
+    if two_pass:
+        kern_bytes = 4 * S + 4 * valid_frames * D          # reads valid samples, writes valid raw rows
+        step_bytes = 4 * S + 4 * B * F * D                 # input once + padded output once
+    else:
+        kern_bytes = 4 * S + out_bytes
+        step_bytes = kern_bytes
+    achieved = kern_bytes / (kern_ms * 1e-3) / 1e9
+    total_audio = audio_s * world
+    line = {
+        "metric": "log-Mel audio-seconds per second", "value": total_audio * steps / (ms_total * 1e-3),
+        "unit": "audio-s/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_total / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "utterances_per_gpu": B, "audio_s_per_step_per_gpu": audio_s,
+                   "padded_len": T, "frames": F, "sharding": "utterance stride [W-1-r::W], no data-path collective",
+                   "cache": f"ring of {ring} distinct batches ({ring * (in_bytes_padded + out_bytes) / 1e6:.0f} MB) > 3x L2"},
+        "clocks": clocks,
+        "e2e": {"value": total_audio * e2e_steps / (e2e_ms * 1e-3), "unit": "audio-s/s",
+                "h2d_bytes_per_step": in_bytes_padded, "d2h_bytes_per_step": 8 * B, "steps": e2e_steps,
+                "note": "public API AcousticFrontend.forward on pinned host (B,T,1) waveforms, copy of step i+1 "
+                        "overlapped with step i; D2H = feature lengths (features stay on the GPU for the model)"},
+        "gpu_launches": steps * (2 if two_pass else 1),
+        "roofline": {"bound": "hbm", "kernel": "sfe::fused_frontend_kernel", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": kern_bytes, "us_per_launch": kern_ms * 1e3,
+                     "step_algorithmic_bytes": step_bytes,
+                     "step_gbs": step_bytes / (ms_total / steps * 1e-3) / 1e9},
+    }
+    traffic_file = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
+    if os.path.exists(traffic_file):
+        with open(traffic_file) as f:
+            line["roofline"]["traffic"] = json.load(f).get("dram_bytes_per_launch")
+    if world == 1 and not args.no_cpu:
+        a_s, ts, threads = time_cpu(w, 5, 1)
+        line["cpu_baseline"] = {"value": a_s * len(ts) / sum(ts), "unit": "audio-s/s", "cores": threads, "kind": "port",
+                                "sample": f"{len(ts)} full passes over one batch ({a_s:.0f} audio-s each) after 1 "
+                                          f"warm-up, {sum(ts):.1f} s of CPU work, {cpu_model()}"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

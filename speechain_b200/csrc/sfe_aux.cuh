@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(NTHREADS) linear2mel_kernel(const __grid_const
   for (int i = lane; i < p2_floats; i += 32) P2[i] = 0.f;
   __syncthreads();
   const int* mstart = reinterpret_cast<const int*>(tab + p.o_mstart);
-  const float* mw = tab + p.o_mw;
+  const float4* mw4 = reinterpret_cast<const float4*>(tab + p.o_mw);
   const float2* P2v = reinterpret_cast<const float2*>(P2);
   const long long pairs = (p.n_rows + FPW - 1) / FPW;
   for (long long pr = static_cast<long long>(blockIdx.x) * NWARPS + warp; pr < pairs;
@@ -365,16 +365,19 @@ __global__ void __launch_bounds__(NTHREADS) linear2mel_kernel(const __grid_const
     int wofs = 0;
     for (int rd = 0; rd < p.mel_rounds; ++rd) {
       const int d = rd * 32 + lane;
-      const int st = mstart[d];
-      const int nt = p.mel_taps[rd];
+      const float2* pp = P2v + mstart[d];
+      const int nq = p.mel_taps[rd] >> 2;
+      const float4* wp = mw4 + wofs + lane;
       float a0 = 0.f, a1 = 0.f;
-      for (int q = 0; q < nt; ++q) {
-        const float wgt = mw[wofs + q * 32 + lane];
-        const float2 pv = P2v[st + q];
-        a0 = fmaf(wgt, pv.x, a0);
-        a1 = fmaf(wgt, pv.y, a1);
+      for (int q = 0; q < nq; ++q) {
+        const float4 w4 = wp[q * 32];
+        const float2 p0 = pp[4 * q], p1 = pp[4 * q + 1], p2 = pp[4 * q + 2], p3 = pp[4 * q + 3];
+        a0 = fmaf(w4.x, p0.x, a0); a1 = fmaf(w4.x, p0.y, a1);
+        a0 = fmaf(w4.y, p1.x, a0); a1 = fmaf(w4.y, p1.y, a1);
+        a0 = fmaf(w4.z, p2.x, a0); a1 = fmaf(w4.z, p2.y, a1);
+        a0 = fmaf(w4.w, p3.x, a0); a1 = fmaf(w4.w, p3.y, a1);
       }
-      wofs += nt * 32;
+      wofs += nq * 32;
       if (d < p.D) {
         if (p.mel_log) {
           a0 = logf(fmaxf(a0, p.mel_clamp)) / p.mel_div;

@@ -1,13 +1,14 @@
 // Fused waveform -> (log-)mel / linear spectrogram kernel for sm_100a.
 //
 // One persistent CTA per resident slot.  A CTA repeatedly claims a *tile* of TILE_F consecutive
-// frames of one utterance (dynamic atomic scheduler), stages the (TILE_F-1)*hop + win samples
-// the tile touches into shared memory with ONE 1-D bulk async copy (cp.async.bulk -> UBLKCP,
-// completion on an mbarrier) — every sample is read from HBM once although it belongs to
-// win/hop frames — and then each warp turns two frames into features:
+// frames of one utterance (dynamic atomic scheduler, claimed two tiles ahead), stages the
+// (TILE_F-1)*hop + n_fft samples the tile touches into shared memory with ONE 1-D bulk async copy
+// (cp.async.bulk -> UBLKCP, completion on an mbarrier; double buffered, so the copy of tile i+1
+// runs under the arithmetic of tile i) — every sample is read from HBM once although it belongs
+// to win/hop frames — and then each warp turns two frames into features:
 //
 //   window (+ pre-emphasis on the fly)  ->  real FFT as an n_fft/2-point complex Stockham FFT
-//   (radix 16/8/5/4/2 butterflies in registers, passes exchanged through a warp-private,
+//   (radix 16/8/5/4/3/2 butterflies in registers, passes exchanged through a warp-private,
 //   padded shared-memory buffer)  ->  real-FFT unpack + |X|^2  ->  banded (sparse) mel filter
 //   ->  clamp/log  ->  [global (x-mean)/std]  ->  [SpecAugment masks]  ->  coalesced stores,
 //   plus fp64 per-utterance sum / sum-of-squares accumulation for the normaliser.
@@ -27,7 +28,7 @@ constexpr int NTHREADS = NWARPS * 32;
 constexpr int FPW = 2;                    // frames per warp per tile
 constexpr int TILE_F = NWARPS * FPW;      // frames per tile
 constexpr int MAX_MEL_ROUNDS = 8;         // n_mels <= 256
-constexpr int MAX_MASKS = 16;
+constexpr int NSTAGE = 2;                 // staging buffers
 
 struct FwdParams {
   // input
@@ -73,9 +74,9 @@ struct FwdParams {
   int tab_floats;
   int o_win, o_tw2, o_tw3, o_wpost, o_mstart, o_mw;  // float offsets into the blob
   int mel_rounds;
-  int mel_taps[MAX_MEL_ROUNDS];
-  int mel_tail;                                      // max taps of any bin (P2 tail padding)
-  int sm_stage, sm_stage_floats, sm_warp, sm_warp_bytes, sm_z_bytes, sm_red, sm_bar;
+  int mel_taps[MAX_MEL_ROUNDS];                      // multiples of 4
+  int mel_tail;                                      // max taps of any round (P2 tail padding)
+  int sm_stage, sm_stage_floats, sm_warp, sm_warp_bytes, sm_p2_off, sm_red_off, sm_bar;
   // scheduler
   unsigned int* sched;  // [0] next tile, [1] CTAs done
 };
@@ -88,8 +89,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -125,6 +126,9 @@ struct FftPlan {
   static constexpr int S = FPW / C;        // sequential sub-iterations per tile
   static constexpr int PADQ = R1_;         // one padding slot every PADQ complex values
   static constexpr int MP = M_ + M_ / R1_ + 1;
+  // the power spectrum may overwrite the FFT scratch only if no later FFT of the tile needs it
+  static constexpr bool ALIAS_P2 = (S == 1);
+  static constexpr int MINB = (M_ == 256 || M_ == 240) ? 3 : ((M_ <= 512) ? 2 : 1);  // resident CTAs per SM aimed for
   static_assert(R1_ * R2_ * R3_ == M_, "radices must multiply to M");
   static_assert(C * S == FPW, "bad lane grouping");
 };
@@ -135,52 +139,57 @@ __device__ __forceinline__ int padidx(int i) { return i + i / PADQ; }
 // One Stockham pass of radix R with P = product of the previous radices.  FIRST passes read the
 // windowed samples; the others read the warp-private Z buffer.  In place: all inputs of all
 // rounds are held in registers before anything is written.
-template <class PL, int R, int P, bool FIRST>
+template <class PL, int R, int P, bool FIRST, bool VEC, bool PRE>
 __device__ __forceinline__ void stockham_pass(cpx* __restrict__ Z, const cpx* __restrict__ tw, int l,
                                               const float* __restrict__ fr, const float* __restrict__ wtab,
-                                              int win, bool vec_ok, bool apply_pre, float pre) {
-  constexpr int M = PL::M, G = PL::G;
+                                              int win, float pre) {
+  constexpr int M = PL::M, G = PL::G, Q = PL::PADQ;
   constexpr int T = M / R;
   constexpr int NR = (T + G - 1) / G;
+  constexpr bool FULL = (T % G == 0);
   cpx u[NR][R];
 #pragma unroll
   for (int rd = 0; rd < NR; ++rd) {
     const int j = l + rd * G;
-    if (T % G == 0 || j < T) {
+    if (FULL || j < T) {
       if (FIRST) {
+        const float* f0 = fr + 2 * j;
+        const float* w0 = wtab + 2 * j;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          const int s = 2 * (j + r * T);
-          float y0 = 0.f, y1 = 0.f;
-          if (s < win) {
+          if (2 * r * T < win) {  // warp-uniform: rows entirely inside the window's zero padding are skipped
             float x0, x1;
-            if (vec_ok) {
-              const float2 v = *reinterpret_cast<const float2*>(fr + s);
+            if (VEC) {
+              const float2 v = *reinterpret_cast<const float2*>(f0 + 2 * r * T);
               x0 = v.x;
               x1 = v.y;
             } else {
-              x0 = fr[s];
-              x1 = fr[s + 1];
+              x0 = f0[2 * r * T];
+              x1 = f0[2 * r * T + 1];
             }
-            if (apply_pre) {
-              const float xm = fr[s - 1];
-              y0 = fmaf(-pre, xm, x0);
-              y1 = fmaf(-pre, x0, x1);
-            } else {
-              y0 = x0;
-              y1 = x1;
+            if (PRE) {
+              const float xm = f0[2 * r * T - 1];
+              x1 = fmaf(-pre, x0, x1);
+              x0 = fmaf(-pre, xm, x0);
             }
-            const float2 w = *reinterpret_cast<const float2*>(wtab + s);
-            y0 *= w.x;
-            y1 = (s + 1 < win) ? y1 * w.y : 0.f;
+            const float2 w = *reinterpret_cast<const float2*>(w0 + 2 * r * T);
+            u[rd][r] = make_float2(x0 * w.x, x1 * w.y);
+          } else {
+            u[rd][r] = make_float2(0.f, 0.f);
           }
-          u[rd][r] = make_float2(y0, y1);
         }
       } else {
+        if (T % Q == 0) {
+          const cpx* zr = Z + padidx<Q>(j);
 #pragma unroll
-        for (int r = 0; r < R; ++r) u[rd][r] = Z[padidx<PL::PADQ>(j + r * T)];
+          for (int r = 0; r < R; ++r) u[rd][r] = zr[r * (T + T / Q)];
+        } else {
 #pragma unroll
-        for (int r = 1; r < R; ++r) u[rd][r] = cmul(u[rd][r], tw[(r - 1) * T + j]);
+          for (int r = 0; r < R; ++r) u[rd][r] = Z[padidx<Q>(j + r * T)];
+        }
+        const cpx* twj = tw + j;
+#pragma unroll
+        for (int r = 1; r < R; ++r) u[rd][r] = cmul(u[rd][r], twj[(r - 1) * T]);
       }
     }
   }
@@ -188,92 +197,179 @@ __device__ __forceinline__ void stockham_pass(cpx* __restrict__ Z, const cpx* __
 #pragma unroll
   for (int rd = 0; rd < NR; ++rd) {
     const int j = l + rd * G;
-    if (T % G == 0 || j < T) {
+    if (FULL || j < T) {
       bfly<R>(u[rd]);
-      const int k = j % P;
-      const int jo = (j - k) * R + k;
+      if (P == 1 && R == Q) {
+        cpx* zw = Z + j * (R + 1);
 #pragma unroll
-      for (int r = 0; r < R; ++r) Z[padidx<PL::PADQ>(jo + r * P)] = u[rd][r];
+        for (int r = 0; r < R; ++r) zw[r] = u[rd][r];
+      } else {
+        const int k = (P >= G * NR) ? j : j % P;  // when every butterfly index is < P the twiddle index is j itself
+        const int jo = (j - k) * R + k;
+        if (P % Q == 0) {
+          cpx* zw = Z + padidx<Q>(jo);
+#pragma unroll
+          for (int r = 0; r < R; ++r) zw[r * (P + P / Q)] = u[rd][r];
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) Z[padidx<Q>(jo + r * P)] = u[rd][r];
+        }
+      }
     }
   }
   __syncwarp();
 }
 
+template <class PL, bool VEC, bool PRE>
+__device__ __forceinline__ void fft_frame(cpx* Zw, const cpx* tw2, const cpx* tw3, int l, const float* fr,
+                                          const float* wtab, int win, float pre) {
+  stockham_pass<PL, PL::R1, 1, true, VEC, PRE>(Zw, nullptr, l, fr, wtab, win, pre);
+  stockham_pass<PL, PL::R2, PL::R1, false, false, false>(Zw, tw2, l, nullptr, nullptr, 0, 0.f);
+  if (PL::R3 > 1)
+    stockham_pass<PL, (PL::R3 > 1 ? PL::R3 : 2), PL::R1 * PL::R2, false, false, false>(Zw, tw3, l, nullptr, nullptr, 0,
+                                                                                       0.f);
+}
+
+// per-tile metadata published by thread 0 one tile ahead
+struct TileInfo {
+  int tile;    // >= num_tiles: no more work
+  int kind;    // 0 pad tile, 1 interior (bulk copy in flight / landed), 2 edge (gather at its turn)
+  int shift;   // staging index of the first sample of frame t0 (interior tiles)
+  int b, t0, flen;
+  long long len;
+};
+enum { TILE_PAD = 0, TILE_BULK = 1, TILE_EDGE = 2 };
+
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
 template <class PL>
-__global__ void __launch_bounds__(NTHREADS) fused_frontend_kernel(const __grid_constant__ FwdParams p) {
+__global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  constexpr int M = PL::M, G = PL::G;
+  constexpr int M = PL::M, G = PL::G, Q = PL::PADQ;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane / G, l = lane % G;
 
   float* tab = reinterpret_cast<float*>(smem);
-  float* stage = reinterpret_cast<float*>(smem + p.sm_stage);
   unsigned char* wbase = smem + p.sm_warp + warp * p.sm_warp_bytes;
   cpx* Zw = reinterpret_cast<cpx*>(wbase) + g * PL::MP;
-  float* P2 = reinterpret_cast<float*>(wbase + p.sm_z_bytes);  // [k][FPW] interleaved
-  double* red = reinterpret_cast<double*>(smem + p.sm_red);    // [NWARPS][D][2]
+  float* P2 = reinterpret_cast<float*>(wbase + p.sm_p2_off);    // [k][FPW] interleaved
+  double* red = reinterpret_cast<double*>(wbase + p.sm_red_off);  // this warp's [D][2] partial sums
   unsigned long long* barp = reinterpret_cast<unsigned long long*>(smem + p.sm_bar);
-  __shared__ int s_tile;
+  __shared__ TileInfo s_info[NSTAGE];
 
-  // ---- one-time setup: tables -> smem, zero the scratch tails, init the mbarrier ----
-  for (int i = tid; i < p.tab_floats; i += NTHREADS) tab[i] = __ldg(p.tables + i);
-  for (int i = tid; i < p.sm_stage_floats; i += NTHREADS) stage[i] = 0.f;
+  // ---- one-time setup: tables -> smem, zero the scratch, init the mbarriers ----
   {
-    const int p2_floats = (p.K + p.mel_tail + 2) * FPW;
-    for (int i = lane; i < p2_floats; i += 32) P2[i] = 0.f;
+    const float4* src = reinterpret_cast<const float4*>(p.tables);
+    float4* dst = reinterpret_cast<float4*>(tab);
+    for (int i = tid; i < p.tab_floats / 4; i += NTHREADS) dst[i] = __ldg(src + i);
+    float* st = reinterpret_cast<float*>(smem + p.sm_stage);
+    for (int i = tid; i < NSTAGE * p.sm_stage_floats; i += NTHREADS) st[i] = 0.f;
+    float* wz = reinterpret_cast<float*>(wbase);
+    for (int i = lane; i < p.sm_warp_bytes / 4; i += 32) wz[i] = 0.f;
   }
-  const uint32_t bar = smem_u32(barp);
-  if (tid == 0) mbar_init(bar, 1);
-  uint32_t bar_parity = 0;
-  __syncthreads();
+  const uint32_t bar0 = smem_u32(barp);
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    fence_mbar_init();
+  }
+  uint32_t parity[NSTAGE] = {0u, 0u};
 
   const float* wtab = tab + p.o_win;
   const cpx* tw2 = reinterpret_cast<const cpx*>(tab + p.o_tw2);
   const cpx* tw3 = reinterpret_cast<const cpx*>(tab + p.o_tw3);
   const cpx* wpost = reinterpret_cast<const cpx*>(tab + p.o_wpost);
   const int* mstart = reinterpret_cast<const int*>(tab + p.o_mstart);
-  const float* mw = tab + p.o_mw;
+  const float4* mw4 = reinterpret_cast<const float4*>(tab + p.o_mw);
   const int hop = p.hop, win = p.win, D = p.D, K = p.K;
   const bool base_aligned = ((reinterpret_cast<uintptr_t>(p.wav) & 15) == 0);
+  const int pre1 = p.has_pre ? 1 : 0;
 
-  for (;;) {
-    if (tid == 0) s_tile = static_cast<int>(atomicAdd(p.sched, 1u));
-    __syncthreads();  // also: every warp is done with the previous tile's staging buffer
-    const int tile = s_tile;
-    if (tile >= p.num_tiles) break;
-    const int b = tile / p.tiles_per_utt;
-    const int t0 = (tile - b * p.tiles_per_utt) * TILE_F;
-    const long long len = p.len[b];
-    const long long flen_ll = (p.center ? (len + 2 * (p.n_fft / 2)) - p.n_fft : len - p.n_fft) / hop + 1;
-    const int flen = static_cast<int>(flen_ll < 0 ? 0 : (flen_ll > p.F ? p.F : flen_ll));
-    if (t0 == 0 && tid == 0 && p.feat_len) p.feat_len[b] = flen_ll;
+  // thread 0: describe tile `tile`, and if it is an interior tile start its bulk copy into `buf`
+  auto publish = [&](int tile, int buf) {
+    TileInfo ti;
+    ti.tile = tile;
+    ti.kind = TILE_PAD;
+    ti.shift = 0;
+    ti.b = 0; ti.t0 = 0; ti.flen = 0; ti.len = 0;
+    if (tile < p.num_tiles) {
+      // tile order: frame-block major, utterance minor -> with descending lengths the cheap
+      // all-padding tiles are claimed last
+      const int tb = tile / p.B;
+      const int b = tile - tb * p.B;
+      const int t0 = tb * TILE_F;
+      const long long len = __ldg(p.len + b);
+      const long long fl = (p.center ? (len + 2 * (p.n_fft / 2)) - p.n_fft : len - p.n_fft) / hop + 1;
+      const int flen = static_cast<int>(fl < 0 ? 0 : (fl > p.F ? p.F : fl));
+      if (t0 == 0 && p.feat_len) p.feat_len[b] = fl;
+      ti.b = b; ti.t0 = t0; ti.flen = flen; ti.len = len;
+      if (t0 < flen) {
+        const long long o_start = static_cast<long long>(t0) * hop + p.off;
+        const long long o_end = o_start + static_cast<long long>(TILE_F - 1) * hop + win;
+        const long long gi = static_cast<long long>(b) * p.pitch + o_start - pre1;
+        const long long ga = gi & ~3LL;
+        const long long ge = (static_cast<long long>(b) * p.pitch + o_end + 3) & ~3LL;
+        const bool interior = base_aligned && (o_start - pre1 >= 0) && (o_end <= len) && (ge <= p.total_floats);
+        if (interior) {
+          ti.kind = TILE_BULK;
+          ti.shift = static_cast<int>(gi - ga) + pre1;
+          const uint32_t bytes = static_cast<uint32_t>((ge - ga) * 4);
+          const uint32_t bar = bar0 + 8 * buf;
+          fence_proxy_async();
+          mbar_expect_tx(bar, bytes);
+          bulk_g2s(smem_u32(smem + p.sm_stage + buf * p.sm_stage_floats * 4), p.wav + ga, bytes, bar);
+        } else {
+          ti.kind = TILE_EDGE;
+        }
+      }
+    }
+    s_info[buf] = ti;
+  };
+
+  // prologue: claim tiles 0 and 1 of this CTA, start tile 0's copy
+  unsigned int claimed = 0;  // (thread 0) tile claimed for the iteration after next
+  __syncthreads();
+  if (tid == 0) {
+    const int first = static_cast<int>(atomicAdd(p.sched, 1u));
+    claimed = atomicAdd(p.sched, 1u);
+    publish(first, 0);
+  }
+  __syncthreads();
+
+  for (int it = 0;; ++it) {
+    const int buf = it & 1;
+    const TileInfo ti = s_info[buf];
+    if (ti.tile >= p.num_tiles) break;
+    // thread 0: the tile of the next iteration was claimed one iteration ago; start its copy now
+    // (its staging buffer was released by the barrier that ended the previous iteration) and claim
+    // the tile after that — both latencies hide under this tile's arithmetic.
+    if (tid == 0) {
+      const int next = static_cast<int>(claimed);
+      claimed = (next < p.num_tiles) ? atomicAdd(p.sched, 1u) : static_cast<unsigned int>(next);
+      publish(next, buf ^ 1);
+    }
+    const int b = ti.b, t0 = ti.t0, flen = ti.flen;
+    const long long len = ti.len;
     const int nfr = min(TILE_F, p.F - t0);  // frames of this tile that exist in the output
+    float* stage = reinterpret_cast<float*>(smem + p.sm_stage) + buf * p.sm_stage_floats;
 
-    // ---------------- pad tile: nothing to transform ----------------
-    if (t0 >= flen) {
+    if (ti.kind == TILE_PAD) {
+      // ---------------- pad tile: nothing to transform ----------------
       if (p.mel && !p.skip_pad) {
         float* dst = p.mel + (static_cast<long long>(b) * p.F + t0) * D;
+        const float fillv = p.fill_dev ? *p.fill_dev : p.fill;
         for (int i = tid; i < nfr * D; i += NTHREADS) {
           const int d = i % D;
           float v = p.pad_mel;
           if (p.norm_mean) v -= p.norm_mean[d];
           if (p.norm_std) v /= p.norm_std[d];
-          dst[i] = v;  // masks on pad rows are applied below only for freq masks
-        }
-        if (p.n_fmask > 0) {
-          const float fillv = p.fill_dev ? *p.fill_dev : p.fill;
-          for (int i = tid; i < nfr * D; i += NTHREADS) {
-            const int d = i % D;
-            bool m = false;
-            for (int q = 0; q < p.n_fmask; ++q) {
-              const int ps = p.fpos[b * p.n_fmask + q], ln = p.flen[b * p.n_fmask + q];
-              m |= (d >= ps) && (d < ps + ln);
-            }
-            if (m) dst[i] = fillv;
+          bool m = false;
+          for (int q = 0; q < p.n_fmask; ++q) {
+            const int ps = p.fpos[b * p.n_fmask + q], ln = p.flen[b * p.n_fmask + q];
+            m |= (d >= ps) && (d < ps + ln);
           }
+          dst[i] = m ? fillv : v;
         }
       }
       if (p.lin) {
@@ -283,56 +379,39 @@ __global__ void __launch_bounds__(NTHREADS) fused_frontend_kernel(const __grid_c
       if (p.energy) {
         for (int i = tid; i < nfr; i += NTHREADS) p.energy[static_cast<long long>(b) * p.F + t0 + i] = 0.f;
       }
+      __syncthreads();
       continue;
     }
 
-    // ---------------- stage the samples of this tile ----------------
-    const long long o_start = static_cast<long long>(t0) * hop + p.off;   // first sample of frame t0
-    const long long o_end = o_start + static_cast<long long>(TILE_F - 1) * hop + win;
-    const int pre1 = p.has_pre ? 1 : 0;
-    int shift;                 // staging index of sample o_start
-    bool staged_raw;           // true: staging holds x (apply pre-emphasis on the fly)
-    {
-      const long long gi = static_cast<long long>(b) * p.pitch + o_start - pre1;
-      const long long ga = gi & ~3LL;
-      const long long ge = (static_cast<long long>(b) * p.pitch + o_end + 3) & ~3LL;
-      const bool interior = base_aligned && (o_start - pre1 >= 0) && (o_end <= len) && (ge <= p.total_floats);
-      if (interior) {
-        shift = static_cast<int>(gi - ga) + pre1;
-        staged_raw = true;
-        if (tid == 0) {
-          const uint32_t bytes = static_cast<uint32_t>((ge - ga) * 4);
-          fence_proxy_async();
-          mbar_expect_tx(bar, bytes);
-          bulk_g2s(smem_u32(stage), p.wav + ga, bytes, bar);
+    // ---------------- samples of this tile ----------------
+    int shift = ti.shift;
+    const bool staged_raw = (ti.kind == TILE_BULK);
+    if (staged_raw) {
+      mbar_wait(bar0 + 8 * buf, parity[buf]);
+      parity[buf] ^= 1u;
+    } else {
+      // edge tile: explicit gather with batch-level reflection, zero beyond the length and
+      // pre-emphasis applied here (staging then holds the final samples)
+      const long long o_start = static_cast<long long>(t0) * hop + p.off;
+      const float* row = p.wav + static_cast<long long>(b) * p.pitch;
+      const int n = (TILE_F - 1) * hop + win;
+      for (int i = tid; i < n; i += NTHREADS) {
+        long long o = o_start + i;
+        if (p.center) {
+          if (o < 0) o = -o;
+          if (o >= p.T_max) o = 2 * (p.T_max - 1) - o;
         }
-        mbar_wait(bar, bar_parity);
-        bar_parity ^= 1u;
-      } else {
-        // edge tile: explicit gather with batch-level reflection, zero beyond the length and
-        // pre-emphasis applied here (staging then holds the final samples)
-        shift = 0;
-        staged_raw = false;
-        const float* row = p.wav + static_cast<long long>(b) * p.pitch;
-        const int n = static_cast<int>(o_end - o_start);
-        for (int i = tid; i < n; i += NTHREADS) {
-          long long o = o_start + i;
-          if (p.center) {
-            if (o < 0) o = -o;
-            if (o >= p.T_max) o = 2 * (p.T_max - 1) - o;
-          }
-          float v = 0.f;
-          if (o >= 0 && o < len) {
-            v = __ldg(row + o);
-            if (p.has_pre && o > 0) v = fmaf(-p.pre, __ldg(row + o - 1), v);
-          }
-          stage[i] = v;
+        float v = 0.f;
+        if (o >= 0 && o < len) {
+          v = __ldg(row + o);
+          if (p.has_pre && o > 0) v = fmaf(-p.pre, __ldg(row + o - 1), v);
         }
-        __syncthreads();
+        stage[i] = v;
       }
+      __syncthreads();
     }
 
-    // ---------------- per-warp: FFT of FPW frames ----------------
+    // ---------------- per-warp: FFT + |X|^2 of FPW frames ----------------
     float esum[PL::S];
 #pragma unroll
     for (int sub = 0; sub < PL::S; ++sub) {
@@ -341,32 +420,52 @@ __global__ void __launch_bounds__(NTHREADS) fused_frontend_kernel(const __grid_c
       const int t = t0 + tl;
       const int fo = tl * hop + shift;
       const float* fr = stage + fo;
-      const bool vec_ok = ((fo & 1) == 0);
-      stockham_pass<PL, PL::R1, 1, true>(Zw, nullptr, l, fr, wtab, win, vec_ok, staged_raw && p.has_pre, p.pre);
-      stockham_pass<PL, PL::R2, PL::R1, false>(Zw, tw2, l, nullptr, nullptr, 0, false, false, 0.f);
-      if (PL::R3 > 1)
-        stockham_pass<PL, (PL::R3 > 1 ? PL::R3 : 2), PL::R1 * PL::R2, false>(Zw, tw3, l, nullptr, nullptr, 0, false,
-                                                                             false, 0.f);
+      const bool pre_on = staged_raw && p.has_pre;
+      if ((fo & 1) == 0) {
+        if (pre_on) fft_frame<PL, true, true>(Zw, tw2, tw3, l, fr, wtab, win, p.pre);
+        else fft_frame<PL, true, false>(Zw, tw2, tw3, l, fr, wtab, win, 0.f);
+      } else {
+        if (pre_on) fft_frame<PL, false, true>(Zw, tw2, tw3, l, fr, wtab, win, p.pre);
+        else fft_frame<PL, false, false>(Zw, tw2, tw3, l, fr, wtab, win, 0.f);
+      }
       // real-FFT unpack: X[k] = E + W^k O, X[M-k] = conj(E - W^k O); the 1/2 lives in the window
-      const bool live = (t < flen);
+      constexpr int NI = (M / 2) / G + 1;
+      cpx za[NI], zb[NI];
+      const cpx* zl = Zw + padidx<Q>(l);
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int k = l + i * G;
+        if (i < NI - 1 || k <= M / 2) {
+          za[i] = (G % Q == 0) ? zl[i * (G + G / Q)] : Zw[padidx<Q>(k)];
+          zb[i] = Zw[padidx<Q>(k == 0 ? 0 : M - k)];
+        }
+      }
+      if (PL::ALIAS_P2) __syncwarp();  // every lane has its Z values: the buffer may now hold P2
+      const float live = (t < flen) ? 1.f : 0.f;
       float es = 0.f;
-      for (int k = l; k <= M / 2; k += G) {
-        const cpx a = Zw[padidx<PL::PADQ>(k)];
-        const cpx bb = Zw[padidx<PL::PADQ>(k == 0 ? 0 : M - k)];
-        const cpx w = wpost[k];
-        const cpx E = make_float2(a.x + bb.x, a.y - bb.y);
-        const cpx O = make_float2(a.y + bb.y, bb.x - a.x);
-        const cpx Tt = cmul(w, O);
-        const float xr = E.x + Tt.x, xi = E.y + Tt.y, yr = E.x - Tt.x, yi = E.y - Tt.y;
-        float pk = fmaf(xr, xr, xi * xi), pm = fmaf(yr, yr, yi * yi);
-        if (!live) { pk = 0.f; pm = 0.f; }
-        es += pk;
-        if (2 * k != M) es += pm;
-        if (p.mag) { pk = sqrtf(pk); pm = sqrtf(pm); }
-        P2[k * FPW + slot] = pk;
-        P2[(M - k) * FPW + slot] = pm;
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int k = l + i * G;
+        if (i < NI - 1 || k <= M / 2) {
+          const cpx a = za[i], bb = zb[i];
+          const cpx w = wpost[k];
+          const cpx E = make_float2(a.x + bb.x, a.y - bb.y);
+          const cpx O = make_float2(a.y + bb.y, bb.x - a.x);
+          const cpx Tt = cmul(w, O);
+          const float xr = E.x + Tt.x, xi = E.y + Tt.y, yr = E.x - Tt.x, yi = E.y - Tt.y;
+          float pk = fmaf(xr, xr, xi * xi) * live, pm = fmaf(yr, yr, yi * yi) * live;
+          es += pk;
+          if (2 * k != M) es += pm;
+          if (p.mag) { pk = sqrtf(pk); pm = sqrtf(pm); }
+          P2[k * FPW + slot] = pk;
+          P2[(M - k) * FPW + slot] = pm;
+        }
       }
       esum[sub] = es;
+      if (PL::ALIAS_P2) {
+        // the zero-weight padding taps of the mel filter read past bin K-1: keep that tail clean
+        for (int i = lane; i < (p.mel_tail + 2) * FPW; i += 32) P2[K * FPW + i] = 0.f;
+      }
       __syncwarp();
     }
 
@@ -402,7 +501,8 @@ __global__ void __launch_bounds__(NTHREADS) fused_frontend_kernel(const __grid_c
     // ---------------- banded mel + log + epilogue ----------------
     if (p.mel) {
       const int tA = t0 + warp * FPW;
-      const float fillv = (p.n_fmask > 0 || p.n_tmask > 0) ? (p.fill_dev ? *p.fill_dev : p.fill) : 0.f;
+      const bool any_mask = (p.n_fmask > 0 || p.n_tmask > 0);
+      const float fillv = any_mask ? (p.fill_dev ? *p.fill_dev : p.fill) : 0.f;
       bool tm[FPW];
 #pragma unroll
       for (int s = 0; s < FPW; ++s) {
@@ -413,19 +513,22 @@ __global__ void __launch_bounds__(NTHREADS) fused_frontend_kernel(const __grid_c
         }
       }
       const float2* P2v = reinterpret_cast<const float2*>(P2);
-      int wofs = 0;
+      int wofs = 0;  // in float4 units
       for (int rd = 0; rd < p.mel_rounds; ++rd) {
         const int d = rd * 32 + lane;
-        const int st = mstart[d];
-        const int nt = p.mel_taps[rd];
+        const float2* pp = P2v + mstart[d];
+        const int nq = p.mel_taps[rd] >> 2;
+        const float4* wp = mw4 + wofs + lane;
         float acc0 = 0.f, acc1 = 0.f;
-        for (int q = 0; q < nt; ++q) {
-          const float wgt = mw[wofs + q * 32 + lane];
-          const float2 pv = P2v[st + q];
-          acc0 = fmaf(wgt, pv.x, acc0);
-          acc1 = fmaf(wgt, pv.y, acc1);
+        for (int q = 0; q < nq; ++q) {
+          const float4 w4 = wp[q * 32];
+          const float2 p0 = pp[4 * q], p1 = pp[4 * q + 1], p2 = pp[4 * q + 2], p3 = pp[4 * q + 3];
+          acc0 = fmaf(w4.x, p0.x, acc0); acc1 = fmaf(w4.x, p0.y, acc1);
+          acc0 = fmaf(w4.y, p1.x, acc0); acc1 = fmaf(w4.y, p1.y, acc1);
+          acc0 = fmaf(w4.z, p2.x, acc0); acc1 = fmaf(w4.z, p2.y, acc1);
+          acc0 = fmaf(w4.w, p3.x, acc0); acc1 = fmaf(w4.w, p3.y, acc1);
         }
-        wofs += nt * 32;
+        wofs += nq * 32;
         if (d < D) {
           float v[FPW] = {acc0, acc1};
           bool fm = false;
@@ -450,22 +553,24 @@ __global__ void __launch_bounds__(NTHREADS) fused_frontend_kernel(const __grid_c
             if (t < p.F && !(p.skip_pad && t >= flen)) p.mel[(static_cast<long long>(b) * p.F + t) * D + d] = x;
           }
           if (p.stats) {
-            red[(warp * D + d) * 2 + 0] = s1;
-            red[(warp * D + d) * 2 + 1] = s2;
+            red[d * 2 + 0] = s1;
+            red[d * 2 + 1] = s2;
           }
         }
       }
     }
 
     // ---------------- per-utterance sums: CTA reduce, then one fp64 atomic per (dim, moment) ----------------
+    __syncthreads();  // all warps are done with this tile's staging buffer and have published `red`
     if (p.stats) {
-      __syncthreads();
       for (int i = tid; i < 2 * D; i += NTHREADS) {
         double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < NWARPS; ++w) s += red[w * D * 2 + i];
+        for (int w = 0; w < NWARPS; ++w)
+          s += *reinterpret_cast<const double*>(smem + p.sm_warp + w * p.sm_warp_bytes + p.sm_red_off + i * 8);
         atomicAdd(p.stats + static_cast<long long>(b) * D * 2 + i, s);
       }
+      __syncthreads();  // `red` lives in the FFT scratch: keep the next tile's FFT out until it is read
     }
   }
 

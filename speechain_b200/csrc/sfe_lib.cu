@@ -122,8 +122,7 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
   // window, pre-scaled by 1/2 (the real-FFT unpack then needs no halving)
   P.o_win = static_cast<int>(tab.size());
   for (int i = 0; i < win; ++i) tab.push_back(0.5f * cfg->window_host[i]);
-  tab.push_back(0.f);
-  tab.push_back(0.f);
+  for (int i = win; i < cfg->n_fft + 2; ++i) tab.push_back(0.f);  // zero padding up to the FFT length
   align4();
   // Stockham twiddles of pass 2 and 3: tw[(r-1)*T + j] = exp(-2 pi i r (j % P) / (P R))
   auto push_tw = [&](int R, int Pp) {
@@ -165,7 +164,6 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
       mst[d] = first;
       mnt[d] = last - first + 1;
     }
-    if (mnt[d] > P.mel_tail) P.mel_tail = mnt[d];
   }
   P.o_mstart = static_cast<int>(tab.size());
   for (int v : mst) {
@@ -178,32 +176,44 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
   for (int rd = 0; rd < P.mel_rounds; ++rd) {
     int nt = 0;
     for (int l = 0; l < 32; ++l) nt = mnt[rd * 32 + l] > nt ? mnt[rd * 32 + l] : nt;
+    nt = round_up(nt, 4);  // the kernel consumes taps four at a time (one float4 of weights per lane)
     P.mel_taps[rd] = nt;
-    for (int q = 0; q < nt; ++q)
-      for (int l = 0; l < 32; ++l) {
-        const int d = rd * 32 + l;
-        float w = 0.f;
-        if (d < D && q < mnt[d]) w = cfg->mel_weight_host[static_cast<size_t>(d) * K + mst[d] + q];
-        tab.push_back(w);
-      }
+    if (nt > P.mel_tail) P.mel_tail = nt;
+    for (int q4 = 0; q4 < nt / 4; ++q4)
+      for (int l = 0; l < 32; ++l)
+        for (int e = 0; e < 4; ++e) {
+          const int d = rd * 32 + l, q = q4 * 4 + e;
+          float w = 0.f;
+          if (d < D && q < mnt[d]) w = cfg->mel_weight_host[static_cast<size_t>(d) * K + mst[d] + q];
+          tab.push_back(w);
+        }
   }
   align4();
   P.tab_floats = static_cast<int>(tab.size());
 
   // ---- shared-memory carve-up ----
-  const int stage_floats = round_up((TILE_F - 1) * cfg->hop_length + win + 16, 4);
+  const bool alias = (fe->C == FPW);  // FftPlan::ALIAS_P2
+  const int stage_floats = round_up((TILE_F - 1) * cfg->hop_length + cfg->n_fft + 16, 4);
   const int z_bytes = round_up(fe->C * fe->MP * 8, 16);
   const int p2_bytes = round_up((K + P.mel_tail + 2) * FPW * 4, 16);
+  const int red_bytes = (D > 0 ? D : 1) * 2 * 8;
   int o = round_up(P.tab_floats * 4, 16);
   P.sm_stage = o;
   P.sm_stage_floats = stage_floats;
-  o += stage_floats * 4;
+  o += NSTAGE * stage_floats * 4;
   P.sm_warp = o;
-  P.sm_z_bytes = z_bytes;
-  P.sm_warp_bytes = z_bytes + p2_bytes;
+  int warp_bytes;
+  if (alias) {  // the power spectrum overwrites the FFT scratch; the partial sums sit behind it
+    P.sm_p2_off = 0;
+    P.sm_red_off = p2_bytes;
+    warp_bytes = z_bytes > p2_bytes + red_bytes ? z_bytes : p2_bytes + red_bytes;
+  } else {      // the partial sums overwrite the FFT scratch; the power spectrum sits behind it
+    P.sm_red_off = 0;
+    P.sm_p2_off = z_bytes > red_bytes ? z_bytes : round_up(red_bytes, 16);
+    warp_bytes = P.sm_p2_off + p2_bytes;
+  }
+  P.sm_warp_bytes = round_up(warp_bytes, 16);
   o += NWARPS * P.sm_warp_bytes;
-  P.sm_red = round_up(o, 16);
-  o = P.sm_red + NWARPS * (D > 0 ? D : 1) * 2 * 8;
   P.sm_bar = round_up(o, 16);
   pl->smem_bytes = P.sm_bar + 16;
   // standalone mel kernel: tables + per-warp P2
