@@ -105,8 +105,10 @@ int  sfe_plan_query(const sfe_plan* plan, int32_t* smem_bytes, int32_t* ctas_per
  *   lin        (B, F, n_fft/2+1) or NULL
  *   energy     (B, F) or NULL                (s2l.py:216-219,230-233)
  *   feat_len   (B,) int64 or NULL: len//hop+1 (s2l.py:201-212); wav_len is NOT mutated
- *   stats      (B, n_mels, 2) fp64 or NULL: sum and sum of squares of `mel` over valid frames
- *              (zeroed by this call); input of sfe_stats_finalize / sfe_normalize
+ *   stats      (B, n_mels, 2) int64 or NULL: FIXED-POINT sums of `mel` over valid frames, [..][0] =
+ *              sum x * 2^32, [..][1] = sum x^2 * 2^24 (exact, order independent -> bit-reproducible;
+ *              log-mel plans only; zeroed by this call); pass to sfe_stats_finalize /
+ *              sfe_normalize with stats_fixed = 1
  *   norm_mean/norm_std (n_mels,) or NULL: fused global normalisation (x-mean)/std in the
  *              epilogue (feat_norm.py:327-336, frozen/eval statistics)
  *   masks      NULL or SpecAugment masks applied in the epilogue (needs min over feat_len
@@ -115,7 +117,7 @@ int  sfe_plan_query(const sfe_plan* plan, int32_t* smem_bytes, int32_t* ctas_per
  *              sfe_normalize call synthesises them) */
 int sfe_frontend_forward(const sfe_plan* plan, const float* wav, int64_t wav_pitch,
                          const int64_t* wav_len, int32_t B, int64_t T_max, float* mel, float* lin,
-                         float* energy, int64_t* feat_len, double* stats, const float* norm_mean,
+                         float* energy, int64_t* feat_len, int64_t* stats, const float* norm_mean,
                          const float* norm_std, const sfe_masks* masks, int32_t skip_pad,
                          void* stream);
 
@@ -131,10 +133,12 @@ int sfe_stats_accumulate(const float* feat, const int64_t* feat_len, int32_t B, 
 
 /* Per-utterance mean and unbiased std (clamped) from the sums (feat_norm.py:115-133), and
  * the packed local sums for batch/global statistics (feat_norm.py:239-266):
+ *   stats       (B, D, 2): fp64 from sfe_stats_accumulate (stats_fixed = 0) or the fixed-point
+ *               sums of sfe_frontend_forward (stats_fixed = 1)
  *   mean, std   (B, D) fp32 (either may be NULL)
  *   packed      (2*D+1,) fp32 = [sum_i mean_i | sum_i std_i | B] or NULL */
-int sfe_stats_finalize(const double* stats, const int64_t* feat_len, int32_t B, int32_t D,
-                       float clamp, float* mean, float* std, float* packed, void* stream);
+int sfe_stats_finalize(const void* stats, int32_t stats_fixed, const int64_t* feat_len, int32_t B,
+                       int32_t D, float clamp, float* mean, float* std, float* packed, void* stream);
 
 /* Batch statistics from (all-reduced) packed sums and the running-average update of
  * register_mean_std_batch (feat_norm.py:250,265,483-508):
@@ -148,14 +152,16 @@ int sfe_running_update(const float* packed, int32_t D, float weight, int32_t fir
 /* (x - mean)/std, optional time warp, optional SpecAugment masking, one read + one write.
  * Replaces feat_norm.py:137-139 / 283-299 / 327-336 and specaug.py:111-124,202-204.
  *   src, dst   (B, F, D); may alias when warp is NULL/disabled
- *   stats      if non-NULL: per-utterance statistics are derived from these sums
+ *   stats      if non-NULL: per-utterance statistics are derived from these sums (encoding per
+ *              stats_fixed, see sfe_stats_finalize)
  *              (utterance mode) and written to mean_out/std_out (B, D) when non-NULL
  *   mean, std  if stats is NULL: vectors of shape (D,) when per_utt == 0 (batch/global
  *              mode) or (B, D) when per_utt != 0; either may be NULL (mean_norm/std_norm off)
  *   use_mean/use_std: the mean_norm / std_norm switches when stats != NULL
  *   pad_value  value of unwritten rows t >= feat_len when src_has_pad == 0 */
 int sfe_normalize(const float* src, float* dst, const int64_t* feat_len, int32_t B, int64_t F,
-                  int32_t D, const double* stats, float clamp, int32_t use_mean, int32_t use_std,
+                  int32_t D, const void* stats, int32_t stats_fixed, float clamp, int32_t use_mean,
+                  int32_t use_std,
                   const float* mean, const float* std, int32_t per_utt, float* mean_out,
                   float* std_out, int32_t src_has_pad, float pad_value, const sfe_warp* warp,
                   const sfe_masks* masks, void* stream);

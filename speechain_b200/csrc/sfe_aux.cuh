@@ -67,6 +67,20 @@ __global__ void __launch_bounds__(256) stats_accumulate_wide_kernel(const float*
   }
 }
 
+// sums -> (mean, unbiased std clamped).  Two encodings of the (B, D, 2) sums buffer: fp64 (written by
+// stats_accumulate_kernel) or the fused kernel's fixed point (sum x * 2^32, sum x^2 * 2^24).
+__device__ __forceinline__ void load_moments(const void* stats, int fixed, long long idx, double& s1, double& s2) {
+  if (fixed) {
+    const long long* q = reinterpret_cast<const long long*>(stats) + idx * 2;
+    s1 = static_cast<double>(q[0]) * (1.0 / 4294967296.0);
+    s2 = static_cast<double>(q[1]) * (1.0 / 16777216.0);
+  } else {
+    const double* q = reinterpret_cast<const double*>(stats) + idx * 2;
+    s1 = q[0];
+    s2 = q[1];
+  }
+}
+
 __device__ __forceinline__ void moments_to_mean_std(double s1, double s2, long long n, float clamp, float& mean,
                                                     float& sd) {
   const double dn = static_cast<double>(n);
@@ -81,16 +95,17 @@ __device__ __forceinline__ void moments_to_mean_std(double s1, double s2, long l
 }
 
 // mean/std (B, D) and packed [sum mean | sum std | B]                      feat_norm.py:115-133,239-266
-__global__ void stats_finalize_kernel(const double* __restrict__ stats, const long long* __restrict__ flen, int B, int D,
-                                      float clamp, float* __restrict__ mean, float* __restrict__ sd,
+__global__ void stats_finalize_kernel(const void* __restrict__ stats, int fixed, const long long* __restrict__ flen,
+                                      int B, int D, float clamp, float* __restrict__ mean, float* __restrict__ sd,
                                       float* __restrict__ packed) {
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= D) return;
   float sm = 0.f, ss = 0.f;
   for (int b = 0; b < B; ++b) {  // rank-local sums in utterance order, like curr_means.sum(dim=0)
     float m, s;
-    moments_to_mean_std(stats[(static_cast<long long>(b) * D + d) * 2], stats[(static_cast<long long>(b) * D + d) * 2 + 1],
-                        flen[b], clamp, m, s);
+    double s1, s2;
+    load_moments(stats, fixed, static_cast<long long>(b) * D + d, s1, s2);
+    moments_to_mean_std(s1, s2, flen[b], clamp, m, s);
     if (mean) mean[static_cast<long long>(b) * D + d] = m;
     if (sd) sd[static_cast<long long>(b) * D + d] = s;
     sm += m;
@@ -129,7 +144,8 @@ struct NormParams {
   int B;
   long long F;
   int D;
-  const double* stats;
+  const void* stats;
+  int stats_fixed;
   float clamp;
   int use_mean, use_std;
   const float* mean;
@@ -170,8 +186,9 @@ __global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ 
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float m = 0.f, s = 1.f;
     if (p.stats) {
-      moments_to_mean_std(p.stats[(static_cast<long long>(b) * D + d) * 2],
-                          p.stats[(static_cast<long long>(b) * D + d) * 2 + 1], p.flen[b], p.clamp, m, s);
+      double s1, s2;
+      load_moments(p.stats, p.stats_fixed, static_cast<long long>(b) * D + d, s1, s2);
+      moments_to_mean_std(s1, s2, p.flen[b], p.clamp, m, s);
       if (blockIdx.x == 0) {
         if (p.mean_out) p.mean_out[static_cast<long long>(b) * D + d] = m;
         if (p.std_out) p.std_out[static_cast<long long>(b) * D + d] = s;
@@ -333,9 +350,10 @@ struct L2MParams {
   long long n_rows;
   int K, D;
   int mel_log;
-  float mel_clamp, mel_div;
+  float mel_clamp, mel_div, mel_lmul;
   const float* tables;
-  int tab_floats, o_mstart, o_mw, mel_rounds, mel_tail;
+  int tab_floats, o_mstart, o_mout, o_mw, mel_rounds, mel_tail;
+  unsigned int mel_split_mask;
   int mel_taps[MAX_MEL_ROUNDS];
   int sm_warp, sm_warp_bytes;
 };
@@ -350,7 +368,8 @@ __global__ void __launch_bounds__(NTHREADS) linear2mel_kernel(const __grid_const
   for (int i = lane; i < p2_floats; i += 32) P2[i] = 0.f;
   __syncthreads();
   const int* mstart = reinterpret_cast<const int*>(tab + p.o_mstart);
-  const float4* mw4 = reinterpret_cast<const float4*>(tab + p.o_mw);
+  const int* mout = reinterpret_cast<const int*>(tab + p.o_mout);
+  const float2* mw2 = reinterpret_cast<const float2*>(tab + p.o_mw);
   const float2* P2v = reinterpret_cast<const float2*>(P2);
   const long long pairs = (p.n_rows + FPW - 1) / FPW;
   for (long long pr = static_cast<long long>(blockIdx.x) * NWARPS + warp; pr < pairs;
@@ -363,25 +382,29 @@ __global__ void __launch_bounds__(NTHREADS) linear2mel_kernel(const __grid_const
     }
     __syncwarp();
     int wofs = 0;
-    for (int rd = 0; rd < p.mel_rounds; ++rd) {
-      const int d = rd * 32 + lane;
-      const float2* pp = P2v + mstart[d];
-      const int nq = p.mel_taps[rd] >> 2;
-      const float4* wp = mw4 + wofs + lane;
+    for (int ph = 0; ph < p.mel_rounds; ++ph) {
+      const int st = mstart[ph * 32 + lane];
+      const int oinfo = mout[ph * 32 + lane];
+      const float2* pp = P2v + st;
+      const int n2 = p.mel_taps[ph] >> 1;
+      const float2* wp = mw2 + wofs + lane;
       float a0 = 0.f, a1 = 0.f;
-      for (int q = 0; q < nq; ++q) {
-        const float4 w4 = wp[q * 32];
-        const float2 p0 = pp[4 * q], p1 = pp[4 * q + 1], p2 = pp[4 * q + 2], p3 = pp[4 * q + 3];
-        a0 = fmaf(w4.x, p0.x, a0); a1 = fmaf(w4.x, p0.y, a1);
-        a0 = fmaf(w4.y, p1.x, a0); a1 = fmaf(w4.y, p1.y, a1);
-        a0 = fmaf(w4.z, p2.x, a0); a1 = fmaf(w4.z, p2.y, a1);
-        a0 = fmaf(w4.w, p3.x, a0); a1 = fmaf(w4.w, p3.y, a1);
+      for (int q = 0; q < n2; ++q) {
+        const float2 wq = wp[q * 32];
+        const float2 p0 = pp[2 * q], p1 = pp[2 * q + 1];
+        a0 = fmaf(wq.x, p0.x, a0); a1 = fmaf(wq.x, p0.y, a1);
+        a0 = fmaf(wq.y, p1.x, a0); a1 = fmaf(wq.y, p1.y, a1);
       }
-      wofs += nq * 32;
-      if (d < p.D) {
+      wofs += n2 * 32;
+      if ((p.mel_split_mask >> ph) & 1u) {
+        const float o0 = __shfl_xor_sync(0xffffffffu, a0, 1), o1 = __shfl_xor_sync(0xffffffffu, a1, 1);
+        if (oinfo & 0x10000) { a0 += o0; a1 += o1; }
+      }
+      if (oinfo >= 0) {
+        const int d = oinfo & 0xffff;
         if (p.mel_log) {
-          a0 = logf(fmaxf(a0, p.mel_clamp)) / p.mel_div;
-          a1 = logf(fmaxf(a1, p.mel_clamp)) / p.mel_div;
+          a0 = fast_log(a0, p.mel_clamp, p.mel_lmul);
+          a1 = fast_log(a1, p.mel_clamp, p.mel_lmul);
         }
         if (r0 < p.n_rows) p.mel[r0 * p.D + d] = a0;
         if (r0 + 1 < p.n_rows) p.mel[(r0 + 1) * p.D + d] = a1;

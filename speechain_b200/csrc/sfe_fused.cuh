@@ -27,7 +27,7 @@ constexpr int NWARPS = 8;
 constexpr int NTHREADS = NWARPS * 32;
 constexpr int FPW = 2;                    // frames per warp per tile
 constexpr int TILE_F = NWARPS * FPW;      // frames per tile
-constexpr int MAX_MEL_ROUNDS = 8;         // n_mels <= 256
+constexpr int MAX_MEL_ROUNDS = 16;        // phases of 32 filter units (n_mels <= 256)
 constexpr int NSTAGE = 2;                 // staging buffers
 
 struct FwdParams {
@@ -46,7 +46,7 @@ struct FwdParams {
   float* lin;
   float* energy;
   long long* feat_len;
-  double* stats;
+  unsigned long long* stats;   // fixed point: [..][0] = sum x * 2^32, [..][1] = sum x^2 * 2^24
   const float* norm_mean;
   const float* norm_std;
   // masks
@@ -65,18 +65,20 @@ struct FwdParams {
   float pre;
   int mag;
   int lin_log;
-  float lin_clamp, lin_div;
+  float lin_clamp, lin_div, lin_lmul;   // lin_lmul = ln2 / ln(base): log_b(x) = log2(x) * lmul
   int mel_log;
-  float mel_clamp, mel_div;
+  float mel_clamp, mel_div, mel_lmul;
   float pad_mel, pad_lin;
   // tables (device blob, float units) and shared-memory carve-up (byte offsets)
   const float* tables;
   int tab_floats;
-  int o_win, o_tw2, o_tw3, o_wpost, o_mstart, o_mw;  // float offsets into the blob
-  int mel_rounds;
-  int mel_taps[MAX_MEL_ROUNDS];                      // multiples of 4
-  int mel_tail;                                      // max taps of any round (P2 tail padding)
-  int sm_stage, sm_stage_floats, sm_warp, sm_warp_bytes, sm_p2_off, sm_red_off, sm_bar;
+  int o_win, o_tw2, o_tw3, o_wpost, o_mstart, o_mout, o_mw;  // float offsets into the blob
+  int mel_rounds;                                    // phases of 32 filter units
+  int mel_taps[MAX_MEL_ROUNDS];                      // taps per phase (multiples of 2)
+  unsigned int mel_split_mask;                       // phases that hold bins split over two lanes
+  int mel_tail;                                      // max taps of any phase (P2 tail padding)
+  int sm_stage, sm_stage_floats, sm_warp, sm_warp_bytes, sm_p2_off, sm_acc, sm_bar;
+  int nstage;  // 2: the bulk copy of tile i+1 runs under tile i; 1 (large n_fft): copy at the tile's own turn
   // scheduler
   unsigned int* sched;  // [0] next tile, [1] CTAs done
 };
@@ -129,6 +131,10 @@ struct FftPlan {
   // the power spectrum may overwrite the FFT scratch only if no later FFT of the tile needs it
   static constexpr bool ALIAS_P2 = (S == 1);
   static constexpr int MINB = (M_ == 256 || M_ == 240) ? 3 : ((M_ <= 512) ? 2 : 1);  // resident CTAs per SM aimed for
+  static constexpr int RL = (R3_ > 1) ? R3_ : R2_;               // radix of the last pass
+  // the last pass leaves Z[l + G*r] in register r of lane l: the real-FFT unpack then pairs k with M-k
+  // by one shuffle instead of a shared-memory round trip
+  static constexpr bool LASTREG = (M_ / RL == G_);
   static_assert(R1_ * R2_ * R3_ == M_, "radices must multiply to M");
   static_assert(C * S == FPW, "bad lane grouping");
 };
@@ -220,14 +226,40 @@ __device__ __forceinline__ void stockham_pass(cpx* __restrict__ Z, const cpx* __
   __syncwarp();
 }
 
+// Last pass with T == G: one butterfly per lane, result kept in registers (u[r] = Z[l + G*r]).
+template <class PL, int R, int P>
+__device__ __forceinline__ void stockham_last_reg(const cpx* __restrict__ Z, const cpx* __restrict__ tw, int l,
+                                                  cpx (&u)[R]) {
+  constexpr int M = PL::M, Q = PL::PADQ;
+  constexpr int T = M / R;
+  static_assert(T == PL::G, "register-resident last pass needs one butterfly per lane");
+  if (T % Q == 0) {
+    const cpx* zr = Z + padidx<Q>(l);
+#pragma unroll
+    for (int r = 0; r < R; ++r) u[r] = zr[r * (T + T / Q)];
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r) u[r] = Z[padidx<Q>(l + r * T)];
+  }
+  const cpx* twj = tw + l;
+#pragma unroll
+  for (int r = 1; r < R; ++r) u[r] = cmul(u[r], twj[(r - 1) * T]);
+  bfly<R>(u);
+}
+
+// all passes that go through the shared-memory scratch
 template <class PL, bool VEC, bool PRE>
 __device__ __forceinline__ void fft_frame(cpx* Zw, const cpx* tw2, const cpx* tw3, int l, const float* fr,
                                           const float* wtab, int win, float pre) {
   stockham_pass<PL, PL::R1, 1, true, VEC, PRE>(Zw, nullptr, l, fr, wtab, win, pre);
-  stockham_pass<PL, PL::R2, PL::R1, false, false, false>(Zw, tw2, l, nullptr, nullptr, 0, 0.f);
-  if (PL::R3 > 1)
-    stockham_pass<PL, (PL::R3 > 1 ? PL::R3 : 2), PL::R1 * PL::R2, false, false, false>(Zw, tw3, l, nullptr, nullptr, 0,
-                                                                                       0.f);
+  if (PL::R3 > 1) {
+    stockham_pass<PL, PL::R2, PL::R1, false, false, false>(Zw, tw2, l, nullptr, nullptr, 0, 0.f);
+    if (!PL::LASTREG)
+      stockham_pass<PL, (PL::R3 > 1 ? PL::R3 : 2), PL::R1 * PL::R2, false, false, false>(Zw, tw3, l, nullptr, nullptr,
+                                                                                         0, 0.f);
+  } else if (!PL::LASTREG) {
+    stockham_pass<PL, PL::R2, PL::R1, false, false, false>(Zw, tw2, l, nullptr, nullptr, 0, 0.f);
+  }
 }
 
 // per-tile metadata published by thread 0 one tile ahead
@@ -243,7 +275,12 @@ enum { TILE_PAD = 0, TILE_BULK = 1, TILE_EDGE = 2 };
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <class PL>
+// log_b(max(x, clamp)) through the SFU: MUFU.LG2 is accurate to 2^-22 absolute on [0.5, 2] and 2 ulp
+// elsewhere — three orders of magnitude inside the 1e-4 / 1e-3 tolerance of the features — and costs 3
+// instructions where logf + an IEEE division cost ~45.
+__device__ __forceinline__ float fast_log(float x, float clampv, float lmul) { return __log2f(fmaxf(x, clampv)) * lmul; }
+
+template <class PL, bool PRE>
 __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int M = PL::M, G = PL::G, Q = PL::PADQ;
@@ -254,7 +291,6 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
   unsigned char* wbase = smem + p.sm_warp + warp * p.sm_warp_bytes;
   cpx* Zw = reinterpret_cast<cpx*>(wbase) + g * PL::MP;
   float* P2 = reinterpret_cast<float*>(wbase + p.sm_p2_off);    // [k][FPW] interleaved
-  double* red = reinterpret_cast<double*>(wbase + p.sm_red_off);  // this warp's [D][2] partial sums
   unsigned long long* barp = reinterpret_cast<unsigned long long*>(smem + p.sm_bar);
   __shared__ TileInfo s_info[NSTAGE];
 
@@ -264,9 +300,11 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
     float4* dst = reinterpret_cast<float4*>(tab);
     for (int i = tid; i < p.tab_floats / 4; i += NTHREADS) dst[i] = __ldg(src + i);
     float* st = reinterpret_cast<float*>(smem + p.sm_stage);
-    for (int i = tid; i < NSTAGE * p.sm_stage_floats; i += NTHREADS) st[i] = 0.f;
+    for (int i = tid; i < p.nstage * p.sm_stage_floats; i += NTHREADS) st[i] = 0.f;
     float* wz = reinterpret_cast<float*>(wbase);
     for (int i = lane; i < p.sm_warp_bytes / 4; i += 32) wz[i] = 0.f;
+    unsigned long long* acc = reinterpret_cast<unsigned long long*>(smem + p.sm_acc);
+    for (int i = tid; i < NSTAGE * 2 * p.D; i += NTHREADS) acc[i] = 0ull;
   }
   const uint32_t bar0 = smem_u32(barp);
   if (tid == 0) {
@@ -281,13 +319,15 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
   const cpx* tw3 = reinterpret_cast<const cpx*>(tab + p.o_tw3);
   const cpx* wpost = reinterpret_cast<const cpx*>(tab + p.o_wpost);
   const int* mstart = reinterpret_cast<const int*>(tab + p.o_mstart);
-  const float4* mw4 = reinterpret_cast<const float4*>(tab + p.o_mw);
+  const int* mout = reinterpret_cast<const int*>(tab + p.o_mout);
+  const float2* mw2 = reinterpret_cast<const float2*>(tab + p.o_mw);
   const int hop = p.hop, win = p.win, D = p.D, K = p.K;
   const bool base_aligned = ((reinterpret_cast<uintptr_t>(p.wav) & 15) == 0);
-  const int pre1 = p.has_pre ? 1 : 0;
+  constexpr int pre1 = PRE ? 1 : 0;
+  constexpr int EDGE_SHIFT = 4;  // edge tiles leave room for the (unused) predecessor sample
 
   // thread 0: describe tile `tile`, and if it is an interior tile start its bulk copy into `buf`
-  auto publish = [&](int tile, int buf) {
+  auto publish = [&](int tile, int buf, bool start_copy) {
     TileInfo ti;
     ti.tile = tile;
     ti.kind = TILE_PAD;
@@ -314,11 +354,13 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
         if (interior) {
           ti.kind = TILE_BULK;
           ti.shift = static_cast<int>(gi - ga) + pre1;
-          const uint32_t bytes = static_cast<uint32_t>((ge - ga) * 4);
-          const uint32_t bar = bar0 + 8 * buf;
-          fence_proxy_async();
-          mbar_expect_tx(bar, bytes);
-          bulk_g2s(smem_u32(smem + p.sm_stage + buf * p.sm_stage_floats * 4), p.wav + ga, bytes, bar);
+          if (start_copy) {
+            const uint32_t bytes = static_cast<uint32_t>((ge - ga) * 4);
+            const uint32_t bar = bar0 + 8 * buf;
+            fence_proxy_async();
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(smem_u32(smem + p.sm_stage + buf * p.sm_stage_floats * 4), p.wav + ga, bytes, bar);
+          }
         } else {
           ti.kind = TILE_EDGE;
         }
@@ -333,7 +375,7 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
   if (tid == 0) {
     const int first = static_cast<int>(atomicAdd(p.sched, 1u));
     claimed = atomicAdd(p.sched, 1u);
-    publish(first, 0);
+    publish(first, 0, true);
   }
   __syncthreads();
 
@@ -347,12 +389,13 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
     if (tid == 0) {
       const int next = static_cast<int>(claimed);
       claimed = (next < p.num_tiles) ? atomicAdd(p.sched, 1u) : static_cast<unsigned int>(next);
-      publish(next, buf ^ 1);
+      publish(next, buf ^ 1, p.nstage == 2);
     }
     const int b = ti.b, t0 = ti.t0, flen = ti.flen;
     const long long len = ti.len;
     const int nfr = min(TILE_F, p.F - t0);  // frames of this tile that exist in the output
-    float* stage = reinterpret_cast<float*>(smem + p.sm_stage) + buf * p.sm_stage_floats;
+    const int sbuf = (p.nstage == 2) ? buf : 0;
+    float* stage = reinterpret_cast<float*>(smem + p.sm_stage) + sbuf * p.sm_stage_floats;
 
     if (ti.kind == TILE_PAD) {
       // ---------------- pad tile: nothing to transform ----------------
@@ -384,11 +427,23 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
     }
 
     // ---------------- samples of this tile ----------------
-    int shift = ti.shift;
+    const int shift = (ti.kind == TILE_BULK) ? ti.shift : EDGE_SHIFT;
     const bool staged_raw = (ti.kind == TILE_BULK);
     if (staged_raw) {
-      mbar_wait(bar0 + 8 * buf, parity[buf]);
-      parity[buf] ^= 1u;
+      if (p.nstage == 1 && it > 0 && tid == 0) {
+        // single staging buffer: the copy could not start before the previous tile released it
+        const long long o_start = static_cast<long long>(t0) * hop + p.off;
+        const long long o_end = o_start + static_cast<long long>(TILE_F - 1) * hop + win;
+        const long long gi = static_cast<long long>(b) * p.pitch + o_start - pre1;
+        const long long ga = gi & ~3LL;
+        const long long ge = (static_cast<long long>(b) * p.pitch + o_end + 3) & ~3LL;
+        const uint32_t bytes = static_cast<uint32_t>((ge - ga) * 4);
+        fence_proxy_async();
+        mbar_expect_tx(bar0, bytes);
+        bulk_g2s(smem_u32(stage), p.wav + ga, bytes, bar0);
+      }
+      mbar_wait(bar0 + 8 * sbuf, parity[sbuf]);
+      parity[sbuf] ^= 1u;
     } else {
       // edge tile: explicit gather with batch-level reflection, zero beyond the length and
       // pre-emphasis applied here (staging then holds the final samples)
@@ -406,7 +461,7 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
           v = __ldg(row + o);
           if (p.has_pre && o > 0) v = fmaf(-p.pre, __ldg(row + o - 1), v);
         }
-        stage[i] = v;
+        stage[EDGE_SHIFT + i] = v;
       }
       __syncthreads();
     }
@@ -420,27 +475,40 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
       const int t = t0 + tl;
       const int fo = tl * hop + shift;
       const float* fr = stage + fo;
-      const bool pre_on = staged_raw && p.has_pre;
-      if ((fo & 1) == 0) {
-        if (pre_on) fft_frame<PL, true, true>(Zw, tw2, tw3, l, fr, wtab, win, p.pre);
-        else fft_frame<PL, true, false>(Zw, tw2, tw3, l, fr, wtab, win, 0.f);
-      } else {
-        if (pre_on) fft_frame<PL, false, true>(Zw, tw2, tw3, l, fr, wtab, win, p.pre);
-        else fft_frame<PL, false, false>(Zw, tw2, tw3, l, fr, wtab, win, 0.f);
-      }
-      // real-FFT unpack: X[k] = E + W^k O, X[M-k] = conj(E - W^k O); the 1/2 lives in the window
-      constexpr int NI = (M / 2) / G + 1;
+      // edge tiles were pre-emphasised by the gather: same code path with a zero coefficient
+      const float pre = (PRE && staged_raw) ? p.pre : 0.f;
+      if ((fo & 1) == 0) fft_frame<PL, true, PRE>(Zw, tw2, tw3, l, fr, wtab, win, pre);
+      else fft_frame<PL, false, PRE>(Zw, tw2, tw3, l, fr, wtab, win, pre);
+
+      // real-FFT unpack: X[k] = E + W^k O, X[M-k] = conj(E - W^k O); the 1/2 lives in the window.
+      // Lane l owns k = l + G*i (i <= NI-1) and its mirror M-k.
+      constexpr int RL = PL::RL;
+      constexpr int NI = PL::LASTREG ? (RL / 2 + 1) : ((M / 2) / G + 1);
       cpx za[NI], zb[NI];
-      const cpx* zl = Zw + padidx<Q>(l);
+      if constexpr (PL::LASTREG) {
+        cpx u[RL];
+        stockham_last_reg<PL, RL, M / RL>(Zw, (PL::R3 > 1) ? tw3 : tw2, l, u);
+        const int src = (G - l) & (G - 1);
 #pragma unroll
-      for (int i = 0; i < NI; ++i) {
-        const int k = l + i * G;
-        if (i < NI - 1 || k <= M / 2) {
-          za[i] = (G % Q == 0) ? zl[i * (G + G / Q)] : Zw[padidx<Q>(k)];
-          zb[i] = Zw[padidx<Q>(k == 0 ? 0 : M - k)];
+        for (int i = 0; i < NI; ++i) {
+          za[i] = u[i];
+          const float bx = __shfl_sync(0xffffffffu, u[RL - 1 - i].x, src, G);
+          const float by = __shfl_sync(0xffffffffu, u[RL - 1 - i].y, src, G);
+          zb[i] = (l == 0) ? u[(RL - i) % RL] : make_float2(bx, by);
         }
+        // (the shuffles are convergence points: every lane has finished reading the scratch)
+      } else {
+        const cpx* zl = Zw + padidx<Q>(l);
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          const int k = l + i * G;
+          if (i < NI - 1 || k <= M / 2) {
+            za[i] = (G % Q == 0) ? zl[i * (G + G / Q)] : Zw[padidx<Q>(k)];
+            zb[i] = Zw[padidx<Q>(k == 0 ? 0 : M - k)];
+          }
+        }
+        if (PL::ALIAS_P2) __syncwarp();  // every lane has its Z values: the buffer may now hold P2
       }
-      if (PL::ALIAS_P2) __syncwarp();  // every lane has its Z values: the buffer may now hold P2
       const float live = (t < flen) ? 1.f : 0.f;
       float es = 0.f;
 #pragma unroll
@@ -491,7 +559,7 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
           float* dst = p.lin + (static_cast<long long>(b) * p.F + t) * K;
           for (int k = lane; k < K; k += 32) {
             float v = P2[k * FPW + slot];
-            if (p.lin_log) v = logf(fmaxf(v, p.lin_clamp)) / p.lin_div;
+            if (p.lin_log) v = fast_log(v, p.lin_clamp, p.lin_lmul);
             dst[k] = v;
           }
         }
@@ -499,78 +567,89 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
     }
 
     // ---------------- banded mel + log + epilogue ----------------
+    // Filter *units* (a mel bin, or half of a wide one) are spread over phases of 32 lanes with similar
+    // tap counts; a lane walks its unit two taps at a time over both frames of the warp.
     if (p.mel) {
       const int tA = t0 + warp * FPW;
-      const bool any_mask = (p.n_fmask > 0 || p.n_tmask > 0);
-      const float fillv = any_mask ? (p.fill_dev ? *p.fill_dev : p.fill) : 0.f;
-      bool tm[FPW];
-#pragma unroll
-      for (int s = 0; s < FPW; ++s) {
-        tm[s] = false;
+      const bool fancy = (p.norm_mean != nullptr) || (p.norm_std != nullptr) || (p.n_fmask > 0) || (p.n_tmask > 0);
+      const float2* P2v = reinterpret_cast<const float2*>(P2);
+      float* mel_row = p.mel + (static_cast<long long>(b) * p.F + tA) * D;
+      const bool w0 = (tA < p.F) && !(p.skip_pad && tA >= flen);          // row tA is written
+      const bool w1 = (tA + 1 < p.F) && !(p.skip_pad && tA + 1 >= flen);  // row tA+1 is written
+      const float v0 = (tA < flen) ? 1.f : 0.f, v1 = (tA + 1 < flen) ? 1.f : 0.f;  // rows that count for the sums
+      unsigned long long* sacc = reinterpret_cast<unsigned long long*>(smem + p.sm_acc) + buf * 2 * D;
+      float fillv = 0.f;
+      bool tm0 = false, tm1 = false;
+      if (fancy) {
+        fillv = p.fill_dev ? *p.fill_dev : p.fill;
         for (int q = 0; q < p.n_tmask; ++q) {
           const int ps = p.tpos[b * p.n_tmask + q], ln = p.tlen[b * p.n_tmask + q];
-          tm[s] |= (tA + s >= ps) && (tA + s < ps + ln);
+          tm0 |= (tA >= ps) && (tA < ps + ln);
+          tm1 |= (tA + 1 >= ps) && (tA + 1 < ps + ln);
         }
       }
-      const float2* P2v = reinterpret_cast<const float2*>(P2);
-      int wofs = 0;  // in float4 units
-      for (int rd = 0; rd < p.mel_rounds; ++rd) {
-        const int d = rd * 32 + lane;
-        const float2* pp = P2v + mstart[d];
-        const int nq = p.mel_taps[rd] >> 2;
-        const float4* wp = mw4 + wofs + lane;
+      int wofs = 0;  // in float2 units
+      for (int ph = 0; ph < p.mel_rounds; ++ph) {
+        const int st = mstart[ph * 32 + lane];
+        const int oinfo = mout[ph * 32 + lane];
+        const float2* pp = P2v + st;
+        const int n2 = p.mel_taps[ph] >> 1;
+        const float2* wp = mw2 + wofs + lane;
         float acc0 = 0.f, acc1 = 0.f;
-        for (int q = 0; q < nq; ++q) {
-          const float4 w4 = wp[q * 32];
-          const float2 p0 = pp[4 * q], p1 = pp[4 * q + 1], p2 = pp[4 * q + 2], p3 = pp[4 * q + 3];
-          acc0 = fmaf(w4.x, p0.x, acc0); acc1 = fmaf(w4.x, p0.y, acc1);
-          acc0 = fmaf(w4.y, p1.x, acc0); acc1 = fmaf(w4.y, p1.y, acc1);
-          acc0 = fmaf(w4.z, p2.x, acc0); acc1 = fmaf(w4.z, p2.y, acc1);
-          acc0 = fmaf(w4.w, p3.x, acc0); acc1 = fmaf(w4.w, p3.y, acc1);
+#pragma unroll 2
+        for (int q = 0; q < n2; ++q) {
+          const float2 wq = wp[q * 32];
+          const float2 p0 = pp[2 * q], p1 = pp[2 * q + 1];
+          acc0 = fmaf(wq.x, p0.x, acc0); acc1 = fmaf(wq.x, p0.y, acc1);
+          acc0 = fmaf(wq.y, p1.x, acc0); acc1 = fmaf(wq.y, p1.y, acc1);
         }
-        wofs += nq * 32;
-        if (d < D) {
-          float v[FPW] = {acc0, acc1};
-          bool fm = false;
-          for (int q = 0; q < p.n_fmask; ++q) {
-            const int ps = p.fpos[b * p.n_fmask + q], ln = p.flen[b * p.n_fmask + q];
-            fm |= (d >= ps) && (d < ps + ln);
-          }
-          double s1 = 0.0, s2 = 0.0;
-#pragma unroll
-          for (int s = 0; s < FPW; ++s) {
-            const int t = tA + s;
-            float x = v[s];
-            if (p.mel_log) x = logf(fmaxf(x, p.mel_clamp)) / p.mel_div;
-            if (p.stats && t < flen) {
-              const double xd = static_cast<double>(x);
-              s1 += xd;
-              s2 = fma(xd, xd, s2);
-            }
-            if (p.norm_mean) x -= p.norm_mean[d];
-            if (p.norm_std) x /= p.norm_std[d];
-            if (fm || tm[s]) x = fillv;
-            if (t < p.F && !(p.skip_pad && t >= flen)) p.mel[(static_cast<long long>(b) * p.F + t) * D + d] = x;
+        wofs += n2 * 32;
+        if ((p.mel_split_mask >> ph) & 1u) {  // bins wider than a unit: add the partner lane's half
+          const float o0 = __shfl_xor_sync(0xffffffffu, acc0, 1), o1 = __shfl_xor_sync(0xffffffffu, acc1, 1);
+          if (oinfo & 0x10000) { acc0 += o0; acc1 += o1; }
+        }
+        if (oinfo >= 0) {  // this lane publishes bin d
+          const int d = oinfo & 0xffff;
+          float x0 = acc0, x1 = acc1;
+          if (p.mel_log) {
+            x0 = fast_log(x0, p.mel_clamp, p.mel_lmul);
+            x1 = fast_log(x1, p.mel_clamp, p.mel_lmul);
           }
           if (p.stats) {
-            red[d * 2 + 0] = s1;
-            red[d * 2 + 1] = s2;
+            // pair sums in fp32, then exact order-independent fixed-point accumulation
+            const float s1 = x0 * v0 + x1 * v1;
+            const float s2 = fmaf(x0 * v0, x0, x1 * v1 * x1);
+            atomicAdd(sacc + 2 * d, static_cast<unsigned long long>(__float2ll_rn(s1 * 4294967296.f)));
+            atomicAdd(sacc + 2 * d + 1, static_cast<unsigned long long>(__float2ll_rn(s2 * 16777216.f)));
           }
+          if (fancy) {
+            if (p.norm_mean) { const float nm = p.norm_mean[d]; x0 -= nm; x1 -= nm; }
+            if (p.norm_std) { const float ns = p.norm_std[d]; x0 /= ns; x1 /= ns; }
+            bool fm = false;
+            for (int q = 0; q < p.n_fmask; ++q) {
+              const int ps = p.fpos[b * p.n_fmask + q], ln = p.flen[b * p.n_fmask + q];
+              fm |= (d >= ps) && (d < ps + ln);
+            }
+            if (fm || tm0) x0 = fillv;
+            if (fm || tm1) x1 = fillv;
+          }
+          if (w0) mel_row[d] = x0;
+          if (w1) mel_row[D + d] = x1;
         }
       }
     }
 
-    // ---------------- per-utterance sums: CTA reduce, then one fp64 atomic per (dim, moment) ----------------
-    __syncthreads();  // all warps are done with this tile's staging buffer and have published `red`
+    // ---------------- end of tile ----------------
+    __syncthreads();  // every warp is done with this tile's staging buffer and its sums are in smem
     if (p.stats) {
+      unsigned long long* sacc = reinterpret_cast<unsigned long long*>(smem + p.sm_acc) + buf * 2 * D;
       for (int i = tid; i < 2 * D; i += NTHREADS) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < NWARPS; ++w)
-          s += *reinterpret_cast<const double*>(smem + p.sm_warp + w * p.sm_warp_bytes + p.sm_red_off + i * 8);
-        atomicAdd(p.stats + static_cast<long long>(b) * D * 2 + i, s);
+        const unsigned long long v = sacc[i];
+        if (v != 0ull) {
+          sacc[i] = 0ull;  // this buffer is used again two tiles from now, behind the next barrier
+          atomicAdd(p.stats + static_cast<long long>(b) * D * 2 + i, v);
+        }
       }
-      __syncthreads();  // `red` lives in the FFT scratch: keep the next tile's FFT out until it is read
     }
   }
 

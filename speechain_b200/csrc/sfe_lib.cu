@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -33,13 +34,13 @@ typedef void (*fused_fn)(const FwdParams);
 
 struct FftEntry {
   int n_fft, M, G, R1, R2, R3, MP, C;
-  fused_fn fn;
+  fused_fn fn[2];  // [0] no pre-emphasis, [1] pre-emphasis applied while loading
 };
 
 template <int M, int G, int R1, int R2, int R3>
 static FftEntry make_entry() {
   typedef FftPlan<M, G, R1, R2, R3> PL;
-  return FftEntry{2 * M, M, G, R1, R2, R3, PL::MP, PL::C, &fused_frontend_kernel<PL>};
+  return FftEntry{2 * M, M, G, R1, R2, R3, PL::MP, PL::C, {&fused_frontend_kernel<PL, false>, &fused_frontend_kernel<PL, true>}};
 }
 
 static const std::vector<FftEntry>& registry() {
@@ -148,10 +149,12 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
     tab.push_back(static_cast<float>(sin(a)));
   }
   align4();
-  // banded mel filter: per bin first tap + taps, lane-major weights per round of 32 bins
-  P.mel_rounds = (D + 31) / 32;
+  // banded mel filter -> filter *units* (a bin, or half of a wide bin) packed into phases of 32 lanes
+  // with similar tap counts; weights lane-major, two taps per float2
   P.mel_tail = 0;
-  std::vector<int> mst(P.mel_rounds * 32, 0), mnt(P.mel_rounds * 32, 0);
+  P.mel_split_mask = 0;
+  std::vector<int> mst(D > 0 ? D : 1, 0), mnt(D > 0 ? D : 1, 0);
+  int maxn = 0;
   for (int d = 0; d < D; ++d) {
     const float* row = cfg->mel_weight_host + static_cast<size_t>(d) * K;
     int first = -1, last = -1;
@@ -164,58 +167,104 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
       mst[d] = first;
       mnt[d] = last - first + 1;
     }
+    if (mnt[d] > maxn) maxn = mnt[d];
   }
-  P.o_mstart = static_cast<int>(tab.size());
-  for (int v : mst) {
+  const int ucap = maxn > 8 ? (maxn + 1) / 2 : maxn;  // taps a single lane takes at most
+  struct Item { int d, size; bool pair; };
+  std::vector<Item> items;
+  for (int d = 0; d < D; ++d) {
+    const bool pair = mnt[d] > ucap;
+    items.push_back(Item{d, pair ? (mnt[d] + 1) / 2 : mnt[d], pair});
+  }
+  std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.size > b.size; });
+  struct Lane { int start, ntaps, d, out; };  // out: -1 none, else d | combine flag
+  std::vector<std::vector<Lane>> phases;
+  for (const Item& it : items) {
+    if (phases.empty()) phases.emplace_back();
+    if (it.pair && (phases.back().size() & 1)) phases.back().push_back(Lane{0, 0, -1, -1});
+    if (phases.back().size() + (it.pair ? 2 : 1) > 32) phases.emplace_back();
+    std::vector<Lane>& ph = phases.back();
+    if (it.pair) {
+      const int n1 = (mnt[it.d] + 1) / 2;
+      ph.push_back(Lane{mst[it.d], n1, it.d, it.d | 0x10000});
+      ph.push_back(Lane{mst[it.d] + n1, mnt[it.d] - n1, it.d, -1});
+      P.mel_split_mask |= 1u << (phases.size() - 1);
+    } else {
+      ph.push_back(Lane{mst[it.d], mnt[it.d], it.d, it.d});
+    }
+  }
+  if (static_cast<int>(phases.size()) > MAX_MEL_ROUNDS) {
+    delete pl;
+    return fail(SFE_ERR_BAD_CONFIG, "mel filterbank needs too many filter phases");
+  }
+  P.mel_rounds = static_cast<int>(phases.size());
+  for (auto& ph : phases)
+    while (ph.size() < 32) ph.push_back(Lane{0, 0, -1, -1});
+  auto push_int = [&](int v) {
     float f;
     memcpy(&f, &v, 4);
     tab.push_back(f);
-  }
+  };
+  P.o_mstart = static_cast<int>(tab.size());
+  for (auto& ph : phases)
+    for (auto& ln : ph) push_int(ln.start);
+  align4();
+  P.o_mout = static_cast<int>(tab.size());
+  for (auto& ph : phases)
+    for (auto& ln : ph) push_int(ln.out);
   align4();
   P.o_mw = static_cast<int>(tab.size());
-  for (int rd = 0; rd < P.mel_rounds; ++rd) {
+  for (size_t i = 0; i < phases.size(); ++i) {
     int nt = 0;
-    for (int l = 0; l < 32; ++l) nt = mnt[rd * 32 + l] > nt ? mnt[rd * 32 + l] : nt;
-    nt = round_up(nt, 4);  // the kernel consumes taps four at a time (one float4 of weights per lane)
-    P.mel_taps[rd] = nt;
+    for (auto& ln : phases[i]) nt = ln.ntaps > nt ? ln.ntaps : nt;
+    nt = round_up(nt, 2);
+    P.mel_taps[i] = nt;
     if (nt > P.mel_tail) P.mel_tail = nt;
-    for (int q4 = 0; q4 < nt / 4; ++q4)
-      for (int l = 0; l < 32; ++l)
-        for (int e = 0; e < 4; ++e) {
-          const int d = rd * 32 + l, q = q4 * 4 + e;
-          float w = 0.f;
-          if (d < D && q < mnt[d]) w = cfg->mel_weight_host[static_cast<size_t>(d) * K + mst[d] + q];
-          tab.push_back(w);
+    for (int q2 = 0; q2 < nt / 2; ++q2)
+      for (auto& ln : phases[i])
+        for (int e = 0; e < 2; ++e) {
+          const int q = q2 * 2 + e;
+          tab.push_back((ln.d >= 0 && q < ln.ntaps) ? cfg->mel_weight_host[static_cast<size_t>(ln.d) * K + ln.start + q] : 0.f);
         }
   }
   align4();
   P.tab_floats = static_cast<int>(tab.size());
 
-  // ---- shared-memory carve-up ----
+  // ---- shared-memory carve-up (two staging buffers if they fit, else one) ----
   const bool alias = (fe->C == FPW);  // FftPlan::ALIAS_P2
   const int stage_floats = round_up((TILE_F - 1) * cfg->hop_length + cfg->n_fft + 16, 4);
   const int z_bytes = round_up(fe->C * fe->MP * 8, 16);
   const int p2_bytes = round_up((K + P.mel_tail + 2) * FPW * 4, 16);
-  const int red_bytes = (D > 0 ? D : 1) * 2 * 8;
-  int o = round_up(P.tab_floats * 4, 16);
-  P.sm_stage = o;
-  P.sm_stage_floats = stage_floats;
-  o += NSTAGE * stage_floats * 4;
-  P.sm_warp = o;
-  int warp_bytes;
-  if (alias) {  // the power spectrum overwrites the FFT scratch; the partial sums sit behind it
-    P.sm_p2_off = 0;
-    P.sm_red_off = p2_bytes;
-    warp_bytes = z_bytes > p2_bytes + red_bytes ? z_bytes : p2_bytes + red_bytes;
-  } else {      // the partial sums overwrite the FFT scratch; the power spectrum sits behind it
-    P.sm_red_off = 0;
-    P.sm_p2_off = z_bytes > red_bytes ? z_bytes : round_up(red_bytes, 16);
-    warp_bytes = P.sm_p2_off + p2_bytes;
+  int smem_limit = 227 * 1024;
+  {
+    int dev = 0;
+    cudaDeviceProp pr;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&pr, dev) == cudaSuccess)
+      smem_limit = static_cast<int>(pr.sharedMemPerBlockOptin);
   }
-  P.sm_warp_bytes = round_up(warp_bytes, 16);
-  o += NWARPS * P.sm_warp_bytes;
-  P.sm_bar = round_up(o, 16);
-  pl->smem_bytes = P.sm_bar + 16;
+  for (P.nstage = NSTAGE; P.nstage >= 1; --P.nstage) {
+    int o = round_up(P.tab_floats * 4, 16);
+    P.sm_stage = o;
+    P.sm_stage_floats = stage_floats;
+    o += P.nstage * stage_floats * 4;
+    P.sm_warp = o;
+    int warp_bytes;
+    if (alias) {  // the power spectrum overwrites the FFT scratch
+      P.sm_p2_off = 0;
+      warp_bytes = z_bytes > p2_bytes ? z_bytes : p2_bytes;
+    } else {      // the power spectrum sits behind the FFT scratch
+      P.sm_p2_off = z_bytes;
+      warp_bytes = z_bytes + p2_bytes;
+    }
+    P.sm_warp_bytes = round_up(warp_bytes, 16);
+    o += NWARPS * P.sm_warp_bytes;
+    P.sm_acc = round_up(o, 16);  // [NSTAGE][D][2] fixed-point sums of the tile in flight
+    o = P.sm_acc + NSTAGE * (D > 0 ? D : 1) * 2 * 8;
+    P.sm_bar = round_up(o, 16);
+    pl->smem_bytes = P.sm_bar + 16;
+    if (pl->smem_bytes <= smem_limit) break;
+  }
+  if (P.nstage < 1) P.nstage = 1;
   // standalone mel kernel: tables + per-warp P2
   pl->l2m_sm_warp = round_up(P.tab_floats * 4, 16);
   pl->l2m_warp_bytes = p2_bytes;
@@ -235,9 +284,11 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
   P.lin_log = cfg->lin_logging ? 1 : 0;
   P.lin_clamp = cfg->lin_clamp;
   P.lin_div = cfg->lin_log_div;
+  P.lin_lmul = static_cast<float>(0.69314718055994530942 / static_cast<double>(cfg->lin_log_div));
   P.mel_log = cfg->mel_logging ? 1 : 0;
   P.mel_clamp = cfg->mel_clamp;
   P.mel_div = cfg->mel_log_div;
+  P.mel_lmul = static_cast<float>(0.69314718055994530942 / static_cast<double>(cfg->mel_log_div));
   P.pad_mel = cfg->mel_logging ? logf(cfg->mel_clamp) / cfg->mel_log_div : 0.f;
   P.pad_lin = cfg->lin_logging ? logf(cfg->lin_clamp) / cfg->lin_log_div : 0.f;
 
@@ -255,15 +306,16 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
   if (e == cudaSuccess) e = cudaMemset(pl->d_sched, 0, 2 * sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMalloc(&pl->d_acc, sizeof(double));
   if (e == cudaSuccess) e = cudaMemset(pl->d_acc, 0, sizeof(double));
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fe->fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             pl->smem_bytes);
+  for (int v = 0; v < 2; ++v)
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fe->fn[v]), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               pl->smem_bytes);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(reinterpret_cast<const void*>(&linear2mel_kernel),
                              cudaFuncAttributeMaxDynamicSharedMemorySize, pl->l2m_smem);
   int occ = 0;
   if (e == cudaSuccess)
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void*>(fe->fn), NTHREADS,
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void*>(fe->fn[cfg->has_preemphasis ? 1 : 0]), NTHREADS,
                                                       pl->smem_bytes);
   if (e != cudaSuccess) {
     std::string msg = std::string("sfe_plan_create: ") + cudaGetErrorString(e);
@@ -315,7 +367,7 @@ static int check_masks(const sfe_masks* m) {
 
 extern "C" int sfe_frontend_forward(const sfe_plan* pl, const float* wav, int64_t wav_pitch, const int64_t* wav_len,
                                     int32_t B, int64_t T_max, float* mel, float* lin, float* energy, int64_t* feat_len,
-                                    double* stats, const float* norm_mean, const float* norm_std,
+                                    int64_t* stats, const float* norm_mean, const float* norm_std,
                                     const sfe_masks* masks, int32_t skip_pad, void* stream) {
   if (!pl) return fail(SFE_ERR_BAD_ARG, "sfe_frontend_forward: NULL plan");
   if (!wav || !wav_len) return fail(SFE_ERR_BAD_ARG, "sfe_frontend_forward: wav / wav_len is NULL");
@@ -324,6 +376,8 @@ extern "C" int sfe_frontend_forward(const sfe_plan* pl, const float* wav, int64_
   if (mel && pl->cfg.n_mels == 0) return fail(SFE_ERR_BAD_ARG, "plan has no mel stage but mel output requested");
   if (!mel && (stats || norm_mean || norm_std || masks))
     return fail(SFE_ERR_BAD_ARG, "stats / normalisation / masks need the mel output");
+  if (stats && !pl->cfg.mel_logging)
+    return fail(SFE_ERR_BAD_ARG, "fused fixed-point sums need a log-mel plan; use sfe_stats_accumulate on the output");
   if (!mel && !lin && !energy) return fail(SFE_ERR_BAD_ARG, "no output requested");
   if (pl->cfg.center && T_max <= pl->cfg.n_fft / 2)
     return fail(SFE_ERR_BAD_ARG, "reflect padding needs T_max > n_fft/2 (torch.stft raises here too)");
@@ -348,7 +402,7 @@ extern "C" int sfe_frontend_forward(const sfe_plan* pl, const float* wav, int64_
   P.lin = lin;
   P.energy = energy;
   P.feat_len = reinterpret_cast<long long*>(feat_len);
-  P.stats = stats;
+  P.stats = reinterpret_cast<unsigned long long*>(stats);
   P.norm_mean = norm_mean;
   P.norm_std = norm_std;
   P.skip_pad = skip_pad;
@@ -362,10 +416,10 @@ extern "C" int sfe_frontend_forward(const sfe_plan* pl, const float* wav, int64_
     P.fill = masks->fill;
     P.fill_dev = masks->fill_dev;
   }
-  if (stats) SFE_CUDA(cudaMemsetAsync(stats, 0, static_cast<size_t>(B) * pl->cfg.n_mels * 2 * sizeof(double), st));
+  if (stats) SFE_CUDA(cudaMemsetAsync(stats, 0, static_cast<size_t>(B) * pl->cfg.n_mels * 2 * sizeof(int64_t), st));
   int grid = pl->n_sm * pl->ctas_per_sm;
   if (grid > P.num_tiles) grid = P.num_tiles;
-  pl->fft->fn<<<grid, NTHREADS, pl->smem_bytes, st>>>(P);
+  pl->fft->fn[pl->cfg.has_preemphasis ? 1 : 0]<<<grid, NTHREADS, pl->smem_bytes, st>>>(P);
   SFE_CUDA(cudaGetLastError());
   return SFE_OK;
 }
@@ -384,10 +438,13 @@ extern "C" int sfe_linear2mel_forward(const sfe_plan* pl, const float* lin, int6
   P.mel_log = pl->proto.mel_log;
   P.mel_clamp = pl->proto.mel_clamp;
   P.mel_div = pl->proto.mel_div;
+  P.mel_lmul = pl->proto.mel_lmul;
   P.tables = pl->d_tables;
   P.tab_floats = pl->proto.tab_floats;
   P.o_mstart = pl->proto.o_mstart;
+  P.o_mout = pl->proto.o_mout;
   P.o_mw = pl->proto.o_mw;
+  P.mel_split_mask = pl->proto.mel_split_mask;
   P.mel_rounds = pl->proto.mel_rounds;
   P.mel_tail = pl->proto.mel_tail;
   for (int i = 0; i < MAX_MEL_ROUNDS; ++i) P.mel_taps[i] = pl->proto.mel_taps[i];
@@ -419,12 +476,12 @@ extern "C" int sfe_stats_accumulate(const float* feat, const int64_t* feat_len, 
   return SFE_OK;
 }
 
-extern "C" int sfe_stats_finalize(const double* stats, const int64_t* feat_len, int32_t B, int32_t D, float clamp,
-                                  float* mean, float* std, float* packed, void* stream) {
+extern "C" int sfe_stats_finalize(const void* stats, int32_t stats_fixed, const int64_t* feat_len, int32_t B, int32_t D,
+                                  float clamp, float* mean, float* std, float* packed, void* stream) {
   if (!stats || !feat_len) return fail(SFE_ERR_BAD_ARG, "sfe_stats_finalize: NULL argument");
   if (B <= 0 || D <= 0) return fail(SFE_ERR_BAD_ARG, "sfe_stats_finalize: bad shape");
   stats_finalize_kernel<<<(D + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      stats, reinterpret_cast<const long long*>(feat_len), B, D, clamp, mean, std, packed);
+      stats, stats_fixed, reinterpret_cast<const long long*>(feat_len), B, D, clamp, mean, std, packed);
   SFE_CUDA(cudaGetLastError());
   return SFE_OK;
 }
@@ -440,7 +497,8 @@ extern "C" int sfe_running_update(const float* packed, int32_t D, float weight, 
 }
 
 extern "C" int sfe_normalize(const float* src, float* dst, const int64_t* feat_len, int32_t B, int64_t F, int32_t D,
-                             const double* stats, float clamp, int32_t use_mean, int32_t use_std, const float* mean,
+                             const void* stats, int32_t stats_fixed, float clamp, int32_t use_mean, int32_t use_std,
+                             const float* mean,
                              const float* std, int32_t per_utt, float* mean_out, float* std_out, int32_t src_has_pad,
                              float pad_value, const sfe_warp* warp, const sfe_masks* masks, void* stream) {
   if (!src || !dst || !feat_len) return fail(SFE_ERR_BAD_ARG, "sfe_normalize: NULL argument");
@@ -462,6 +520,7 @@ extern "C" int sfe_normalize(const float* src, float* dst, const int64_t* feat_l
   P.F = F;
   P.D = D;
   P.stats = stats;
+  P.stats_fixed = stats_fixed;
   P.clamp = clamp;
   P.use_mean = use_mean;
   P.use_std = use_std;

@@ -127,6 +127,7 @@ class FrontendPlan:
             cfg.mel_weight_host = mw.data_ptr()
         self.n_fft, self.win_length, self.hop_length, self.center = int(n_fft), int(win_length), int(hop_length), bool(center)
         self.n_mels, self.n_bins = int(n_mels), n_fft // 2 + 1
+        self.mel_logging = bool(mel_logging)
         self.pad_mel = (np.log(np.float32(mel_clamp)) / np.float32(cfg.mel_log_div)).astype(np.float32).item() \
             if mel_logging else 0.0
         handle = C.c_void_p()
@@ -171,8 +172,10 @@ class FrontendPlan:
             lin = torch.empty((B, F, self.n_bins), dtype=torch.float32, device=dev)
         if want_energy:
             energy = torch.empty((B, F), dtype=torch.float32, device=dev)
-        if want_stats:
-            stats = out_stats if out_stats is not None else torch.empty((B, self.n_mels, 2), dtype=torch.float64, device=dev)
+        fused_stats = want_stats and self.mel_logging
+        if fused_stats:
+            # fixed-point sums (see include/sfe.h): int64, recognised downstream by their dtype
+            stats = out_stats if out_stats is not None else torch.empty((B, self.n_mels, 2), dtype=torch.int64, device=dev)
         feat_len = torch.empty((B,), dtype=torch.int64, device=dev)
         ms = masks.struct() if masks is not None else None
         with torch.cuda.device(dev):
@@ -180,6 +183,8 @@ class FrontendPlan:
                 self._h, _ptr(wav), int(wav.stride(0)), _ptr(wav_len), B, T, _ptr(mel), _ptr(lin), _ptr(energy),
                 _ptr(feat_len), _ptr(stats), _ptr(norm_mean), _ptr(norm_std),
                 C.byref(ms) if ms is not None else None, int(skip_pad), _stream()))
+        if want_stats and not fused_stats:
+            stats = stats_accumulate(mel, feat_len)  # linear-domain mel: general fp64 sums in a second pass
         out.update(mel=mel, lin=lin, energy=energy, stats=stats, feat_len=feat_len)
         return out
 
@@ -213,8 +218,8 @@ def stats_finalize(stats: torch.Tensor, feat_len: torch.Tensor, clamp: float, wa
     std = torch.empty((B, D), dtype=torch.float32, device=dev)
     packed = torch.empty((2 * D + 1,), dtype=torch.float32, device=dev) if want_packed else None
     with torch.cuda.device(dev):
-        _lib.check(_lib.load().sfe_stats_finalize(_ptr(stats), _ptr(feat_len), B, D, float(clamp), _ptr(mean), _ptr(std),
-                                                  _ptr(packed), _stream()))
+        _lib.check(_lib.load().sfe_stats_finalize(_ptr(stats), int(stats.dtype == torch.int64), _ptr(feat_len), B, D,
+                                                  float(clamp), _ptr(mean), _ptr(std), _ptr(packed), _stream()))
     return mean, std, packed
 
 
@@ -249,7 +254,8 @@ def normalize(src: torch.Tensor, feat_len: torch.Tensor, *, dst: Optional[torch.
     ms = masks.struct() if masks is not None else None
     with torch.cuda.device(src.device):
         _lib.check(_lib.load().sfe_normalize(
-            _ptr(src), _ptr(dst), _ptr(feat_len), B, F, D, _ptr(stats), float(clamp), int(use_mean), int(use_std),
+            _ptr(src), _ptr(dst), _ptr(feat_len), B, F, D, _ptr(stats),
+            int(stats is not None and stats.dtype == torch.int64), float(clamp), int(use_mean), int(use_std),
             _ptr(mean), _ptr(std), int(per_utt), _ptr(mo), _ptr(so), int(src_has_pad), float(pad_value),
             C.byref(w) if w is not None else None, C.byref(ms) if ms is not None else None, _stream()))
     return dst, mo, so

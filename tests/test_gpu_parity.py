@@ -306,7 +306,10 @@ def test_c2_full_size_vs_oracle_and_properties():
     d = O.specaug_draw(O.TorchCpuRandint(1234), 64, 80, flen, O.SpecAugCfg(time_warp=False))
     mask = O.specaug_mask(64, y.shape[1], 80, d)
     got = y.cpu().numpy()
-    assert np.array_equal(got == 0.0, mask), "mask pattern must be bit-exact at full size"
+    assert (got[mask] == 0.0).all(), "every masked element must hold the fill value"
+    # un-masked elements are non-zero, except that among ~1e7 values one may equal its utterance mean
+    # exactly in fp32 ((x - mean) / std == 0.0): allow a handful of such natural zeros
+    assert np.count_nonzero((got == 0.0) & ~mask) <= 4, "mask pattern must match the reference draw sequence"
     # the batch-level reflect padding means utterance 0 (len == T_max) differs from a solo run only
     # in its last frame; check three utterances against the oracle run on the *padded batch rows*
     sub = [0, 20, 63]
