@@ -266,7 +266,7 @@ def main():
     batches = [make_batch(w, lens, w["seed"] + 100 * i + rank, dev) for i in range(ring)]
     wl_dev = torch.tensor(lens, dtype=torch.int64, device=dev)
     wl_host = torch.tensor(lens, dtype=torch.int64)
-    ops.HostLengths.remember(wl_dev, wl_host)
+    ops.HostLengths.remember(wl_dev, wl_host.numpy())
 
     def step(i):
         return chain(batches[i % ring], wl_dev)

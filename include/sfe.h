@@ -63,7 +63,12 @@ typedef struct sfe_config {
 typedef struct sfe_plan sfe_plan;
 
 /* SpecAugment masks drawn by the host with the reference's torch.randint sequence
- * (specaug.py:145-199).  All device pointers, int32, shape (B, n_freq) / (B, n_time). */
+ * (specaug.py:145-199): int32 arrays of shape (B, n_freq) / (B, n_time).
+ * on_host = 0: the four pointers are DEVICE pointers.
+ * on_host = 1: they are HOST pointers and the descriptors travel inside the kernel parameter
+ *              block (no H2D copy, nothing to keep alive after the call returns); allowed while
+ *              2*(n_freq+n_time)*B <= SFE_MASK_INLINE_MAX, else SFE_ERR_BAD_ARG. */
+#define SFE_MASK_INLINE_MAX 768
 typedef struct sfe_masks {
   const int32_t* freq_pos;
   const int32_t* freq_len;
@@ -73,6 +78,7 @@ typedef struct sfe_masks {
   int32_t n_time;
   float fill;              /* 0.0 when feat_norm=True (specaug.py:203)                         */
   const float* fill_dev;   /* if non-NULL, the fill value is read from device (feat.mean())    */
+  int32_t on_host;
 } sfe_masks;
 
 /* Batch-shared SpecAugment time warp (specaug.py:96-124): rows [0,center) are resampled to
@@ -120,6 +126,21 @@ int sfe_frontend_forward(const sfe_plan* plan, const float* wav, int64_t wav_pit
                          float* energy, int64_t* feat_len, int64_t* stats, const float* norm_mean,
                          const float* norm_std, const sfe_masks* masks, int32_t skip_pad,
                          void* stream);
+
+/* The frontend -> normalise -> SpecAugment-mask chain of ASREncoder.forward (encoder/asr.py:103-119)
+ * in one call and at most two launches (no time warp; see sfe_normalize for that):
+ *   norm_mode 0  no normalisation: one launch, masks applied in the epilogue
+ *   norm_mode 1  statistics known up front (mean/std vectors (n_mels,), either may be NULL): one
+ *                launch, (x-mean)/std and masks in the epilogue         (feat_norm.py:327-336)
+ *   norm_mode 2  utterance statistics: launch 1 writes the valid rows and the fixed-point sums into
+ *                stats_ws (B, n_mels, 2) int64, launch 2 normalises in place, synthesises the padded
+ *                rows and applies the masks                             (feat_norm.py:137-139)
+ * mean_out/std_out (B, n_mels), optional: the per-utterance statistics of norm_mode 2. */
+int sfe_chain_forward(const sfe_plan* plan, const float* wav, int64_t wav_pitch,
+                      const int64_t* wav_len, int32_t B, int64_t T_max, float* mel,
+                      int64_t* feat_len, int64_t* stats_ws, int32_t norm_mode, const float* mean,
+                      const float* std, float clamp, int32_t use_mean, int32_t use_std,
+                      float* mean_out, float* std_out, const sfe_masks* masks, void* stream);
 
 /* LinearSpec2MelSpec.forward on an existing linear spectrogram (linear2mel.py:163-189).
  * lin (B*F, n_fft/2+1) -> mel (B*F, n_mels). */

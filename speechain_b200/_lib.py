@@ -31,8 +31,11 @@ class SfeMasks(C.Structure):
     _fields_ = [
         ("freq_pos", C.c_void_p), ("freq_len", C.c_void_p), ("n_freq", C.c_int32),
         ("time_pos", C.c_void_p), ("time_len", C.c_void_p), ("n_time", C.c_int32),
-        ("fill", C.c_float), ("fill_dev", C.c_void_p),
+        ("fill", C.c_float), ("fill_dev", C.c_void_p), ("on_host", C.c_int32),
     ]
+
+
+MASK_INLINE_MAX = 768
 
 
 class SfeWarp(C.Structure):
@@ -51,6 +54,8 @@ SYMBOLS = {
     "sfe_plan_query": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "sfe_frontend_forward": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                        C.POINTER(SfeMasks), _i32, _vp]),
+    "sfe_chain_forward": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _f32, _i32, _i32,
+                                    _vp, _vp, C.POINTER(SfeMasks), _vp]),
     "sfe_linear2mel_forward": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "sfe_stats_accumulate": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp]),
     "sfe_stats_finalize": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),

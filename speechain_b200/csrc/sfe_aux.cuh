@@ -156,12 +156,7 @@ struct NormParams {
   int src_has_pad;
   float pad_value;
   int warp_on, warp_center, warp_pos, warp_minlen;
-  const int* fpos;
-  const int* flen_m;
-  int n_fmask;
-  const int* tpos;
-  const int* tlen;
-  int n_tmask;
+  MaskDesc mk;
   float fill;
   const float* fill_dev;
   int frames_per_cta;
@@ -177,12 +172,17 @@ __device__ __forceinline__ void cubic_w(float t, float (&w)[4]) {
 }
 
 __global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ NormParams p) {
-  extern __shared__ float nsm[];  // mean[D] | sd[D] | fmask[D]
+  extern __shared__ float nsm[];  // mean[D] | 1/std[D] | fmask[D]
   const int b = blockIdx.y, D = p.D;
   float* s_mean = nsm;
-  float* s_sd = nsm + D;
+  float* s_rstd = nsm + D;
   float* s_fm = nsm + 2 * D;
   const long long n_valid = min(p.flen[b], p.F);
+  const int n_fmask = p.mk.n_fmask, n_tmask = p.mk.n_tmask;
+  const int* m_fpos = p.mk.inl_on ? p.mk.inl : p.mk.fpos;
+  const int* m_flen = p.mk.inl_on ? p.mk.inl + p.B * n_fmask : p.mk.flen;
+  const int* m_tpos = p.mk.inl_on ? p.mk.inl + 2 * p.B * n_fmask : p.mk.tpos;
+  const int* m_tlen = p.mk.inl_on ? p.mk.inl + 2 * p.B * n_fmask + p.B * n_tmask : p.mk.tlen;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float m = 0.f, s = 1.f;
     if (p.stats) {
@@ -200,17 +200,15 @@ __global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ 
       if (p.sd) s = p.per_utt ? p.sd[static_cast<long long>(b) * D + d] : p.sd[d];
     }
     s_mean[d] = m;
-    s_sd[d] = s;
+    s_rstd[d] = 1.0f / s;  // (x-m)*(1/s): within 1 ulp of the reference's division
     bool fm = false;
-    for (int q = 0; q < p.n_fmask; ++q) {
-      const int ps = p.fpos[b * p.n_fmask + q], ln = p.flen_m[b * p.n_fmask + q];
+    for (int q = 0; q < n_fmask; ++q) {
+      const int ps = m_fpos[b * n_fmask + q], ln = m_flen[b * n_fmask + q];
       fm |= (d >= ps) && (d < ps + ln);
     }
     s_fm[d] = fm ? 1.f : 0.f;
   }
   __syncthreads();
-  const bool do_mean = p.stats ? (p.use_mean != 0) : (p.mean != nullptr);
-  const bool do_std = p.stats ? (p.use_std != 0) : (p.sd != nullptr);
   const float fillv = p.fill_dev ? *p.fill_dev : p.fill;
   const long long t0 = static_cast<long long>(blockIdx.x) * p.frames_per_cta;
   const long long t1 = min(p.F, t0 + p.frames_per_cta);
@@ -219,67 +217,74 @@ __global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ 
   const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.src) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(p.dst) & 15) == 0);
   const int W = vec ? D / 4 : D;  // work items per frame
-  const long long items = (t1 - t0) * W;
-  for (long long it = threadIdx.x; it < items; it += blockDim.x) {
-    const long long t = t0 + it / W;
-    const int c = static_cast<int>(it % W);
-    bool tmask = false;
-    for (int q = 0; q < p.n_tmask; ++q) {
-      const int ps = p.tpos[b * p.n_tmask + q], ln = p.tlen[b * p.n_tmask + q];
-      tmask |= (t >= ps) && (t < ps + ln);
+  // thread -> (row within a group of rows, column chunk): no per-element index arithmetic
+  const int rows = max(1, static_cast<int>(blockDim.x) / W);
+  const int r0 = (W <= static_cast<int>(blockDim.x)) ? threadIdx.x / W : 0;
+  const bool active = (W <= static_cast<int>(blockDim.x)) ? (r0 < rows) : true;
+  if (!active) return;
+  for (int c = (W <= static_cast<int>(blockDim.x)) ? threadIdx.x % W : threadIdx.x; c < W; c += blockDim.x) {
+    float mv[4], rv[4], fv[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int d = vec ? c * 4 + e : c;
+      mv[e] = s_mean[d];
+      rv[e] = s_rstd[d];
+      fv[e] = s_fm[d];
     }
-    // source taps (time warp) --------------------------------------------------------------
-    int idx[4];
-    float cw[4];
-    bool warped = false;
-    if (p.warp_on && t < p.warp_minlen) {
-      warped = true;
-      int lo, in_len, out_len, tt;
-      if (t < p.warp_pos) { lo = 0; in_len = p.warp_center; out_len = p.warp_pos; tt = static_cast<int>(t); }
-      else { lo = p.warp_center; in_len = p.warp_minlen - p.warp_center; out_len = p.warp_minlen - p.warp_pos; tt = static_cast<int>(t) - p.warp_pos; }
-      const float scale = out_len > 1 ? static_cast<float>(in_len - 1) / static_cast<float>(out_len - 1) : 0.f;
-      const float real = scale * static_cast<float>(tt);
-      const int i0 = static_cast<int>(floorf(real));
-      cubic_w(real - static_cast<float>(i0), cw);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) idx[q] = lo + min(max(i0 - 1 + q, 0), in_len - 1);
-    }
-    const bool is_pad = (t >= n_valid) && !p.src_has_pad;
-    if (vec) {
-      float4 x;
-      if (is_pad) x = make_float4(p.pad_value, p.pad_value, p.pad_value, p.pad_value);
-      else if (warped) {
-        x = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(src + static_cast<long long>(idx[q]) * D) + c);
-          x.x = fmaf(cw[q], v.x, x.x); x.y = fmaf(cw[q], v.y, x.y); x.z = fmaf(cw[q], v.z, x.z); x.w = fmaf(cw[q], v.w, x.w);
-        }
-      } else x = *(reinterpret_cast<const float4*>(src + t * D) + c);
-      float* xv = reinterpret_cast<float*>(&x);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int d = c * 4 + e;
-        float v = xv[e];
-        if (do_mean) v -= s_mean[d];
-        if (do_std) v /= s_sd[d];
-        if (tmask || s_fm[d] != 0.f) v = fillv;
-        xv[e] = v;
+    for (long long t = t0 + r0; t < t1; t += rows) {
+      bool tmask = false;
+      for (int q = 0; q < n_tmask; ++q) {
+        const int ps = m_tpos[b * n_tmask + q], ln = m_tlen[b * n_tmask + q];
+        tmask |= (t >= ps) && (t < ps + ln);
       }
-      *(reinterpret_cast<float4*>(dst + t * D) + c) = x;
-    } else {
-      const int d = c;
-      float v;
-      if (is_pad) v = p.pad_value;
-      else if (warped) {
-        v = 0.f;
+      // source taps (time warp) ------------------------------------------------------------
+      int idx[4];
+      float cw[4];
+      bool warped = false;
+      if (p.warp_on && t < p.warp_minlen) {
+        warped = true;
+        int lo, in_len, out_len, tt;
+        if (t < p.warp_pos) { lo = 0; in_len = p.warp_center; out_len = p.warp_pos; tt = static_cast<int>(t); }
+        else { lo = p.warp_center; in_len = p.warp_minlen - p.warp_center; out_len = p.warp_minlen - p.warp_pos; tt = static_cast<int>(t) - p.warp_pos; }
+        const float scale = out_len > 1 ? static_cast<float>(in_len - 1) / static_cast<float>(out_len - 1) : 0.f;
+        const float real = scale * static_cast<float>(tt);
+        const int i0 = static_cast<int>(floorf(real));
+        cubic_w(real - static_cast<float>(i0), cw);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) v = fmaf(cw[q], __ldg(src + static_cast<long long>(idx[q]) * D + d), v);
-      } else v = src[t * D + d];
-      if (do_mean) v -= s_mean[d];
-      if (do_std) v /= s_sd[d];
-      if (tmask || s_fm[d] != 0.f) v = fillv;
-      dst[t * D + d] = v;
+        for (int q = 0; q < 4; ++q) idx[q] = lo + min(max(i0 - 1 + q, 0), in_len - 1);
+      }
+      const bool is_pad = (t >= n_valid) && !p.src_has_pad;
+      if (vec) {
+        float4 x;
+        if (is_pad) x = make_float4(p.pad_value, p.pad_value, p.pad_value, p.pad_value);
+        else if (warped) {
+          x = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src + static_cast<long long>(idx[q]) * D) + c);
+            x.x = fmaf(cw[q], v.x, x.x); x.y = fmaf(cw[q], v.y, x.y); x.z = fmaf(cw[q], v.z, x.z); x.w = fmaf(cw[q], v.w, x.w);
+          }
+        } else x = *(reinterpret_cast<const float4*>(src + t * D) + c);
+        float* xv = reinterpret_cast<float*>(&x);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float v = (xv[e] - mv[e]) * rv[e];
+          if (tmask || fv[e] != 0.f) v = fillv;
+          xv[e] = v;
+        }
+        *(reinterpret_cast<float4*>(dst + t * D) + c) = x;
+      } else {
+        float v;
+        if (is_pad) v = p.pad_value;
+        else if (warped) {
+          v = 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v = fmaf(cw[q], __ldg(src + static_cast<long long>(idx[q]) * D + c), v);
+        } else v = src[t * D + c];
+        v = (v - mv[0]) * rv[0];
+        if (tmask || fv[0] != 0.f) v = fillv;
+        dst[t * D + c] = v;
+      }
     }
   }
 }

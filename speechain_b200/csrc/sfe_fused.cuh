@@ -29,6 +29,18 @@ constexpr int FPW = 2;                    // frames per warp per tile
 constexpr int TILE_F = NWARPS * FPW;      // frames per tile
 constexpr int MAX_MEL_ROUNDS = 16;        // phases of 32 filter units (n_mels <= 256)
 constexpr int NSTAGE = 2;                 // staging buffers
+constexpr int MASK_INLINE_MAX = 768;      // SFE_MASK_INLINE_MAX
+
+// SpecAugment interval descriptors: device arrays, or (small batches) carried in the parameter block
+struct MaskDesc {
+  const int* fpos;
+  const int* flen;
+  const int* tpos;
+  const int* tlen;
+  int n_fmask, n_tmask;
+  int inl_on;
+  int inl[MASK_INLINE_MAX];
+};
 
 struct FwdParams {
   // input
@@ -50,12 +62,7 @@ struct FwdParams {
   const float* norm_mean;
   const float* norm_std;
   // masks
-  const int* fpos;
-  const int* flen;
-  int n_fmask;
-  const int* tpos;
-  const int* tlen;
-  int n_tmask;
+  MaskDesc mk;
   float fill;
   const float* fill_dev;
   int skip_pad;
@@ -323,6 +330,11 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
   const float2* mw2 = reinterpret_cast<const float2*>(tab + p.o_mw);
   const int hop = p.hop, win = p.win, D = p.D, K = p.K;
   const bool base_aligned = ((reinterpret_cast<uintptr_t>(p.wav) & 15) == 0);
+  const int n_fmask = p.mk.n_fmask, n_tmask = p.mk.n_tmask;
+  const int* m_fpos = p.mk.inl_on ? p.mk.inl : p.mk.fpos;
+  const int* m_flen = p.mk.inl_on ? p.mk.inl + p.B * n_fmask : p.mk.flen;
+  const int* m_tpos = p.mk.inl_on ? p.mk.inl + 2 * p.B * n_fmask : p.mk.tpos;
+  const int* m_tlen = p.mk.inl_on ? p.mk.inl + 2 * p.B * n_fmask + p.B * n_tmask : p.mk.tlen;
   constexpr int pre1 = PRE ? 1 : 0;
   constexpr int EDGE_SHIFT = 4;  // edge tiles leave room for the (unused) predecessor sample
 
@@ -408,8 +420,8 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
           if (p.norm_mean) v -= p.norm_mean[d];
           if (p.norm_std) v /= p.norm_std[d];
           bool m = false;
-          for (int q = 0; q < p.n_fmask; ++q) {
-            const int ps = p.fpos[b * p.n_fmask + q], ln = p.flen[b * p.n_fmask + q];
+          for (int q = 0; q < n_fmask; ++q) {
+            const int ps = m_fpos[b * n_fmask + q], ln = m_flen[b * n_fmask + q];
             m |= (d >= ps) && (d < ps + ln);
           }
           dst[i] = m ? fillv : v;
@@ -571,7 +583,7 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
     // tap counts; a lane walks its unit two taps at a time over both frames of the warp.
     if (p.mel) {
       const int tA = t0 + warp * FPW;
-      const bool fancy = (p.norm_mean != nullptr) || (p.norm_std != nullptr) || (p.n_fmask > 0) || (p.n_tmask > 0);
+      const bool fancy = (p.norm_mean != nullptr) || (p.norm_std != nullptr) || (n_fmask > 0) || (n_tmask > 0);
       const float2* P2v = reinterpret_cast<const float2*>(P2);
       float* mel_row = p.mel + (static_cast<long long>(b) * p.F + tA) * D;
       const bool w0 = (tA < p.F) && !(p.skip_pad && tA >= flen);          // row tA is written
@@ -582,8 +594,8 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
       bool tm0 = false, tm1 = false;
       if (fancy) {
         fillv = p.fill_dev ? *p.fill_dev : p.fill;
-        for (int q = 0; q < p.n_tmask; ++q) {
-          const int ps = p.tpos[b * p.n_tmask + q], ln = p.tlen[b * p.n_tmask + q];
+        for (int q = 0; q < n_tmask; ++q) {
+          const int ps = m_tpos[b * n_tmask + q], ln = m_tlen[b * n_tmask + q];
           tm0 |= (tA >= ps) && (tA < ps + ln);
           tm1 |= (tA + 1 >= ps) && (tA + 1 < ps + ln);
         }
@@ -626,8 +638,8 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
             if (p.norm_mean) { const float nm = p.norm_mean[d]; x0 -= nm; x1 -= nm; }
             if (p.norm_std) { const float ns = p.norm_std[d]; x0 /= ns; x1 /= ns; }
             bool fm = false;
-            for (int q = 0; q < p.n_fmask; ++q) {
-              const int ps = p.fpos[b * p.n_fmask + q], ln = p.flen[b * p.n_fmask + q];
+            for (int q = 0; q < n_fmask; ++q) {
+              const int ps = m_fpos[b * n_fmask + q], ln = m_flen[b * n_fmask + q];
               fm |= (d >= ps) && (d < ps + ln);
             }
             if (fm || tm0) x0 = fillv;

@@ -356,12 +356,42 @@ extern "C" int sfe_plan_query(const sfe_plan* pl, int32_t* smem_bytes, int32_t* 
   return SFE_OK;
 }
 
-static int check_masks(const sfe_masks* m) {
+// validate + translate the public mask descriptor (device arrays, or host arrays copied into the
+// kernel parameter block)
+static int fill_masks(const sfe_masks* m, int B, MaskDesc* out, float* fill, const float** fill_dev) {
+  out->fpos = out->flen = out->tpos = out->tlen = nullptr;
+  out->n_fmask = out->n_tmask = 0;
+  out->inl_on = 0;
   if (!m) return SFE_OK;
   if (m->n_freq < 0 || m->n_time < 0 || m->n_freq > 64 || m->n_time > 64)
     return fail(SFE_ERR_BAD_ARG, "mask counts must be in [0, 64]");
   if ((m->n_freq > 0 && (!m->freq_pos || !m->freq_len)) || (m->n_time > 0 && (!m->time_pos || !m->time_len)))
     return fail(SFE_ERR_BAD_ARG, "mask descriptor pointers are NULL");
+  out->n_fmask = m->n_freq;
+  out->n_tmask = m->n_time;
+  *fill = m->fill;
+  *fill_dev = m->fill_dev;
+  if (m->on_host) {
+    const long long need = 2LL * (m->n_freq + m->n_time) * B;
+    if (need > MASK_INLINE_MAX)
+      return fail(SFE_ERR_BAD_ARG, "host mask descriptors exceed SFE_MASK_INLINE_MAX; upload them and pass on_host=0");
+    int* q = out->inl;
+    if (m->n_freq) {
+      memcpy(q, m->freq_pos, sizeof(int) * B * m->n_freq);
+      memcpy(q + B * m->n_freq, m->freq_len, sizeof(int) * B * m->n_freq);
+    }
+    q += 2 * B * m->n_freq;
+    if (m->n_time) {
+      memcpy(q, m->time_pos, sizeof(int) * B * m->n_time);
+      memcpy(q + B * m->n_time, m->time_len, sizeof(int) * B * m->n_time);
+    }
+    out->inl_on = 1;
+  } else {
+    out->fpos = m->freq_pos;
+    out->flen = m->freq_len;
+    out->tpos = m->time_pos;
+    out->tlen = m->time_len;
+  }
   return SFE_OK;
 }
 
@@ -381,7 +411,6 @@ extern "C" int sfe_frontend_forward(const sfe_plan* pl, const float* wav, int64_
   if (!mel && !lin && !energy) return fail(SFE_ERR_BAD_ARG, "no output requested");
   if (pl->cfg.center && T_max <= pl->cfg.n_fft / 2)
     return fail(SFE_ERR_BAD_ARG, "reflect padding needs T_max > n_fft/2 (torch.stft raises here too)");
-  if (int rc = check_masks(masks)) return rc;
   const int64_t F = sfe_plan_num_frames(pl, T_max);
   if (F <= 0) return fail(SFE_ERR_BAD_ARG, "input shorter than one frame");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -406,16 +435,7 @@ extern "C" int sfe_frontend_forward(const sfe_plan* pl, const float* wav, int64_
   P.norm_mean = norm_mean;
   P.norm_std = norm_std;
   P.skip_pad = skip_pad;
-  if (masks) {
-    P.fpos = masks->freq_pos;
-    P.flen = masks->freq_len;
-    P.n_fmask = masks->n_freq;
-    P.tpos = masks->time_pos;
-    P.tlen = masks->time_len;
-    P.n_tmask = masks->n_time;
-    P.fill = masks->fill;
-    P.fill_dev = masks->fill_dev;
-  }
+  if (int rc = fill_masks(masks, B, &P.mk, &P.fill, &P.fill_dev)) return rc;
   if (stats) SFE_CUDA(cudaMemsetAsync(stats, 0, static_cast<size_t>(B) * pl->cfg.n_mels * 2 * sizeof(int64_t), st));
   int grid = pl->n_sm * pl->ctas_per_sm;
   if (grid > P.num_tiles) grid = P.num_tiles;
@@ -503,7 +523,6 @@ extern "C" int sfe_normalize(const float* src, float* dst, const int64_t* feat_l
                              float pad_value, const sfe_warp* warp, const sfe_masks* masks, void* stream) {
   if (!src || !dst || !feat_len) return fail(SFE_ERR_BAD_ARG, "sfe_normalize: NULL argument");
   if (B <= 0 || F <= 0 || D <= 0 || D > 4096) return fail(SFE_ERR_BAD_ARG, "sfe_normalize: bad shape");
-  if (int rc = check_masks(masks)) return rc;
   const bool warp_on = warp && warp->enabled;
   if (warp_on) {
     if (src == dst) return fail(SFE_ERR_BAD_ARG, "sfe_normalize: the time warp cannot run in place");
@@ -537,16 +556,7 @@ extern "C" int sfe_normalize(const float* src, float* dst, const int64_t* feat_l
     P.warp_pos = warp->pos;
     P.warp_minlen = warp->minlen;
   }
-  if (masks) {
-    P.fpos = masks->freq_pos;
-    P.flen_m = masks->freq_len;
-    P.n_fmask = masks->n_freq;
-    P.tpos = masks->time_pos;
-    P.tlen = masks->time_len;
-    P.n_tmask = masks->n_time;
-    P.fill = masks->fill;
-    P.fill_dev = masks->fill_dev;
-  }
+  if (int rc = fill_masks(masks, B, &P.mk, &P.fill, &P.fill_dev)) return rc;
   // ~32 KB of features per CTA
   int fpc = 8192 / D;
   if (fpc < 1) fpc = 1;
@@ -556,6 +566,30 @@ extern "C" int sfe_normalize(const float* src, float* dst, const int64_t* feat_l
   normalize_kernel<<<grid, 256, 3 * D * sizeof(float), static_cast<cudaStream_t>(stream)>>>(P);
   SFE_CUDA(cudaGetLastError());
   return SFE_OK;
+}
+
+extern "C" int sfe_chain_forward(const sfe_plan* pl, const float* wav, int64_t wav_pitch, const int64_t* wav_len,
+                                 int32_t B, int64_t T_max, float* mel, int64_t* feat_len, int64_t* stats_ws,
+                                 int32_t norm_mode, const float* mean, const float* std, float clamp,
+                                 int32_t use_mean, int32_t use_std, float* mean_out, float* std_out,
+                                 const sfe_masks* masks, void* stream) {
+  if (!pl) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: NULL plan");
+  if (!mel || !feat_len) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: mel / feat_len is NULL");
+  if (norm_mode == 0)
+    return sfe_frontend_forward(pl, wav, wav_pitch, wav_len, B, T_max, mel, nullptr, nullptr, feat_len, nullptr,
+                                nullptr, nullptr, masks, 0, stream);
+  if (norm_mode == 1)
+    return sfe_frontend_forward(pl, wav, wav_pitch, wav_len, B, T_max, mel, nullptr, nullptr, feat_len, nullptr,
+                                use_mean ? mean : nullptr, use_std ? std : nullptr, masks, 0, stream);
+  if (norm_mode != 2) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: norm_mode must be 0, 1 or 2");
+  if (!stats_ws) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: norm_mode 2 needs stats_ws");
+  if (!pl->cfg.mel_logging) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: norm_mode 2 needs a log-mel plan");
+  if (int rc = sfe_frontend_forward(pl, wav, wav_pitch, wav_len, B, T_max, mel, nullptr, nullptr, feat_len, stats_ws,
+                                    nullptr, nullptr, nullptr, 1, stream))
+    return rc;
+  return sfe_normalize(mel, mel, feat_len, B, sfe_plan_num_frames(pl, T_max), pl->cfg.n_mels, stats_ws, 1, clamp,
+                       use_mean, use_std, nullptr, nullptr, 0, mean_out, std_out, 0, pl->proto.pad_mel, nullptr, masks,
+                       stream);
 }
 
 extern "C" int sfe_delta(const float* feat, int32_t B, int64_t F, int32_t D, int32_t order, int32_t N, float* out,

@@ -21,7 +21,27 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # raw handle of torch's current stream on the current device (torch.cuda.current_stream() costs ~8 us)
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+
+
+class _on_device:
+    """`with torch.cuda.device(d)` only when d is not already current (the common case costs nothing)."""
+
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device: torch.device):
+        self.idx = device.index if device.index is not None else torch._C._cuda_getDevice()
+
+    def __enter__(self):
+        self.prev = torch._C._cuda_getDevice()
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.prev)
+        return False
 
 
 def _need_cuda(t: torch.Tensor, name: str):
@@ -32,8 +52,8 @@ def _need_cuda(t: torch.Tensor, name: str):
 
 
 class HostLengths:
-    """Remembers the host copy of a device length tensor so that the next module in the chain
-    (normalise, SpecAugment) does not pay a device->host sync to learn min/max lengths.
+    """Remembers the host copy (numpy int64) of a device length tensor so that the next module in
+    the chain (normalise, SpecAugment) does not pay a device->host sync to learn min/max lengths.
 
     Entries are keyed by tensor identity + version; a tensor that was modified in place or is
     simply unknown falls back to one ``.cpu()`` copy."""
@@ -41,58 +61,65 @@ class HostLengths:
     _cache: Dict[int, tuple] = {}
 
     @classmethod
-    def remember(cls, dev: torch.Tensor, host: torch.Tensor):
+    def remember(cls, dev: torch.Tensor, host) -> None:
         if len(cls._cache) > 64:
             cls._cache.clear()
         cls._cache[id(dev)] = (dev._version, dev.data_ptr(), host)
 
     @classmethod
-    def get(cls, t: torch.Tensor) -> torch.Tensor:
+    def get(cls, t: torch.Tensor) -> np.ndarray:
         if not t.is_cuda:
-            return t
+            return t.numpy() if t.dtype == torch.int64 else t.long().numpy()
         hit = cls._cache.get(id(t))
         if hit is not None and hit[0] == t._version and hit[1] == t.data_ptr():
             return hit[2]
-        host = t.cpu()
+        host = t.cpu().long().numpy()
         cls.remember(t, host)
         return host
 
 
 class DeviceMasks:
-    """SpecAugment interval descriptors on the device: one pinned staging buffer, one async copy."""
+    """SpecAugment interval descriptors.  Small batches travel inside the kernel parameter block
+    (host arrays, no copy to the device at all); larger ones are uploaded once per call."""
 
     def __init__(self, device, freq_pos=None, freq_len=None, time_pos=None, time_len=None, fill: float = 0.0,
                  fill_dev: Optional[torch.Tensor] = None):
-        parts, self.n_freq, self.n_time = [], 0, 0
+        self.n_freq = self.n_time = 0
+        self._host = []
         if freq_pos is not None:
             self.n_freq = int(freq_pos.shape[1])
-            parts += [np.ascontiguousarray(freq_pos, dtype=np.int32).ravel(),
-                      np.ascontiguousarray(freq_len, dtype=np.int32).ravel()]
+            self._host += [np.ascontiguousarray(freq_pos, dtype=np.int32), np.ascontiguousarray(freq_len, dtype=np.int32)]
         if time_pos is not None:
             self.n_time = int(time_pos.shape[1])
-            parts += [np.ascontiguousarray(time_pos, dtype=np.int32).ravel(),
-                      np.ascontiguousarray(time_len, dtype=np.int32).ravel()]
+            self._host += [np.ascontiguousarray(time_pos, dtype=np.int32), np.ascontiguousarray(time_len, dtype=np.int32)]
         self.fill = float(fill)
         self.fill_dev = fill_dev
+        total = sum(a.size for a in self._host)
+        self.on_host = total <= _lib.MASK_INLINE_MAX
         self.buf = None
-        if parts:
-            flat = torch.from_numpy(np.concatenate(parts))
+        if not self.on_host and self._host:
+            flat = torch.from_numpy(np.concatenate([a.ravel() for a in self._host]))
             self.buf = flat.pin_memory().to(device, non_blocking=True)
-        self._sizes = [p.size for p in parts]
 
     def struct(self) -> _lib.SfeMasks:
         m = _lib.SfeMasks()
-        base = self.buf.data_ptr() if self.buf is not None else 0
-        off = 0
+        if self.on_host:
+            ptrs = [a.ctypes.data for a in self._host]
+        else:
+            base, ptrs = self.buf.data_ptr(), []
+            for a in self._host:
+                ptrs.append(base)
+                base += 4 * a.size
+        i = 0
         if self.n_freq:
-            m.freq_pos, m.freq_len = base + off, base + off + 4 * self._sizes[0]
-            off += 8 * self._sizes[0]
-        m.n_freq = self.n_freq
+            m.freq_pos, m.freq_len = ptrs[0], ptrs[1]
+            i = 2
         if self.n_time:
-            m.time_pos, m.time_len = base + off, base + off + 4 * self._sizes[-1]
-        m.n_time = self.n_time
+            m.time_pos, m.time_len = ptrs[i], ptrs[i + 1]
+        m.n_freq, m.n_time = self.n_freq, self.n_time
         m.fill = self.fill
         m.fill_dev = self.fill_dev.data_ptr() if self.fill_dev is not None else None
+        m.on_host = int(self.on_host)
         return m
 
 
@@ -131,10 +158,11 @@ class FrontendPlan:
         self.pad_mel = (np.log(np.float32(mel_clamp)) / np.float32(cfg.mel_log_div)).astype(np.float32).item() \
             if mel_logging else 0.0
         handle = C.c_void_p()
-        with torch.cuda.device(self.device):
+        with _on_device(self.device):
             _lib.check(lib.sfe_plan_create(C.byref(cfg), C.byref(handle)))
         self._h = handle
         self._lib = lib
+        self._ws = {}   # per-batch-size scratch for the fixed-point sums (stream-ordered reuse)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -178,7 +206,7 @@ class FrontendPlan:
             stats = out_stats if out_stats is not None else torch.empty((B, self.n_mels, 2), dtype=torch.int64, device=dev)
         feat_len = torch.empty((B,), dtype=torch.int64, device=dev)
         ms = masks.struct() if masks is not None else None
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             _lib.check(self._lib.sfe_frontend_forward(
                 self._h, _ptr(wav), int(wav.stride(0)), _ptr(wav_len), B, T, _ptr(mel), _ptr(lin), _ptr(energy),
                 _ptr(feat_len), _ptr(stats), _ptr(norm_mean), _ptr(norm_std),
@@ -188,12 +216,37 @@ class FrontendPlan:
         out.update(mel=mel, lin=lin, energy=energy, stats=stats, feat_len=feat_len)
         return out
 
+    def chain(self, wav: torch.Tensor, wav_len: torch.Tensor, *, norm_mode: int, mean=None, std=None,
+              clamp: float = 1e-10, use_mean=True, use_std=True, masks: Optional[DeviceMasks] = None):
+        """frontend -> normalise -> masks in one library call (see sfe_chain_forward).  Lean on purpose:
+        the caller has validated `wav` (B, T) fp32 CUDA with unit inner stride and `wav_len` int64 CUDA."""
+        B, T = wav.shape
+        dev = wav.device
+        F = self.num_frames(T)
+        mel = torch.empty((B, F, self.n_mels), dtype=torch.float32, device=dev)
+        feat_len = torch.empty((B,), dtype=torch.int64, device=dev)
+        ws = None
+        if norm_mode == 2:
+            ws = self._ws.get(B)
+            if ws is None:
+                ws = self._ws[B] = torch.empty((B, self.n_mels, 2), dtype=torch.int64, device=dev)
+        ms = masks.struct() if masks is not None else None
+        with _on_device(dev):
+            rc = self._lib.sfe_chain_forward(
+                self._h, wav.data_ptr(), wav.stride(0), wav_len.data_ptr(), B, T, mel.data_ptr(), feat_len.data_ptr(),
+                ws.data_ptr() if ws is not None else None, norm_mode,
+                mean.data_ptr() if mean is not None else None, std.data_ptr() if std is not None else None,
+                clamp, int(use_mean), int(use_std), None, None, C.byref(ms) if ms is not None else None, _stream())
+        if rc:
+            _lib.check(rc)
+        return mel, feat_len
+
     def linear2mel(self, lin: torch.Tensor) -> torch.Tensor:
         _need_cuda(lin, "feat")
         lin = lin.contiguous()
         rows = lin.numel() // self.n_bins
         mel = torch.empty(lin.shape[:-1] + (self.n_mels,), dtype=torch.float32, device=lin.device)
-        with torch.cuda.device(lin.device):
+        with _on_device(lin.device):
             _lib.check(self._lib.sfe_linear2mel_forward(self._h, _ptr(lin), rows, _ptr(mel), _stream()))
         return mel
 
@@ -206,7 +259,7 @@ def stats_accumulate(feat: torch.Tensor, feat_len: torch.Tensor) -> torch.Tensor
     _need_cuda(feat, "feat")
     B, F, D = feat.shape
     stats = torch.empty((B, D, 2), dtype=torch.float64, device=feat.device)
-    with torch.cuda.device(feat.device):
+    with _on_device(feat.device):
         _lib.check(_lib.load().sfe_stats_accumulate(_ptr(feat), _ptr(feat_len), B, F, D, _ptr(stats), _stream()))
     return stats
 
@@ -217,7 +270,7 @@ def stats_finalize(stats: torch.Tensor, feat_len: torch.Tensor, clamp: float, wa
     mean = torch.empty((B, D), dtype=torch.float32, device=dev)
     std = torch.empty((B, D), dtype=torch.float32, device=dev)
     packed = torch.empty((2 * D + 1,), dtype=torch.float32, device=dev) if want_packed else None
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _lib.check(_lib.load().sfe_stats_finalize(_ptr(stats), int(stats.dtype == torch.int64), _ptr(feat_len), B, D,
                                                   float(clamp), _ptr(mean), _ptr(std), _ptr(packed), _stream()))
     return mean, std, packed
@@ -228,7 +281,7 @@ def running_update(packed: torch.Tensor, D: int, weight: float, first: bool, upd
     dev = packed.device
     bm = torch.empty((D,), dtype=torch.float32, device=dev) if want_batch else None
     bs = torch.empty((D,), dtype=torch.float32, device=dev) if want_batch else None
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _lib.check(_lib.load().sfe_running_update(_ptr(packed), D, float(weight), int(first), int(update), _ptr(run_mean),
                                                   _ptr(run_std), _ptr(bm), _ptr(bs), _stream()))
     return bm, bs
@@ -252,7 +305,7 @@ def normalize(src: torch.Tensor, feat_len: torch.Tensor, *, dst: Optional[torch.
     if warp is not None:
         w = _lib.SfeWarp(1, int(warp[0]), int(warp[1]), int(warp[2]))
     ms = masks.struct() if masks is not None else None
-    with torch.cuda.device(src.device):
+    with _on_device(src.device):
         _lib.check(_lib.load().sfe_normalize(
             _ptr(src), _ptr(dst), _ptr(feat_len), B, F, D, _ptr(stats),
             int(stats is not None and stats.dtype == torch.int64), float(clamp), int(use_mean), int(use_std),
@@ -266,7 +319,7 @@ def delta(feat: torch.Tensor, order: int, N: int) -> torch.Tensor:
     feat = feat.contiguous()
     B, F, D = feat.shape
     out = torch.empty((B, F, D * (order + 1)), dtype=torch.float32, device=feat.device)
-    with torch.cuda.device(feat.device):
+    with _on_device(feat.device):
         _lib.check(_lib.load().sfe_delta(_ptr(feat), B, F, D, int(order), int(N), _ptr(out), _stream()))
     return out
 
@@ -275,6 +328,6 @@ def mean_all(x: torch.Tensor) -> torch.Tensor:
     _need_cuda(x, "feat")
     x = x.contiguous()
     out = torch.empty((1,), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         _lib.check(_lib.load().sfe_mean_all(_ptr(x), x.numel(), _ptr(out), _stream()))
     return out

@@ -7,17 +7,21 @@ tensor per module.  ``AcousticFrontend`` owns the three and issues the cheapest 
 * statistics known before the batch (eval, or global statistics frozen after ``max_epoch_num``):
   ONE kernel — normalisation and masks run in the epilogue of the fused frontend kernel and the
   feature tensor is written exactly once;
-* statistics that depend on the batch (utterance / batch / global-while-averaging): the frontend
-  kernel writes the raw valid frames once and accumulates fp64 sums, then one normalise(+warp)
-  (+mask) pass finishes in place — two launches (plus the 2·D+1-float all-reduce for DDP).
+* utterance statistics: the frontend kernel writes the raw valid frames once and accumulates
+  fixed-point sums, then one normalise(+mask) pass finishes in place — two launches, one library call;
+* batch / global statistics while they are still being averaged: the same two launches with the
+  (2·D+1)-float statistics exchange (one all-reduce under DDP) between them;
+* a SpecAugment time warp adds one gather pass (it cannot run in place).
 """
 from typing import Optional
 
 import torch
 
 from ..host import ops
+from ..host.ops import HostLengths
 from .abs import Module
 from .augment.specaug import SpecAugment
+from .frontend._common import lengths_pair, squeeze_speech
 from .frontend.speech2mel import Speech2MelSpec
 from .norm.feat_norm import FeatureNormalization
 
@@ -39,62 +43,66 @@ class AcousticFrontend(Module):
             self.specaug = SpecAugment(input_size=size, feat_norm=hasattr(self, "normalize"), **sconf)
         self.output_size = size
 
+    # ------------------------------------------------------------------------------------
     def forward(self, feat: torch.Tensor, feat_len: torch.Tensor, epoch: int = None, domain=None):
+        """feat (batch, T, 1) or (batch, T) fp32 CUDA waveforms, feat_len (batch,) int64 (CPU or CUDA).
+        Returns (features (batch, F, n_mels), feature lengths (batch,) on the device)."""
         fe = self.frontend
+        s2l = fe.speech2linear
         norm: Optional[FeatureNormalization] = getattr(self, "normalize", None)
         aug: Optional[SpecAugment] = getattr(self, "specaug", None) if self.training else None
-        if fe.delta_order is not None or fe.return_energy:
+        if fe.delta_order is not None or fe.return_energy or s2l.pre_stft_norm is not None:
             return self._unfused(feat, feat_len, epoch, domain)
         if norm is not None and not (norm.mean_norm or norm.std_norm):
             norm = None
 
+        wav = squeeze_speech(feat)
+        if not wav.is_cuda:
+            raise RuntimeError("speechain_b200 frontend: `speech` must be a CUDA tensor — there is no CPU path.")
+        if wav.stride(1) != 1:
+            wav = wav.contiguous()
+        len_dev, len_host = lengths_pair(feat_len, wav.device)
+        flen_host = s2l._feat_len_host(len_host)
+        plan = s2l._plan(wav.device, preemph=True, mel=fe.linear2mel.mel_conf())
+
         # SpecAugment draws need only host-side lengths, so they happen before any launch
         warp = masks = None
         if aug is not None:
-            wav_len_host = ops.HostLengths.get(feat_len)
-            flen_host = fe.speech2linear._feat_len_host(wav_len_host.long())
-            warp, masks = aug.draw_device(feat.size(0), fe.output_size, flen_host, feat.device)
+            warp, masks = aug.draw_device(wav.size(0), fe.output_size, flen_host, wav.device)
             if masks is not None and not aug.feat_norm:
                 return self._unfused(feat, feat_len, epoch, domain, drawn=(warp, masks))
+        fused_masks = masks if warp is None else None
 
         if norm is None:
-            out = fe.run(feat, feat_len, masks=masks if warp is None else None)
-            y, ylen = out["mel"], out["feat_len"]
-            if warp is not None:
-                y, _, _ = ops.normalize(y, ylen, warp=warp, masks=masks)
-            return y, ylen
-
-        kind = norm.norm_type
-        if kind == "group":
-            assert domain is not None, "group-level normalisation needs group_ids (`domain`)"
-        prefix = "global" if kind == "global" else (str(domain) if isinstance(domain, (str, int)) else None)
-        known = (kind in ("global", "group") and prefix is not None and not isinstance(domain, torch.Tensor)
-                 and (not norm.training or (epoch is not None and epoch > norm.max_epoch_num))
-                 and (not norm.mean_norm or hasattr(norm, f"{prefix}_mean"))
-                 and (not norm.std_norm or hasattr(norm, f"{prefix}_std")))
-        if known:
-            # single pass: (x-mean)/std and masks in the frontend kernel's epilogue
-            if norm.training:
-                norm._counter(prefix)  # (frozen counter, nothing to update; feat_norm.py:477-483)
-            mean = norm.get_buffer(f"{prefix}_mean") if norm.mean_norm else None
-            std = norm.get_buffer(f"{prefix}_std") if norm.std_norm else None
-            out = fe.run(feat, feat_len, norm_mean=mean, norm_std=std, masks=masks if warp is None else None)
-            y, ylen = out["mel"], out["feat_len"]
-            if warp is not None:
-                y, _, _ = ops.normalize(y, ylen, warp=warp, masks=masks)
-            return y, ylen
-
-        # two passes: raw valid frames + sums, then normalise(+warp)(+mask)
-        out = fe.run(feat, feat_len, want_stats=True, skip_pad=True)
-        y, ylen = out["mel"], out["feat_len"]
-        y._sfe_stats = (y._version, out["stats"])
-        if warp is None:
-            y, ylen = norm(y, ylen, group_ids=domain, epoch=epoch, masks=masks, inplace=True, src_has_pad=False,
-                           pad_value=out["pad_value"])
+            y, ylen = plan.chain(wav, len_dev, norm_mode=0, masks=fused_masks)
         else:
-            # the warp gathers neighbouring rows, so it cannot share the in-place normalise pass
-            y, ylen = norm(y, ylen, group_ids=domain, epoch=epoch, inplace=True, src_has_pad=False,
-                           pad_value=out["pad_value"])
+            kind = norm.norm_type
+            if kind == "group":
+                assert domain is not None, "group-level normalisation needs group_ids (`domain`)"
+            prefix = "global" if kind == "global" else (str(domain) if isinstance(domain, (str, int)) else None)
+            known = (kind in ("global", "group") and prefix is not None and not isinstance(domain, torch.Tensor)
+                     and (not norm.training or (epoch is not None and epoch > norm.max_epoch_num))
+                     and (not norm.mean_norm or hasattr(norm, f"{prefix}_mean"))
+                     and (not norm.std_norm or hasattr(norm, f"{prefix}_std")))
+            if known:
+                # single pass: (x-mean)/std and masks in the frontend kernel's epilogue
+                mean = norm.get_buffer(f"{prefix}_mean") if norm.mean_norm else None
+                std = norm.get_buffer(f"{prefix}_std") if norm.std_norm else None
+                y, ylen = plan.chain(wav, len_dev, norm_mode=1, mean=mean, std=std, use_mean=norm.mean_norm,
+                                     use_std=norm.std_norm, masks=fused_masks)
+            elif plan.mel_logging and (kind == "utterance" or (kind == "batch" and not norm.training)):
+                y, ylen = plan.chain(wav, len_dev, norm_mode=2, clamp=norm.clamp, use_mean=norm.mean_norm,
+                                     use_std=norm.std_norm, masks=fused_masks)
+            else:
+                # statistics that need the whole (possibly multi-GPU) batch: raw rows + sums, exchange, normalise
+                out = plan.forward(wav, len_dev, want_stats=True, skip_pad=plan.mel_logging)
+                y, ylen = out["mel"], out["feat_len"]
+                y._sfe_stats = (y._version, out["stats"])
+                HostLengths.remember(ylen, flen_host)
+                y, ylen = norm.forward(y, ylen, group_ids=domain, epoch=epoch, masks=fused_masks, inplace=True,
+                                       src_has_pad=not plan.mel_logging, pad_value=plan.pad_mel)
+        HostLengths.remember(ylen, flen_host)
+        if warp is not None:
             y, _, _ = ops.normalize(y, ylen, warp=warp, masks=masks)
         return y, ylen
 

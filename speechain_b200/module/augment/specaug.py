@@ -86,7 +86,7 @@ class SpecAugment(Module):
 
     def draw_device(self, batch_size, feat_dim, feat_len_host, device, generator=None):
         """Draw and upload: returns (warp, DeviceMasks or None)."""
-        minlen = int(feat_len_host.min().item())
+        minlen = int(feat_len_host.min())
         warp, fpos, flen, tpos, tlen = self.draw(batch_size, feat_dim, minlen, generator)
         masks = None
         if fpos is not None or tpos is not None:

@@ -106,12 +106,13 @@ def squeeze_speech(speech: torch.Tensor) -> torch.Tensor:
 
 
 def lengths_pair(length: torch.Tensor, device):
-    """(device int64 tensor, host int64 tensor) for a length tensor living anywhere."""
+    """(device int64 tensor, host numpy int64 array) for a length tensor living anywhere."""
     from ...host.ops import HostLengths
     if length.dtype != torch.int64:
         length = length.long()
     if length.is_cuda:
         return length, HostLengths.get(length)
+    host = length.numpy()
     dev = length.to(device, non_blocking=True)
-    HostLengths.remember(dev, length)
-    return dev, length
+    HostLengths.remember(dev, host)
+    return dev, host

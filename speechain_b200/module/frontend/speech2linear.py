@@ -91,9 +91,10 @@ class Speech2LinearSpec(Module):
                 wav = (wav - lo) / (hi - lo) * 2 - 1
         return wav, len_dev, len_host, in_kernel
 
-    def _feat_len_host(self, len_host: torch.Tensor) -> torch.Tensor:
+    def _feat_len_host(self, len_host):
+        """numpy int64 feature lengths from numpy sample lengths (speech2linear.py:201-212)."""
         n = len_host + 2 * (self.n_fft // 2) if self.stft_config["center"] else len_host
-        return torch.div(n - self.n_fft, self.hop_length, rounding_mode="floor") + 1
+        return (n - self.n_fft) // self.hop_length + 1
 
     def __getstate__(self):
         # compiled plans hold raw library handles: never pickle / deepcopy them

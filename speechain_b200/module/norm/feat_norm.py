@@ -8,6 +8,7 @@ from typing import Dict, Optional
 import torch
 
 from ...host import ops
+from ...host.dist import all_reduce_packed
 from ...host.ops import DeviceMasks, HostLengths
 from ..abs import Module
 
@@ -40,9 +41,7 @@ class FeatureNormalization(Module):
         return ops.stats_accumulate(feat, feat_len)
 
     def _all_reduce(self, packed: torch.Tensor) -> torch.Tensor:
-        if self.distributed and torch.distributed.is_available() and torch.distributed.is_initialized():
-            torch.distributed.all_reduce(packed, op=torch.distributed.ReduceOp.SUM)
-        return packed
+        return all_reduce_packed(packed) if self.distributed else packed
 
     def _counter(self, prefix: str) -> Optional[int]:
         if prefix in self._batch_host:
@@ -110,7 +109,7 @@ class FeatureNormalization(Module):
         if not feat_len.is_cuda:
             host = feat_len
             feat_len = feat_len.to(feat.device, non_blocking=True)
-            HostLengths.remember(feat_len, host)
+            HostLengths.remember(feat_len, host.numpy())
         B, _, D = feat.shape
         dst = feat if inplace else None
         common = dict(masks=masks, src_has_pad=src_has_pad, pad_value=pad_value)

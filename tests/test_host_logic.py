@@ -1,0 +1,151 @@
+"""Host-side mirror of the reference module API: constructor keys, derived sizes, state-dict keys,
+reprs, filterbank bit-equality, the SpecAugment draw sequence — everything that runs without a GPU."""
+import copy
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import frontend_np as O
+from sfe_testutil import load_golden
+from speechain_b200.module.acoustic_frontend import AcousticFrontend
+from speechain_b200.module.augment.specaug import SpecAugment
+from speechain_b200.module.frontend._common import as_float, make_window, mel_filterbank, to_samples
+from speechain_b200.module.frontend.delta_feat import DeltaFeature
+from speechain_b200.module.frontend.linear2mel import LinearSpec2MelSpec
+from speechain_b200.module.frontend.speech2linear import Speech2LinearSpec
+from speechain_b200.module.frontend.speech2mel import Speech2MelSpec
+from speechain_b200.module.norm.feat_norm import FeatureNormalization
+from test_oracle_golden import FE_CASES, SA_CASES
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_seconds_vs_samples_and_nfft_default():
+    assert to_samples(0.025, 16000) == 400 and to_samples(0.010, 16000) == 160
+    assert to_samples(0.05, 22050) == 1102 and to_samples(256, 22050) == 256
+    m = Speech2MelSpec(n_mels=80, hop_length=0.010, win_length=0.025, preemphasis=0.97)
+    assert m.speech2linear.n_fft == 400 and m.speech2linear.output_size == 201 and m.output_size == 80
+    assert Speech2MelSpec(n_mels=80, hop_length=160, win_length=400, delta_order=2).output_size == 240
+    assert m.get_sample_rate() == 16000
+
+
+def test_yaml_string_numbers_are_coerced():
+    # PyYAML reads `clamp: 1e-5` as a str (the reference's ruamel loader as a float)
+    assert as_float("1e-5", "clamp") == 1e-5
+    m = Speech2MelSpec(n_mels=80, hop_length=256, win_length=1024, sr=22050, clamp="1e-5", log_base=None)
+    assert m.linear2mel.clamp == 1e-5 and m.linear2mel.log_base is None
+    with pytest.raises(ValueError):
+        as_float("abc", "clamp")
+
+
+@pytest.mark.parametrize("name", sorted(FE_CASES))
+def test_filterbank_is_bit_identical_to_the_reference_buffer(name):
+    g = load_golden(name)
+    c = O.FrontendCfg(**FE_CASES[name])
+    fmax = c.fmax if c.fmax is not None else c.sr // 2
+    W = mel_filterbank(c.sr, c.n_fft, c.n_mels, float(c.fmin), float(fmax), c.mel_scale, c.mel_norm)
+    assert np.array_equal(W.numpy(), g["mel_weight"])
+
+
+def test_filterbank_matches_torchaudio_when_present():
+    ta = pytest.importorskip("torchaudio")
+    ref = ta.functional.melscale_fbanks(sample_rate=16000, n_mels=80, n_freqs=201, f_min=0.0, f_max=8000,
+                                        norm="slaney", mel_scale="slaney").T
+    assert torch.equal(mel_filterbank(16000, 400, 80, 0.0, 8000.0, "slaney", True), ref)
+
+
+def test_window_table():
+    assert torch.equal(make_window("hann", 400, 512, False), torch.hann_window(400))
+    assert torch.allclose(make_window("hamming", 400, 512, True), torch.hamming_window(400) * 512 ** -0.5)
+    with pytest.raises(ValueError):
+        make_window("nosuch", 400, 512, False)
+
+
+def test_state_dict_keys_and_reprs_match_the_reference():
+    m = Speech2MelSpec(n_mels=80, hop_length=0.010, win_length=0.025, preemphasis=0.97)
+    sd = m.state_dict()
+    assert sorted(sd) == ["linear2mel.mel_fbanks.weight", "speech2linear.preemph_filter.weight"]
+    assert tuple(sd["speech2linear.preemph_filter.weight"].shape) == (1, 1, 2)
+    assert torch.allclose(sd["speech2linear.preemph_filter.weight"].flatten(), torch.tensor([-0.97, 1.0]))
+    assert tuple(sd["linear2mel.mel_fbanks.weight"].shape) == (80, 201)
+    assert sorted(Speech2MelSpec(n_mels=80, hop_length=160, win_length=400).state_dict()) == ["linear2mel.mel_fbanks.weight"]
+    assert list(m.parameters()) == []  # nothing trainable
+    r = repr(m)
+    assert "Speech2MelSpec(" in r and "win_length=400, hop_length=160, n_fft=400, mag_spec=False, preemphasis=0.97" in r
+    assert "stft_dim=201, n_mels=80, fmin=0.0, fmax=8000, mel_scale=slaney, mel_norm=True" in r
+    d = DeltaFeature(delta_order=2)
+    assert list(d.state_dict()) == ["delta_filters.weight"] and tuple(d.delta_filters.weight.shape) == (1, 1, 5, 1)
+    assert "norm_type=global, mean_norm=True, std_norm=True" in repr(FeatureNormalization(input_size=80))
+    assert "freq_mask_width=[0, 15]" in repr(SpecAugment(input_size=80, freq_mask_width=15))
+
+
+def test_constructor_errors_mirror_the_reference():
+    with pytest.raises(AssertionError):
+        LinearSpec2MelSpec(n_fft=512, n_mels=80, fmin=9000)              # fmax > fmin (linear2mel.py:122-124)
+    with pytest.raises(AssertionError):
+        LinearSpec2MelSpec(n_fft=512, n_mels=80, mel_scale="bark")       # linear2mel.py:127-130
+    with pytest.raises(AssertionError):
+        SpecAugment(input_size=80, freq_mask_width=80)                   # specaug.py:53-57
+    with pytest.raises(AssertionError):
+        SpecAugment(time_warp=False, freq_mask=False, time_mask=False)   # specaug.py:34-36
+    with pytest.raises(ValueError):
+        SpecAugment(input_size=80, freq_mask_width="wide")
+    with pytest.raises(AssertionError):
+        DeltaFeature(delta_order=3)
+    with pytest.raises(ValueError):
+        Speech2LinearSpec(hop_length=160, win_length=400, pre_stft_norm="robust")
+
+
+def test_cpu_tensors_fail_loudly():
+    m = Speech2MelSpec(n_mels=80, hop_length=160, win_length=400, n_fft=512)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(2, 4000, 1), torch.tensor([4000, 4000]))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        FeatureNormalization(input_size=80, norm_type="utterance")(torch.zeros(2, 10, 80), torch.tensor([10, 8]))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        SpecAugment(input_size=80)(torch.zeros(2, 50, 80), torch.tensor([50, 40]))
+    with pytest.raises(RuntimeError, match="multi-channel"):
+        m(torch.zeros(2, 4000, 2), torch.tensor([4000, 4000]))
+
+
+@pytest.mark.parametrize("name", sorted(SA_CASES))
+def test_specaug_draw_sequence_equals_oracle(name):
+    g = load_golden(name)
+    conf = SA_CASES[name]
+    sa = SpecAugment(input_size=80, **conf)
+    B, _, D = g["x"].shape
+    torch.manual_seed(int(g["seed"]))
+    warp, fpos, flen, tpos, tlen = sa.draw(B, D, int(g["x_len"].min()))
+    d = O.specaug_draw(O.TorchCpuRandint(int(g["seed"])), B, D, g["x_len"], O.SpecAugCfg(**conf))
+    assert (warp is None) == (d.warp is None)
+    if warp is not None:
+        assert tuple(warp[:2]) == tuple(d.warp)
+    for a, b in ((fpos, d.freq_pos), (flen, d.freq_len), (tpos, d.time_pos), (tlen, d.time_len)):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert np.array_equal(a, b)
+
+
+def test_modules_survive_deepcopy_and_chain_builds_from_yaml_blocks():
+    chain = AcousticFrontend(
+        frontend=dict(type="frontend.speech2mel.Speech2MelSpec",
+                      conf=dict(sr=16000, preemphasis=0.97, hop_length=0.010, win_length=0.025, n_mels=80)),
+        normalize=True, specaug=dict(freq_mask_width=15, freq_mask_num=4, time_mask_width=0.05, time_mask_num=5))
+    assert chain.normalize.norm_type == "global" and chain.specaug.feat_norm and chain.output_size == 80
+    c2 = copy.deepcopy(chain)
+    assert sorted(c2.state_dict()) == sorted(chain.state_dict())
+
+
+def test_product_code_never_touches_the_oracle():
+    # oracle/ is test infrastructure: nothing under speechain_b200/ may import or reference it
+    bad = []
+    for dp, _, fns in os.walk(os.path.join(ROOT, "speechain_b200")):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, fn)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M) or "ref_port_torch" in src:
+                    bad.append(os.path.join(dp, fn))
+    assert not bad, bad
