@@ -329,14 +329,14 @@ def main():
             free[s].record(main_stream)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(free[0])
-            dbuf[0].copy_(host[0], non_blocking=True)
+            ops.upload_waveforms(host[0], wl_host, out=dbuf[0])
             ready[0].record(copy_stream)
         for i in range(n):
             s = i % 2
             if i + 1 < n:
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(free[1 - s])
-                    dbuf[1 - s].copy_(host[(i + 1) % 2], non_blocking=True)
+                    ops.upload_waveforms(host[(i + 1) % 2], wl_host, out=dbuf[1 - s])
                     ready[1 - s].record(copy_stream)
             main_stream.wait_event(ready[s])
             ylen = chain(dbuf[s], wl_host)[1]       # lengths arrive on the host, like a collated batch
@@ -385,9 +385,10 @@ def main():
                    "cache": f"ring of {ring} distinct batches ({ring * (in_bytes_padded + out_bytes) / 1e6:.0f} MB) > 3x L2"},
         "clocks": clocks,
         "e2e": {"value": total_audio * e2e_steps / (e2e_ms * 1e-3), "unit": "audio-s/s",
-                "h2d_bytes_per_step": in_bytes_padded, "d2h_bytes_per_step": 8 * B, "steps": e2e_steps,
-                "note": "public API AcousticFrontend.forward on pinned host (B,T,1) waveforms, copy of step i+1 "
-                        "overlapped with step i; D2H = feature lengths (features stay on the GPU for the model)"},
+                "h2d_bytes_per_step": 4 * S + 8 * B, "d2h_bytes_per_step": 8 * B, "steps": e2e_steps,
+                "note": "pinned host (B,T,1) waveforms -> ops.upload_waveforms (valid samples only) -> public API "
+                        "AcousticFrontend.forward; copy of step i+1 overlapped with step i; D2H = feature lengths "
+                        "(the features stay on the GPU for the model)"},
         "gpu_launches": steps * (2 if two_pass else 1),
         "roofline": {"bound": "hbm", "kernel": "sfe::fused_frontend_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

@@ -186,7 +186,15 @@ __device__ __forceinline__ void stockham_pass(cpx* __restrict__ Z, const cpx* __
               x0 = fmaf(-pre, xm, x0);
             }
             const float2 w = *reinterpret_cast<const float2*>(w0 + 2 * r * T);
-            u[rd][r] = make_float2(x0 * w.x, x1 * w.y);
+            float y0 = x0 * w.x, y1 = x1 * w.y;
+            if (2 * r * T + 2 * T > win) {
+              // (warp-uniform) this row straddles the end of the window: samples past it may be anything
+              // — memory beyond an utterance's length is never assumed to be initialised — so select, don't scale
+              const int sidx = 2 * (j + r * T);
+              if (sidx >= win) y0 = 0.f;
+              if (sidx + 1 >= win) y1 = 0.f;
+            }
+            u[rd][r] = make_float2(y0, y1);
           } else {
             u[rd][r] = make_float2(0.f, 0.f);
           }

@@ -592,6 +592,20 @@ extern "C" int sfe_chain_forward(const sfe_plan* pl, const float* wav, int64_t w
                        stream);
 }
 
+extern "C" int sfe_upload_waveforms(const float* wav_host, int64_t host_pitch, const int64_t* len_host, int32_t B,
+                                    float* wav_dev, int64_t dev_pitch, void* stream) {
+  if (!wav_host || !len_host || !wav_dev || B <= 0) return fail(SFE_ERR_BAD_ARG, "sfe_upload_waveforms: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int b = 0; b < B; ++b) {
+    const int64_t n = len_host[b];
+    if (n < 0 || n > host_pitch || n > dev_pitch) return fail(SFE_ERR_BAD_ARG, "sfe_upload_waveforms: length exceeds the row pitch");
+    if (n == 0) continue;
+    SFE_CUDA(cudaMemcpyAsync(wav_dev + b * dev_pitch, wav_host + b * host_pitch, static_cast<size_t>(n) * sizeof(float),
+                             cudaMemcpyHostToDevice, st));
+  }
+  return SFE_OK;
+}
+
 extern "C" int sfe_delta(const float* feat, int32_t B, int64_t F, int32_t D, int32_t order, int32_t N, float* out,
                          void* stream) {
   if (!feat || !out) return fail(SFE_ERR_BAD_ARG, "sfe_delta: NULL argument");

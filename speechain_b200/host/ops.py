@@ -331,3 +331,23 @@ def mean_all(x: torch.Tensor) -> torch.Tensor:
     with _on_device(x.device):
         _lib.check(_lib.load().sfe_mean_all(_ptr(x), x.numel(), _ptr(out), _stream()))
     return out
+
+
+def upload_waveforms(wav_host: torch.Tensor, len_host: torch.Tensor, out: Optional[torch.Tensor] = None,
+                     device=None) -> torch.Tensor:
+    """Ragged H2D copy of a collated batch: only the valid prefix of every row crosses PCIe.
+
+    wav_host (B, T, 1) or (B, T) fp32 CPU (pinned for an asynchronous copy), len_host (B,) int64 CPU.
+    Returns the device tensor of the same shape; samples beyond each length are NOT initialised
+    (the frontend never reads them).  Replaces the padded copy of model/abs.py:329-352 for this path."""
+    if wav_host.is_cuda or len_host.is_cuda:
+        raise RuntimeError("upload_waveforms expects host tensors")
+    if wav_host.dtype != torch.float32 or not wav_host.is_contiguous():
+        wav_host = wav_host.float().contiguous()
+    len_host = len_host.long().contiguous()
+    B, T = wav_host.shape[0], wav_host.shape[1]
+    if out is None:
+        out = torch.empty(wav_host.shape, dtype=torch.float32, device=device if device is not None else "cuda")
+    with _on_device(out.device):
+        _lib.check(_lib.load().sfe_upload_waveforms(wav_host.data_ptr(), T, len_host.data_ptr(), B, out.data_ptr(), T, _stream()))
+    return out

@@ -361,3 +361,36 @@ def test_repeated_calls_are_deterministic_and_scheduler_rearms():
     for _ in range(3):
         b, _ = m(wav[..., None], wl)
         assert torch.equal(a, b)
+
+
+def test_memory_beyond_each_length_is_never_read():
+    # the kernel treats samples >= len as zero by construction: poison them with NaN (also odd lengths / pitch)
+    for conf in (dict(n_mels=80, n_fft=512, win_length=0.025, hop_length=0.010, preemphasis=0.97),
+                 dict(n_mels=80, win_length=0.025, hop_length=0.010),
+                 dict(sr=22050, n_mels=80, win_length=1024, hop_length=256, mag_spec=True, log_base=None, clamp=1e-5)):
+        lens = [40001, 39999, 25600, 25607, 16161, 4000]
+        clean = _wave(11, lens, zero_seg=False).to(DEV)
+        dirty = clean.clone()
+        for i, n in enumerate(lens):
+            dirty[i, n:] = float("nan")
+        m = Speech2MelSpec(**conf).to(DEV)
+        wl = torch.tensor(lens, device=DEV)
+        a, _ = m(clean[..., None], wl)
+        b, _ = m(dirty[..., None], wl)
+        assert torch.isfinite(b).all()
+        assert torch.equal(a, b)
+
+
+def test_ragged_upload_equals_padded_copy():
+    lens = [30000, 22222, 9999, 1]
+    host = _wave(12, lens, zero_seg=False)[..., None].contiguous().pin_memory()
+    wl = torch.tensor(lens, dtype=torch.int64)
+    dev = torch.full(host.shape, float("nan"), device=DEV)
+    ops.upload_waveforms(host, wl, out=dev)
+    for i, n in enumerate(lens):
+        assert torch.equal(dev[i, :n].cpu(), host[i, :n])
+        assert torch.isnan(dev[i, n:]).all()  # padding is not transferred
+    m = Speech2MelSpec(n_mels=80, n_fft=512, win_length=0.025, hop_length=0.010).to(DEV)
+    a, _ = m(dev, wl.to(DEV))
+    b, _ = m(host.to(DEV), wl.to(DEV))
+    assert torch.equal(a, b)
