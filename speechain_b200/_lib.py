@@ -10,7 +10,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libsfe.so")
+# SFE_LIB_PATH lets a benchmark load an alternative build of the same ABI (A/B timing on one box)
+LIB_PATH = os.environ.get("SFE_LIB_PATH") or os.path.join(_HERE, "csrc", "libsfe.so")
 
 ABI_VERSION = 1
 

@@ -168,25 +168,46 @@ __device__ __forceinline__ void stockham_pass(cpx* __restrict__ Z, const cpx* __
       if (FIRST) {
         const float* f0 = fr + 2 * j;
         const float* w0 = wtab + 2 * j;
+        // 1) raw sample pairs (rows entirely inside the window's zero padding are not touched)
+        cpx raw[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          if (2 * r * T < win) {  // warp-uniform: rows entirely inside the window's zero padding are skipped
-            float x0, x1;
-            if (VEC) {
-              const float2 v = *reinterpret_cast<const float2*>(f0 + 2 * r * T);
-              x0 = v.x;
-              x1 = v.y;
-            } else {
-              x0 = f0[2 * r * T];
-              x1 = f0[2 * r * T + 1];
+          raw[r] = make_float2(0.f, 0.f);
+          if (2 * r * T < win) {  // warp-uniform
+            if (VEC) raw[r] = *reinterpret_cast<const float2*>(f0 + 2 * r * T);
+            else raw[r] = make_float2(f0[2 * r * T], f0[2 * r * T + 1]);
+          }
+        }
+        // 2) pre-emphasis needs x[2n-1]: the .y of the pair one lane to the left (same row), or of the
+        //    last lane of the previous row for lane 0 — one select + one shuffle instead of a second,
+        //    bank-conflicting load.  Kept outside any branch so the shuffles are unconditional.
+        if (PRE) {
+          if (T == G && NR == 1) {
+            float carry = fr[-1];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              const float give = (l == G - 1) ? carry : raw[r].y;
+              const float xm = __shfl_sync(0xffffffffu, give, (l + G - 1) & (G - 1), G);
+              carry = raw[r].y;
+              raw[r] = f2fma(make_float2(-pre, -pre), make_float2(xm, raw[r].x), raw[r]);
             }
-            if (PRE) {
-              const float xm = f0[2 * r * T - 1];
-              x1 = fmaf(-pre, x0, x1);
-              x0 = fmaf(-pre, xm, x0);
+          } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              if (2 * r * T < win) {
+                const float xm = f0[2 * r * T - 1];
+                raw[r] = f2fma(make_float2(-pre, -pre), make_float2(xm, raw[r].x), raw[r]);
+              }
             }
+          }
+        }
+        // 3) window
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (2 * r * T < win) {
             const float2 w = *reinterpret_cast<const float2*>(w0 + 2 * r * T);
-            float y0 = x0 * w.x, y1 = x1 * w.y;
+            const float2 yw = f2mul(raw[r], w);
+            float y0 = yw.x, y1 = yw.y;
             if (2 * r * T + 2 * T > win) {
               // (warp-uniform) this row straddles the end of the window: samples past it may be anything
               // — memory beyond an utterance's length is never assumed to be initialised — so select, don't scale
@@ -318,8 +339,8 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
     for (int i = tid; i < p.nstage * p.sm_stage_floats; i += NTHREADS) st[i] = 0.f;
     float* wz = reinterpret_cast<float*>(wbase);
     for (int i = lane; i < p.sm_warp_bytes / 4; i += 32) wz[i] = 0.f;
-    unsigned long long* acc = reinterpret_cast<unsigned long long*>(smem + p.sm_acc);
-    for (int i = tid; i < NSTAGE * 2 * p.D; i += NTHREADS) acc[i] = 0ull;
+    int* acc = reinterpret_cast<int*>(smem + p.sm_acc);
+    for (int i = tid; i < NSTAGE * 4 * p.D; i += NTHREADS) acc[i] = 0;
   }
   const uint32_t bar0 = smem_u32(barp);
   if (tid == 0) {
@@ -537,11 +558,12 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
         if (i < NI - 1 || k <= M / 2) {
           const cpx a = za[i], bb = zb[i];
           const cpx w = wpost[k];
-          const cpx E = make_float2(a.x + bb.x, a.y - bb.y);
-          const cpx O = make_float2(a.y + bb.y, bb.x - a.x);
-          const cpx Tt = cmul(w, O);
-          const float xr = E.x + Tt.x, xi = E.y + Tt.y, yr = E.x - Tt.x, yi = E.y - Tt.y;
-          float pk = fmaf(xr, xr, xi * xi) * live, pm = fmaf(yr, yr, yi * yi) * live;
+          const cpx E = f2add(a, make_float2(bb.x, -bb.y));
+          const cpx O = f2add(make_float2(a.y, -a.x), make_float2(bb.y, bb.x));
+          const cpx Tt = cmul(O, w);
+          const cpx X = f2add(E, Tt), Y = f2sub(E, Tt);
+          const float2 pp2 = f2mul(make_float2(fmaf(X.x, X.x, X.y * X.y), fmaf(Y.x, Y.x, Y.y * Y.y)), make_float2(live, live));
+          float pk = pp2.x, pm = pp2.y;
           es += pk;
           if (2 * k != M) es += pm;
           if (p.mag) { pk = sqrtf(pk); pm = sqrtf(pm); }
@@ -597,7 +619,7 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
       const bool w0 = (tA < p.F) && !(p.skip_pad && tA >= flen);          // row tA is written
       const bool w1 = (tA + 1 < p.F) && !(p.skip_pad && tA + 1 >= flen);  // row tA+1 is written
       const float v0 = (tA < flen) ? 1.f : 0.f, v1 = (tA + 1 < flen) ? 1.f : 0.f;  // rows that count for the sums
-      unsigned long long* sacc = reinterpret_cast<unsigned long long*>(smem + p.sm_acc) + buf * 2 * D;
+      int* sacc = reinterpret_cast<int*>(smem + p.sm_acc) + buf * 4 * D;  // [D][s1 hi, s1 lo, s2 hi, s2 lo]
       float fillv = 0.f;
       bool tm0 = false, tm1 = false;
       if (fancy) {
@@ -615,14 +637,16 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
         const float2* pp = P2v + st;
         const int n2 = p.mel_taps[ph] >> 1;
         const float2* wp = mw2 + wofs + lane;
-        float acc0 = 0.f, acc1 = 0.f;
+        float2 accA = make_float2(0.f, 0.f), accB = make_float2(0.f, 0.f);  // (frame 0, frame 1) pairs
 #pragma unroll 2
         for (int q = 0; q < n2; ++q) {
           const float2 wq = wp[q * 32];
           const float2 p0 = pp[2 * q], p1 = pp[2 * q + 1];
-          acc0 = fmaf(wq.x, p0.x, acc0); acc1 = fmaf(wq.x, p0.y, acc1);
-          acc0 = fmaf(wq.y, p1.x, acc0); acc1 = fmaf(wq.y, p1.y, acc1);
+          accA = f2fma(make_float2(wq.x, wq.x), p0, accA);
+          accB = f2fma(make_float2(wq.y, wq.y), p1, accB);
         }
+        const float2 accs = f2add(accA, accB);
+        float acc0 = accs.x, acc1 = accs.y;
         wofs += n2 * 32;
         if ((p.mel_split_mask >> ph) & 1u) {  // bins wider than a unit: add the partner lane's half
           const float o0 = __shfl_xor_sync(0xffffffffu, acc0, 1), o1 = __shfl_xor_sync(0xffffffffu, acc1, 1);
@@ -639,8 +663,12 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
             // pair sums in fp32, then exact order-independent fixed-point accumulation
             const float s1 = x0 * v0 + x1 * v1;
             const float s2 = fmaf(x0 * v0, x0, x1 * v1 * x1);
-            atomicAdd(sacc + 2 * d, static_cast<unsigned long long>(__float2ll_rn(s1 * 4294967296.f)));
-            atomicAdd(sacc + 2 * d + 1, static_cast<unsigned long long>(__float2ll_rn(s2 * 16777216.f)));
+            // (64-bit shared atomics are CAS loops; two native 32-bit adds on disjoint bit ranges are not)
+            const long long f1 = __float2ll_rn(s1 * 4294967296.f), f2 = __float2ll_rn(s2 * 16777216.f);
+            atomicAdd(sacc + 4 * d + 0, static_cast<int>(f1 >> 24));
+            atomicAdd(sacc + 4 * d + 1, static_cast<int>(f1 & 0xffffff));
+            atomicAdd(sacc + 4 * d + 2, static_cast<int>(f2 >> 24));
+            atomicAdd(sacc + 4 * d + 3, static_cast<int>(f2 & 0xffffff));
           }
           if (fancy) {
             if (p.norm_mean) { const float nm = p.norm_mean[d]; x0 -= nm; x1 -= nm; }
@@ -662,12 +690,14 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
     // ---------------- end of tile ----------------
     __syncthreads();  // every warp is done with this tile's staging buffer and its sums are in smem
     if (p.stats) {
-      unsigned long long* sacc = reinterpret_cast<unsigned long long*>(smem + p.sm_acc) + buf * 2 * D;
+      int* sacc = reinterpret_cast<int*>(smem + p.sm_acc) + buf * 4 * D;
       for (int i = tid; i < 2 * D; i += NTHREADS) {
-        const unsigned long long v = sacc[i];
-        if (v != 0ull) {
-          sacc[i] = 0ull;  // this buffer is used again two tiles from now, behind the next barrier
-          atomicAdd(p.stats + static_cast<long long>(b) * D * 2 + i, v);
+        const int hi = sacc[2 * i], lo = sacc[2 * i + 1];
+        if ((hi | lo) != 0) {
+          sacc[2 * i] = 0;  // this buffer is used again two tiles from now, behind the next barrier
+          sacc[2 * i + 1] = 0;
+          const long long v = static_cast<long long>(hi) * 16777216LL + static_cast<long long>(lo);
+          atomicAdd(p.stats + static_cast<long long>(b) * D * 2 + i, static_cast<unsigned long long>(v));
         }
       }
     }
