@@ -401,10 +401,13 @@ def main():
         with open(traffic_file) as f:
             line["roofline"]["traffic"] = json.load(f).get("dram_bytes_per_launch")
     if world == 1 and not args.no_cpu:
-        a_s, ts, threads = time_cpu(w, 5, 1)
+        # bounded sample: probe one pass, then as many full passes as fit in ~10 s of CPU work (3..60)
+        _, probe, _ = time_cpu(w, 1, 1)
+        n_pass = int(min(60, max(3, round(10.0 / max(probe[0], 1e-3)))))
+        a_s, ts, threads = time_cpu(w, n_pass, 0)
         line["cpu_baseline"] = {"value": a_s * len(ts) / sum(ts), "unit": "audio-s/s", "cores": threads, "kind": "port",
-                                "sample": f"{len(ts)} full passes over one batch ({a_s:.0f} audio-s each) after 1 "
-                                          f"warm-up, {sum(ts):.1f} s of CPU work, {cpu_model()}"}
+                                "sample": f"{len(ts)} full passes over one batch ({a_s:.0f} audio-s each) after 2 "
+                                          f"warm-ups, {sum(ts):.1f} s of CPU work, {cpu_model()}"}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
