@@ -1,7 +1,7 @@
 // Fused waveform -> (log-)mel / linear spectrogram kernel for sm_100a.
 //
 // One persistent CTA per resident slot.  A CTA repeatedly claims a *tile* of TILE_F consecutive
-// frames of one utterance (dynamic atomic scheduler, claimed two tiles ahead), stages the
+// frames of one utterance (dynamic atomic scheduler, claimed one tile ahead), stages the
 // (TILE_F-1)*hop + n_fft samples the tile touches into shared memory with ONE 1-D bulk async copy
 // (cp.async.bulk -> UBLKCP, completion on an mbarrier; double buffered, so the copy of tile i+1
 // runs under the arithmetic of tile i) — every sample is read from HBM once although it belongs
@@ -410,28 +410,21 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
     s_info[buf] = ti;
   };
 
-  // prologue: claim tiles 0 and 1 of this CTA, start tile 0's copy
-  unsigned int claimed = 0;  // (thread 0) tile claimed for the iteration after next
+  // prologue: claim this CTA's first tile and start its copy
+  unsigned int claimed = 0;  // (thread 0) tile claimed for the next iteration
   __syncthreads();
-  if (tid == 0) {
-    const int first = static_cast<int>(atomicAdd(p.sched, 1u));
-    claimed = atomicAdd(p.sched, 1u);
-    publish(first, 0, true);
-  }
+  if (tid == 0) publish(static_cast<int>(atomicAdd(p.sched, 1u)), 0, true);
   __syncthreads();
 
   for (int it = 0;; ++it) {
     const int buf = it & 1;
     const TileInfo ti = s_info[buf];
     if (ti.tile >= p.num_tiles) break;
-    // thread 0: the tile of the next iteration was claimed one iteration ago; start its copy now
-    // (its staging buffer was released by the barrier that ended the previous iteration) and claim
-    // the tile after that — both latencies hide under this tile's arithmetic.
-    if (tid == 0) {
-      const int next = static_cast<int>(claimed);
-      claimed = (next < p.num_tiles) ? atomicAdd(p.sched, 1u) : static_cast<unsigned int>(next);
-      publish(next, buf ^ 1, p.nstage == 2);
-    }
+    // thread 0 claims the next tile now; the answer is consumed in the middle of this tile, where the
+    // next tile is described and its bulk copy started (its staging buffer was released by the barrier
+    // that ended the previous iteration).  Claiming exactly one tile ahead keeps the tail short: a CTA
+    // never sits on more than one tile that an idle CTA could have taken.
+    if (tid == 0) claimed = atomicAdd(p.sched, 1u);
     const int b = ti.b, t0 = ti.t0, flen = ti.flen;
     const long long len = ti.len;
     const int nfr = min(TILE_F, p.F - t0);  // frames of this tile that exist in the output
@@ -463,6 +456,7 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
       if (p.energy) {
         for (int i = tid; i < nfr; i += NTHREADS) p.energy[static_cast<long long>(b) * p.F + t0 + i] = 0.f;
       }
+      if (tid == 0) publish(static_cast<int>(claimed), buf ^ 1, p.nstage == 2);
       __syncthreads();
       continue;
     }
@@ -578,6 +572,9 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
       }
       __syncwarp();
     }
+
+    // the next tile's claim has long returned: describe it and start its copy under the rest of this tile
+    if (tid == 0) publish(static_cast<int>(claimed), buf ^ 1, p.nstage == 2);
 
     // ---------------- energy (sum of the power spectrum of each frame) ----------------
     if (p.energy) {
