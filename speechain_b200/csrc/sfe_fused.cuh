@@ -329,6 +329,9 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
   float* P2 = reinterpret_cast<float*>(wbase + p.sm_p2_off);    // [k][FPW] interleaved
   unsigned long long* barp = reinterpret_cast<unsigned long long*>(smem + p.sm_bar);
   __shared__ TileInfo s_info[NSTAGE];
+  constexpr int COMPACT_MAX_B = 256;
+  __shared__ int s_cum[COMPACT_MAX_B + 1];  // compact mode: first tile index of every utterance
+  __shared__ int s_ntiles;
 
   // ---- one-time setup: tables -> smem, zero the scratch, init the mbarriers ----
   {
@@ -349,6 +352,30 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
     fence_mbar_init();
   }
   uint32_t parity[NSTAGE] = {0u, 0u};
+
+  // Tiles that hold only frames past an utterance's length have nothing to compute.  When they have
+  // nothing to write either (the normalise pass synthesises those rows), enumerate real tiles only:
+  // tile -> (utterance, frame block) through a per-utterance prefix sum kept in shared memory.
+  const bool compact = (p.B <= COMPACT_MAX_B) && p.skip_pad && !p.lin && !p.energy;
+  if (compact) {
+    for (int b = tid; b < p.B; b += NTHREADS) {
+      const long long len = __ldg(p.len + b);
+      const long long fl = (p.center ? (len + 2 * (p.n_fft / 2)) - p.n_fft : len - p.n_fft) / p.hop + 1;
+      const long long fc = fl < 0 ? 0 : (fl > p.F ? p.F : fl);
+      s_cum[b + 1] = static_cast<int>((fc + TILE_F - 1) / TILE_F);
+      if (blockIdx.x == 0 && p.feat_len) p.feat_len[b] = fl;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      s_cum[0] = 0;
+      for (int b = 0; b < p.B; ++b) s_cum[b + 1] += s_cum[b];
+      s_ntiles = s_cum[p.B];
+    }
+  } else if (tid == 0) {
+    s_ntiles = p.num_tiles;
+  }
+  __syncthreads();
+  const int num_tiles = s_ntiles;
 
   const float* wtab = tab + p.o_win;
   const cpx* tw2 = reinterpret_cast<const cpx*>(tab + p.o_tw2);
@@ -374,16 +401,27 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
     ti.kind = TILE_PAD;
     ti.shift = 0;
     ti.b = 0; ti.t0 = 0; ti.flen = 0; ti.len = 0;
-    if (tile < p.num_tiles) {
-      // tile order: frame-block major, utterance minor -> with descending lengths the cheap
-      // all-padding tiles are claimed last
-      const int tb = tile / p.B;
-      const int b = tile - tb * p.B;
+    if (tile < num_tiles) {
+      int tb, b;
+      if (compact) {
+        // utterance major over real tiles: binary search of the prefix sums
+        int lo = 0, hi = p.B - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (s_cum[mid] <= tile) lo = mid; else hi = mid - 1;
+        }
+        b = lo;
+        tb = tile - s_cum[b];
+      } else {
+        // frame-block major, utterance minor -> with descending lengths the cheap all-padding tiles come last
+        tb = tile / p.B;
+        b = tile - tb * p.B;
+      }
       const int t0 = tb * TILE_F;
       const long long len = __ldg(p.len + b);
       const long long fl = (p.center ? (len + 2 * (p.n_fft / 2)) - p.n_fft : len - p.n_fft) / hop + 1;
       const int flen = static_cast<int>(fl < 0 ? 0 : (fl > p.F ? p.F : fl));
-      if (t0 == 0 && p.feat_len) p.feat_len[b] = fl;
+      if (t0 == 0 && p.feat_len && !compact) p.feat_len[b] = fl;
       ti.b = b; ti.t0 = t0; ti.flen = flen; ti.len = len;
       if (t0 < flen) {
         const long long o_start = static_cast<long long>(t0) * hop + p.off;
@@ -419,7 +457,7 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
   for (int it = 0;; ++it) {
     const int buf = it & 1;
     const TileInfo ti = s_info[buf];
-    if (ti.tile >= p.num_tiles) break;
+    if (ti.tile >= num_tiles) break;
     // thread 0 claims the next tile now; the answer is consumed in the middle of this tile, where the
     // next tile is described and its bulk copy started (its staging buffer was released by the barrier
     // that ended the previous iteration).  Claiming exactly one tile ahead keeps the tail short: a CTA
