@@ -208,6 +208,13 @@ __global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ 
     }
     s_fm[d] = fm ? 1.f : 0.f;
   }
+  // this utterance's time-mask intervals [lo, hi) -> shared memory (n_tmask <= 64)
+  __shared__ int s_tlo[64], s_thi[64];
+  for (int q = threadIdx.x; q < n_tmask; q += blockDim.x) {
+    const int ps = m_tpos[b * n_tmask + q];
+    s_tlo[q] = ps;
+    s_thi[q] = ps + m_tlen[b * n_tmask + q];
+  }
   __syncthreads();
   const float fillv = p.fill_dev ? *p.fill_dev : p.fill;
   const long long t0 = static_cast<long long>(blockIdx.x) * p.frames_per_cta;
@@ -231,12 +238,40 @@ __global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ 
       rv[e] = s_rstd[d];
       fv[e] = s_fm[d];
     }
+    if (vec && !p.warp_on) {
+      // common case: four independent rows in flight per thread (the pass is latency bound otherwise)
+      auto finish = [&](long long t, float4 x) {
+        bool tmask = false;
+        for (int q = 0; q < n_tmask; ++q) tmask |= (t >= s_tlo[q]) && (t < s_thi[q]);
+        float* xv = reinterpret_cast<float*>(&x);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float v = (xv[e] - mv[e]) * rv[e];
+          if (tmask || fv[e] != 0.f) v = fillv;
+          xv[e] = v;
+        }
+        __stcs(reinterpret_cast<float4*>(dst + t * D) + c, x);
+      };
+      const float4 padv = make_float4(p.pad_value, p.pad_value, p.pad_value, p.pad_value);
+      const bool synth = !p.src_has_pad;
+      long long t = t0 + r0;
+      for (; t + 3 * rows < t1; t += 4 * rows) {
+        float4 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const long long tt = t + u * rows;
+          x[u] = (synth && tt >= n_valid) ? padv : __ldcs(reinterpret_cast<const float4*>(src + tt * D) + c);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) finish(t + u * rows, x[u]);
+      }
+      for (; t < t1; t += rows)
+        finish(t, (synth && t >= n_valid) ? padv : __ldcs(reinterpret_cast<const float4*>(src + t * D) + c));
+      continue;
+    }
     for (long long t = t0 + r0; t < t1; t += rows) {
       bool tmask = false;
-      for (int q = 0; q < n_tmask; ++q) {
-        const int ps = m_tpos[b * n_tmask + q], ln = m_tlen[b * n_tmask + q];
-        tmask |= (t >= ps) && (t < ps + ln);
-      }
+      for (int q = 0; q < n_tmask; ++q) tmask |= (t >= s_tlo[q]) && (t < s_thi[q]);
       // source taps (time warp) ------------------------------------------------------------
       int idx[4];
       float cw[4];
