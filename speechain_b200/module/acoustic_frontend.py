@@ -11,7 +11,8 @@ tensor per module.  ``AcousticFrontend`` owns the three and issues the cheapest 
   fixed-point sums, then one normalise(+mask) pass finishes in place — two launches, one library call;
 * batch / global statistics while they are still being averaged: the same two launches with the
   (2·D+1)-float statistics exchange (one all-reduce under DDP) between them;
-* a SpecAugment time warp adds one gather pass (it cannot run in place).
+* a SpecAugment time warp is a 4-tap gather along time and cannot run in place: when a normalise pass exists
+  it carries the warp (and the masks) out of place, otherwise the warp costs one extra pass.
 """
 from typing import Optional
 
@@ -71,7 +72,10 @@ class AcousticFrontend(Module):
             warp, masks = aug.draw_device(wav.size(0), fe.output_size, flen_host, wav.device)
             if masks is not None and not aug.feat_norm:
                 return self._unfused(feat, feat_len, epoch, domain, drawn=(warp, masks))
+        # masks ride in a kernel epilogue; a time warp needs one out-of-place gather pass, which also
+        # carries the normalisation and the masks when the statistics are only known after the first pass
         fused_masks = masks if warp is None else None
+        warp_done = warp is None
 
         if norm is None:
             y, ylen = plan.chain(wav, len_dev, norm_mode=0, masks=fused_masks)
@@ -90,19 +94,20 @@ class AcousticFrontend(Module):
                 std = norm.get_buffer(f"{prefix}_std") if norm.std_norm else None
                 y, ylen = plan.chain(wav, len_dev, norm_mode=1, mean=mean, std=std, use_mean=norm.mean_norm,
                                      use_std=norm.std_norm, masks=fused_masks)
-            elif plan.mel_logging and (kind == "utterance" or (kind == "batch" and not norm.training)):
+            elif warp is None and plan.mel_logging and (kind == "utterance" or (kind == "batch" and not norm.training)):
                 y, ylen = plan.chain(wav, len_dev, norm_mode=2, clamp=norm.clamp, use_mean=norm.mean_norm,
                                      use_std=norm.std_norm, masks=fused_masks)
             else:
-                # statistics that need the whole (possibly multi-GPU) batch: raw rows + sums, exchange, normalise
+                # raw rows + sums, then ONE pass: statistics (exchanged across ranks if needed), warp, masks
                 out = plan.forward(wav, len_dev, want_stats=True, skip_pad=plan.mel_logging)
                 y, ylen = out["mel"], out["feat_len"]
                 y._sfe_stats = (y._version, out["stats"])
                 HostLengths.remember(ylen, flen_host)
-                y, ylen = norm.forward(y, ylen, group_ids=domain, epoch=epoch, masks=fused_masks, inplace=True,
-                                       src_has_pad=not plan.mel_logging, pad_value=plan.pad_mel)
+                y, ylen = norm.forward(y, ylen, group_ids=domain, epoch=epoch, masks=masks, inplace=True,
+                                       src_has_pad=not plan.mel_logging, pad_value=plan.pad_mel, warp=warp)
+                warp_done = True
         HostLengths.remember(ylen, flen_host)
-        if warp is not None:
+        if not warp_done:
             y, _, _ = ops.normalize(y, ylen, warp=warp, masks=masks)
         return y, ylen
 

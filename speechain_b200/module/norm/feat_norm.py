@@ -82,10 +82,10 @@ class FeatureNormalization(Module):
     # ------------------------------------------------------------------------------------
     def forward(self, feat: torch.Tensor, feat_len: torch.Tensor, group_ids=None, epoch: int = None,
                 masks: Optional[DeviceMasks] = None, inplace: bool = False, src_has_pad: bool = True,
-                pad_value: float = 0.0):
+                pad_value: float = 0.0, warp=None):
         """feat (batch, length, channel) or (batch, length) fp32 CUDA; feat_len (batch,).
-        ``masks`` / ``inplace`` / ``src_has_pad`` are extensions used by AcousticFrontend to fuse the
-        SpecAugment masking into the same pass; the reference signature is the first four."""
+        ``masks`` / ``warp`` / ``inplace`` / ``src_has_pad`` are extensions used by AcousticFrontend to fuse
+        SpecAugment (time warp gather + masking) into the same pass; the reference signature is the first four."""
         if self.norm_type == "group":
             assert group_ids is not None, (
                 "You are using group-level feature normalization, but group_ids is not given. "
@@ -111,8 +111,8 @@ class FeatureNormalization(Module):
             feat_len = feat_len.to(feat.device, non_blocking=True)
             HostLengths.remember(feat_len, host.numpy())
         B, _, D = feat.shape
-        dst = feat if inplace else None
-        common = dict(masks=masks, src_has_pad=src_has_pad, pad_value=pad_value)
+        dst = feat if (inplace and warp is None) else None  # the warp gathers neighbouring rows: never in place
+        common = dict(masks=masks, src_has_pad=src_has_pad, pad_value=pad_value, warp=warp)
         if dst is None:
             dst = torch.empty_like(feat)
         if not (self.mean_norm or self.std_norm):

@@ -394,3 +394,29 @@ def test_ragged_upload_equals_padded_copy():
     a, _ = m(dev, wl.to(DEV))
     b, _ = m(host.to(DEV), wl.to(DEV))
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("norm_type", ["utterance", "global"])
+def test_fused_chain_with_time_warp_vs_oracle(norm_type):
+    # recipe-default SpecAugment (time_warp on): frontend -> normalise -> warp -> masks
+    g = torch.Generator().manual_seed(4242)
+    lens = sorted(torch.randint(16000, 64001, (6,), generator=g).tolist(), reverse=True)
+    wav = _wave(21, lens, zero_seg=False)
+    conf = dict(n_mels=80, win_length=0.025, hop_length=0.010, sr=16000, preemphasis=0.97)  # n_fft = 400
+    sconf = dict(freq_mask_width=15, freq_mask_num=4, time_mask_width=0.05, time_mask_num=5)
+    chain = AcousticFrontend(frontend=dict(conf=conf), normalize=dict(norm_type=norm_type), specaug=sconf).to(DEV)
+    chain.train()
+    torch.manual_seed(99)
+    y, yl = chain(wav.to(DEV)[..., None], torch.tensor(lens, device=DEV), epoch=1)
+    feat, flen, _ = O.speech2mel(wav.numpy().astype(np.float64), lens, O.FrontendCfg(**conf))
+    if norm_type == "utterance":
+        ref = O.feat_norm_utterance(feat, flen)
+    else:
+        ref = O.feat_norm_global([(feat, flen)], O.RunningStats(), 1)[0]
+    d = O.specaug_draw(O.TorchCpuRandint(99), len(lens), 80, flen, O.SpecAugCfg(**sconf))
+    assert d.warp is not None
+    ref = O.specaug_apply(ref, flen, d, feat_norm=True)
+    got = y.cpu().numpy()
+    mask = O.specaug_mask(*got.shape, d)
+    assert (got[mask] == 0.0).all() and np.count_nonzero((got == 0.0) & ~mask) <= 2
+    assert_close(got, ref, what=f"warp chain {norm_type}")
