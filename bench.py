@@ -47,6 +47,23 @@ WORKLOADS = {
                frontend=dict(sr=22050, n_mels=80, win_length=1024, hop_length=256, mag_spec=True, fmin=0, fmax=8000,
                              log_base=None, clamp=1e-5, return_energy=True),
                normalize=None, specaug=None),
+    # BASELINE.json configs[3]: 2048 x 30 s split by utterance over 8 GPUs = 256 utterances per GPU (weak scaling
+    # at other N), global normalisation in training mode: one packed (2D+1)-float all-reduce per step
+    "c4": dict(desc="C4: sharded extraction, 256 x 30 s @16 kHz per GPU (2048 over 8), 80-Mel + global norm "
+                    "(training, epoch=None) with the statistics all-reduce over NCCL",
+               sr=16000, B=256, fixed_len=480000, seed=1238,
+               frontend=dict(n_mels=80, n_fft=512, win_length=0.025, hop_length=0.010, sr=16000),
+               normalize=dict(norm_type="global"), specaug=None, epoch=None),
+    # BASELINE.json configs[4]: one batch of the offline TTS->ASR re-extraction (128 utterances 2-12 s @22.05 kHz):
+    # linear magnitude spectrogram AND mel from one launch, mel -> global norm (epoch=1) -> SpecAugment
+    "c5": dict(desc="C5: TTS->ASR chain batch, 128 x 2-12 s @22.05 kHz, linear (513 bins) + 80-Mel, global norm "
+                    "(running average, epoch=1) + SpecAugment",
+               sr=22050, B=128, len_range=(44100, 264601), seed=1239,
+               frontend=dict(sr=22050, n_mels=80, win_length=1024, hop_length=256, mag_spec=True, fmin=0, fmax=8000,
+                             log_base=None, clamp=1e-5),
+               normalize=dict(norm_type="global"),
+               specaug=dict(time_warp=False, freq_mask_width=30, freq_mask_num=2, time_mask_width=0.05,
+                            time_mask_num=2), epoch=1, want_lin=True),
 }
 
 
@@ -148,7 +165,10 @@ def cpu_pass(w, wav, wl, weight, port):
                                       mag_spec=fc.get("mag_spec", False), return_energy=fc.get("return_energy", False))
     feat = port.linear2mel(spec, weight, clamp=fc.get("clamp", 1e-10), logging=True, log_base=fc.get("log_base", 10.0))
     if w["normalize"] is not None:
-        feat = port.norm_utterance(feat, fl)
+        if w["normalize"].get("norm_type") == "global":
+            feat = port.norm_global_train(feat, fl, w.setdefault("_cpu_state", {}), w.get("epoch"))
+        else:
+            feat = port.norm_utterance(feat, fl)
     if w["specaug"] is not None:
         s = w["specaug"]
         feat = port.specaug(feat, fl, freq_mask_width=(0, s["freq_mask_width"]), freq_mask_num=s["freq_mask_num"],
@@ -268,8 +288,19 @@ def main():
     wl_host = torch.tensor(lens, dtype=torch.int64)
     ops.HostLengths.remember(wl_dev, wl_host.numpy())
 
+    epoch = w.get("epoch")
+    want_lin = w.get("want_lin", False)
+
     def step(i):
-        return chain(batches[i % ring], wl_dev)
+        if not want_lin:
+            return chain(batches[i % ring], wl_dev, epoch=epoch)
+        # C5: linear + mel from ONE launch, then the mel goes through normalise + SpecAugment in one pass
+        out = fe.run(batches[i % ring], wl_dev, want_lin=True, want_stats=True)
+        y = out["mel"]
+        y._sfe_stats = (y._version, out["stats"])
+        _, masks = chain.specaug.draw_device(B, D, out["feat_len_host"], dev)
+        y, ylen = chain.normalize.forward(y, out["feat_len"], epoch=epoch, masks=masks, inplace=True)
+        return y, ylen, out["lin"]
 
     torch.manual_seed(1234 + rank)
     sampler = ClockSampler(local)
@@ -303,6 +334,8 @@ def main():
     # ---- (2) the dominant kernel alone (fused frontend), same arguments as inside the step ----
     two_pass = w["normalize"] is not None
     kw = dict(want_stats=True, skip_pad=True) if two_pass else {}
+    if want_lin:
+        kw = dict(want_lin=True, want_stats=True)
     for i in range(3):
         fe.run(batches[i % ring], wl_dev, **kw)
     torch.cuda.synchronize()
@@ -339,7 +372,7 @@ def main():
                     ops.upload_waveforms(host[(i + 1) % 2], wl_host, out=dbuf[1 - s])
                     ready[1 - s].record(copy_stream)
             main_stream.wait_event(ready[s])
-            ylen = chain(dbuf[s], wl_host)[1]       # lengths arrive on the host, like a collated batch
+            ylen = chain(dbuf[s], wl_host, epoch=epoch)[1]       # lengths arrive on the host, like a collated batch
             free[s].record(main_stream)
             res_host.copy_(ylen, non_blocking=True)
         main_stream.synchronize()
@@ -368,7 +401,11 @@ def main():
     peak, peak_src = load_peaks()
     S = sum(lens)
     valid_frames = sum(min(f, F) for f in flen)
-    if two_pass:
+    K = fe.speech2linear.output_size
+    if want_lin:
+        kern_bytes = 4 * S + 4 * B * F * K + 4 * B * F * D          # linear + raw mel written once
+        step_bytes = kern_bytes + 2 * 4 * B * F * D                 # + mel read and re-written normalised/masked
+    elif two_pass:
         kern_bytes = 4 * S + 4 * valid_frames * D          # reads valid samples, writes valid raw rows
         step_bytes = 4 * S + 4 * B * F * D                 # input once + padded output once
     else:
@@ -389,7 +426,7 @@ def main():
                 "note": "pinned host (B,T,1) waveforms -> ops.upload_waveforms (valid samples only) -> public API "
                         "AcousticFrontend.forward; copy of step i+1 overlapped with step i; D2H = feature lengths "
                         "(the features stay on the GPU for the model)"},
-        "gpu_launches": steps * (2 if two_pass else 1),
+        "gpu_launches": steps * ({"utterance": 2, "global": 4}.get((w["normalize"] or {}).get("norm_type"), 1)),
         "roofline": {"bound": "hbm", "kernel": "sfe::fused_frontend_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": kern_bytes, "us_per_launch": kern_ms * 1e3,

@@ -420,3 +420,35 @@ def test_fused_chain_with_time_warp_vs_oracle(norm_type):
     mask = O.specaug_mask(*got.shape, d)
     assert (got[mask] == 0.0).all() and np.count_nonzero((got == 0.0) & ~mask) <= 2
     assert_close(got, ref, what=f"warp chain {norm_type}")
+
+
+def test_c5_style_linear_and_mel_from_one_launch_with_running_global_norm():
+    # BASELINE config 5 in miniature: magnitude linear spectrogram AND mel from one launch; mel -> global norm with
+    # the running average over several batches (epoch=1) -> SpecAugment
+    conf = dict(sr=22050, n_mels=80, win_length=1024, hop_length=256, mag_spec=True, fmin=0, fmax=8000, log_base=None,
+                clamp=1e-5)
+    fe = Speech2MelSpec(**conf).to(DEV)
+    gn = FeatureNormalization(input_size=80, norm_type="global").to(DEV)
+    gn.train()
+    sa = SpecAugment(input_size=80, time_warp=False).to(DEV)
+    st = O.RunningStats()
+    g = torch.Generator().manual_seed(555)
+    torch.manual_seed(7)
+    rng = O.TorchCpuRandint(7)
+    for step in range(3):
+        lens = sorted(torch.randint(2 * 22050, 5 * 22050, (5,), generator=g).tolist(), reverse=True)
+        wav = _wave(30 + step, lens, zero_seg=False)
+        out = fe.run(wav.to(DEV), torch.tensor(lens, device=DEV), want_lin=True, want_stats=True)
+        y = out["mel"]
+        y._sfe_stats = (y._version, out["stats"])
+        _, masks = sa.draw_device(len(lens), 80, out["feat_len_host"], DEV)
+        y, _ = gn.forward(y, out["feat_len"], epoch=1, masks=masks, inplace=True)
+        cfg = O.FrontendCfg(**conf)
+        lin_ref, flen, _ = O.speech2linear(wav.numpy().astype(np.float64), lens, O.FrontendCfg(**{**cfg.__dict__}))
+        assert_close(out["lin"].cpu().numpy(), lin_ref, what=f"linear {step}")
+        feat, _, _ = O.speech2mel(wav.numpy().astype(np.float64), lens, cfg)
+        ref = O.feat_norm_global([(feat, flen)], st, 1)[0]
+        d = O.specaug_draw(rng, len(lens), 80, flen, O.SpecAugCfg(time_warp=False))
+        ref = O.specaug_apply(ref, flen, d, feat_norm=True)
+        assert_close(y.cpu().numpy(), ref, what=f"mel {step}")
+        assert int(gn.global_batch.item()) == step + 1
