@@ -126,15 +126,15 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // ---------------------------------------------------------------------------------------------
 // FFT plan (compile time)
 // ---------------------------------------------------------------------------------------------
-template <int M_, int G_, int R1_, int R2_, int R3_>
+template <int M_, int G_, int R1_, int R2_, int R3_, int PADQ_ = R1_>
 struct FftPlan {
   static constexpr int M = M_;     // complex FFT length = n_fft / 2
   static constexpr int G = G_;     // lanes cooperating on one frame (16 or 32)
   static constexpr int R1 = R1_, R2 = R2_, R3 = R3_;
   static constexpr int C = 32 / G_;        // frames in flight per warp
   static constexpr int S = FPW / C;        // sequential sub-iterations per tile
-  static constexpr int PADQ = R1_;         // one padding slot every PADQ complex values
-  static constexpr int MP = M_ + M_ / R1_ + 1;
+  static constexpr int PADQ = PADQ_;       // one padding slot every PADQ complex values
+  static constexpr int MP = M_ + M_ / PADQ_ + 1;
   // the power spectrum may overwrite the FFT scratch only if no later FFT of the tile needs it
   static constexpr bool ALIAS_P2 = (S == 1);
   static constexpr int MINB = (M_ == 256 || M_ == 240) ? 3 : ((M_ <= 512) ? 2 : 1);  // resident CTAs per SM aimed for

@@ -37,9 +37,9 @@ struct FftEntry {
   fused_fn fn[2];  // [0] no pre-emphasis, [1] pre-emphasis applied while loading
 };
 
-template <int M, int G, int R1, int R2, int R3>
+template <int M, int G, int R1, int R2, int R3, int PADQ = R1>
 static FftEntry make_entry() {
-  typedef FftPlan<M, G, R1, R2, R3> PL;
+  typedef FftPlan<M, G, R1, R2, R3, PADQ> PL;
   return FftEntry{2 * M, M, G, R1, R2, R3, PL::MP, PL::C, {&fused_frontend_kernel<PL, false>, &fused_frontend_kernel<PL, true>}};
 }
 
@@ -54,7 +54,7 @@ static const std::vector<FftEntry>& registry() {
       make_entry<256, 16, 16, 16, 1>(),   // n_fft 512
       make_entry<320, 32, 16, 5, 4>(),    // n_fft 640
       make_entry<400, 32, 16, 5, 5>(),    // n_fft 800
-      make_entry<512, 32, 8, 8, 8>(),     // n_fft 1024 (TTS recipes)
+      make_entry<512, 32, 4, 8, 16, 16>(),  // n_fft 1024 (TTS recipes): last radix-16 pass stays in registers
       make_entry<1024, 32, 16, 8, 8>(),   // n_fft 2048
   };
   return r;
