@@ -126,9 +126,12 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // ---------------------------------------------------------------------------------------------
 // FFT plan (compile time)
 // ---------------------------------------------------------------------------------------------
-template <int M_, int G_, int R1_, int R2_, int R3_, int PADQ_ = R1_>
+// WIN_ > 0 fixes the window length at compile time (the common (n_fft, win_length) pairs): the rows of the
+// first pass that fall into the window's zero padding, and every test against `win`, vanish from the code.
+template <int M_, int G_, int R1_, int R2_, int R3_, int PADQ_ = R1_, int WIN_ = 0>
 struct FftPlan {
   static constexpr int M = M_;     // complex FFT length = n_fft / 2
+  static constexpr int WIN = WIN_;
   static constexpr int G = G_;     // lanes cooperating on one frame (16 or 32)
   static constexpr int R1 = R1_, R2 = R2_, R3 = R3_;
   static constexpr int C = 32 / G_;        // frames in flight per warp
@@ -160,6 +163,7 @@ __device__ __forceinline__ void stockham_pass(cpx* __restrict__ Z, const cpx* __
   constexpr int T = M / R;
   constexpr int NR = (T + G - 1) / G;
   constexpr bool FULL = (T % G == 0);
+  if (PL::WIN > 0) win = PL::WIN;  // compile-time window length: the row tests below fold away
   cpx u[NR][R];
 #pragma unroll
   for (int rd = 0; rd < NR; ++rd) {

@@ -33,14 +33,15 @@ static int fail(int code, const std::string& msg) {
 typedef void (*fused_fn)(const FwdParams);
 
 struct FftEntry {
-  int n_fft, M, G, R1, R2, R3, MP, C;
+  int n_fft, win;  // win == 0: any window length (run-time tests)
+  int M, G, R1, R2, R3, MP, C;
   fused_fn fn[2];  // [0] no pre-emphasis, [1] pre-emphasis applied while loading
 };
 
-template <int M, int G, int R1, int R2, int R3, int PADQ = R1>
+template <int M, int G, int R1, int R2, int R3, int PADQ = R1, int WIN = 0>
 static FftEntry make_entry() {
-  typedef FftPlan<M, G, R1, R2, R3, PADQ> PL;
-  return FftEntry{2 * M, M, G, R1, R2, R3, PL::MP, PL::C, {&fused_frontend_kernel<PL, false>, &fused_frontend_kernel<PL, true>}};
+  typedef FftPlan<M, G, R1, R2, R3, PADQ, WIN> PL;
+  return FftEntry{2 * M, WIN, M, G, R1, R2, R3, PL::MP, PL::C, {&fused_frontend_kernel<PL, false>, &fused_frontend_kernel<PL, true>}};
 }
 
 static const std::vector<FftEntry>& registry() {
@@ -56,6 +57,10 @@ static const std::vector<FftEntry>& registry() {
       make_entry<400, 32, 16, 5, 5>(),    // n_fft 800
       make_entry<512, 32, 4, 8, 16, 16>(),  // n_fft 1024 (TTS recipes): last radix-16 pass stays in registers
       make_entry<1024, 32, 16, 8, 8>(),   // n_fft 2048
+      // window length fixed at compile time for the (n_fft, win_length) pairs of the shipped recipes
+      make_entry<200, 16, 8, 5, 5, 8, 400>(),      // 25 ms window @16 kHz, n_fft = win (ASR recipe default)
+      make_entry<256, 16, 16, 16, 1, 16, 400>(),   // 25 ms window @16 kHz in a 512-point FFT (BASELINE C1/C2)
+      make_entry<512, 32, 4, 8, 16, 16, 1024>(),   // 1024/1024 (TTS recipes, BASELINE C3)
   };
   return r;
 }
@@ -81,8 +86,13 @@ extern "C" const char* sfe_last_error(void) { return g_err.c_str(); }
 
 extern "C" int sfe_supported_nfft(int32_t* out, int cap) {
   const auto& r = registry();
-  for (int i = 0; i < static_cast<int>(r.size()) && i < cap; ++i) out[i] = r[i].n_fft;
-  return static_cast<int>(r.size());
+  int n = 0;
+  for (const auto& e : r)
+    if (e.win == 0) {
+      if (n < cap) out[n] = e.n_fft;
+      ++n;
+    }
+  return n;
 }
 
 static int round_up(int x, int a) { return (x + a - 1) / a * a; }
@@ -100,7 +110,7 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
   if (cfg->n_mels > 0 && !cfg->mel_weight_host) return fail(SFE_ERR_BAD_CONFIG, "mel_weight_host is NULL");
   const FftEntry* fe = nullptr;
   for (const auto& e : registry())
-    if (e.n_fft == cfg->n_fft) fe = &e;
+    if (e.n_fft == cfg->n_fft && (e.win == 0 || e.win == cfg->win_length) && (!fe || e.win != 0)) fe = &e;
   if (!fe) {
     std::string s = "unsupported n_fft " + std::to_string(cfg->n_fft) + "; compiled plans:";
     for (const auto& e : registry()) s += " " + std::to_string(e.n_fft);
