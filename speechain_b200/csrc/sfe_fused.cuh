@@ -337,24 +337,30 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
   __shared__ int s_cum[COMPACT_MAX_B + 1];  // compact mode: first tile index of every utterance
   __shared__ int s_ntiles;
 
-  // ---- one-time setup: tables -> smem, zero the scratch, init the mbarriers ----
-  {
-    const float4* src = reinterpret_cast<const float4*>(p.tables);
-    float4* dst = reinterpret_cast<float4*>(tab);
-    for (int i = tid; i < p.tab_floats / 4; i += NTHREADS) dst[i] = __ldg(src + i);
-    float* st = reinterpret_cast<float*>(smem + p.sm_stage);
-    for (int i = tid; i < p.nstage * p.sm_stage_floats; i += NTHREADS) st[i] = 0.f;
-    float* wz = reinterpret_cast<float*>(wbase);
-    for (int i = lane; i < p.sm_warp_bytes / 4; i += 32) wz[i] = 0.f;
-    int* acc = reinterpret_cast<int*>(smem + p.sm_acc);
-    for (int i = tid; i < NSTAGE * 4 * p.D; i += NTHREADS) acc[i] = 0;
-  }
+  // ---- one-time setup: mbarriers, tables -> smem with one bulk copy, zero what must be zero ----
+  // (the staging buffers need no initialisation: every read of them is either covered by a copy or
+  //  replaced by a select, see the first Stockham pass)
   const uint32_t bar0 = smem_u32(barp);
   if (tid == 0) {
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8, 1);
+    mbar_init(bar0 + 16, 1);
     fence_mbar_init();
+    const uint32_t bytes = static_cast<uint32_t>(p.tab_floats) * 4u;
+    mbar_expect_tx(bar0 + 16, bytes);
+    bulk_g2s(smem_u32(tab), p.tables, bytes, bar0 + 16);
   }
+  {
+    int* acc = reinterpret_cast<int*>(smem + p.sm_acc);
+    for (int i = tid; i < NSTAGE * 4 * p.D; i += NTHREADS) acc[i] = 0;
+    if (!PL::ALIAS_P2) {
+      // zero-weight padding taps of the mel filter read past bin K-1 (aliased layouts redo this per frame)
+      float* p2 = reinterpret_cast<float*>(wbase + p.sm_p2_off);
+      for (int i = lane; i < (p.mel_tail + 2) * FPW; i += 32) p2[p.K * FPW + i] = 0.f;
+    }
+  }
+  __syncthreads();               // barrier inits are visible before anyone waits on them
+  mbar_wait(bar0 + 16, 0u);      // tables have landed
   uint32_t parity[NSTAGE] = {0u, 0u};
 
   // Tiles that hold only frames past an utterance's length have nothing to compute.  When they have
@@ -540,6 +546,7 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
         }
         stage[EDGE_SHIFT + i] = v;
       }
+      if (tid == 0) stage[EDGE_SHIFT - 1] = 0.f;  // read (times a zero coefficient) as the predecessor of sample 0
       __syncthreads();
     }
 

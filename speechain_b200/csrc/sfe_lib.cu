@@ -271,7 +271,7 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
     P.sm_acc = round_up(o, 16);  // [NSTAGE][D][2] fixed-point sums of the tile in flight
     o = P.sm_acc + NSTAGE * (D > 0 ? D : 1) * 4 * 4;
     P.sm_bar = round_up(o, 16);
-    pl->smem_bytes = P.sm_bar + 16;
+    pl->smem_bytes = P.sm_bar + 32;
     if (pl->smem_bytes <= smem_limit) break;
   }
   if (P.nstage < 1) P.nstage = 1;
