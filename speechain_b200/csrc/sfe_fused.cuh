@@ -19,6 +19,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "sfe_fft.cuh"
 
 namespace sfe {
@@ -676,60 +678,80 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
           tm1 |= (tA + 1 >= ps) && (tA + 1 < ps + ln);
         }
       }
-      int wofs = 0;  // in float2 units
-      for (int ph = 0; ph < p.mel_rounds; ++ph) {
-        const int st = mstart[ph * 32 + lane];
-        const int oinfo = mout[ph * 32 + lane];
-        const float2* pp = P2v + st;
-        const int n2 = p.mel_taps[ph] >> 1;
-        const float2* wp = mw2 + wofs + lane;
-        float2 accA = make_float2(0.f, 0.f), accB = make_float2(0.f, 0.f);  // (frame 0, frame 1) pairs
+      // The option flags are kernel constants: pick one of eight straight-line variants per tile instead
+      // of testing them for every bin.
+      auto mel_stage = [&](auto kLogT, auto kStatsT, auto kFancyT) {
+        constexpr bool kLog = decltype(kLogT)::value, kStats = decltype(kStatsT)::value,
+                       kFancy = decltype(kFancyT)::value;
+        const float clampv = p.mel_clamp, lmul = p.mel_lmul;
+        int wofs = 0;  // in float2 units
+        const int nph = p.mel_rounds;
+        for (int ph = 0; ph < nph; ++ph) {
+          const int st = mstart[ph * 32 + lane];
+          const int oinfo = mout[ph * 32 + lane];
+          const float2* pp = P2v + st;
+          const int n2 = p.mel_taps[ph] >> 1;
+          const float2* wp = mw2 + wofs + lane;
+          float2 accA = make_float2(0.f, 0.f), accB = make_float2(0.f, 0.f);  // (frame 0, frame 1) pairs
 #pragma unroll 2
-        for (int q = 0; q < n2; ++q) {
-          const float2 wq = wp[q * 32];
-          const float2 p0 = pp[2 * q], p1 = pp[2 * q + 1];
-          accA = f2fma(make_float2(wq.x, wq.x), p0, accA);
-          accB = f2fma(make_float2(wq.y, wq.y), p1, accB);
-        }
-        const float2 accs = f2add(accA, accB);
-        float acc0 = accs.x, acc1 = accs.y;
-        wofs += n2 * 32;
-        if ((p.mel_split_mask >> ph) & 1u) {  // bins wider than a unit: add the partner lane's half
-          const float o0 = __shfl_xor_sync(0xffffffffu, acc0, 1), o1 = __shfl_xor_sync(0xffffffffu, acc1, 1);
-          if (oinfo & 0x10000) { acc0 += o0; acc1 += o1; }
-        }
-        if (oinfo >= 0) {  // this lane publishes bin d
-          const int d = oinfo & 0xffff;
-          float x0 = acc0, x1 = acc1;
-          if (p.mel_log) {
-            x0 = fast_log(x0, p.mel_clamp, p.mel_lmul);
-            x1 = fast_log(x1, p.mel_clamp, p.mel_lmul);
+          for (int q = 0; q < n2; ++q) {
+            const float2 wq = wp[q * 32];
+            const float2 p0 = pp[2 * q], p1 = pp[2 * q + 1];
+            accA = f2fma(make_float2(wq.x, wq.x), p0, accA);
+            accB = f2fma(make_float2(wq.y, wq.y), p1, accB);
           }
-          if (p.stats) {
-            // pair sums in fp32, then exact order-independent fixed-point accumulation
-            const float s1 = x0 * v0 + x1 * v1;
-            const float s2 = fmaf(x0 * v0, x0, x1 * v1 * x1);
-            // (64-bit shared atomics are CAS loops; two native 32-bit adds on disjoint bit ranges are not)
-            const long long f1 = __float2ll_rn(s1 * 4294967296.f), f2 = __float2ll_rn(s2 * 16777216.f);
-            atomicAdd(sacc + 4 * d + 0, static_cast<int>(f1 >> 24));
-            atomicAdd(sacc + 4 * d + 1, static_cast<int>(f1 & 0xffffff));
-            atomicAdd(sacc + 4 * d + 2, static_cast<int>(f2 >> 24));
-            atomicAdd(sacc + 4 * d + 3, static_cast<int>(f2 & 0xffffff));
+          float2 acc = f2add(accA, accB);
+          wofs += n2 * 32;
+          if ((p.mel_split_mask >> ph) & 1u) {  // bins wider than a unit: add the partner lane's half
+            const float o0 = __shfl_xor_sync(0xffffffffu, acc.x, 1), o1 = __shfl_xor_sync(0xffffffffu, acc.y, 1);
+            if (oinfo & 0x10000) acc = f2add(acc, make_float2(o0, o1));
           }
-          if (fancy) {
-            if (p.norm_mean) { const float nm = p.norm_mean[d]; x0 -= nm; x1 -= nm; }
-            if (p.norm_std) { const float ns = p.norm_std[d]; x0 /= ns; x1 /= ns; }
-            bool fm = false;
-            for (int q = 0; q < n_fmask; ++q) {
-              const int ps = m_fpos[b * n_fmask + q], ln = m_flen[b * n_fmask + q];
-              fm |= (d >= ps) && (d < ps + ln);
+          if (oinfo >= 0) {  // this lane publishes bin d
+            const int d = oinfo & 0xffff;
+            float x0 = acc.x, x1 = acc.y;
+            if (kLog) {
+              x0 = fast_log(x0, clampv, lmul);
+              x1 = fast_log(x1, clampv, lmul);
             }
-            if (fm || tm0) x0 = fillv;
-            if (fm || tm1) x1 = fillv;
+            if (kStats) {
+              // pair sums in fp32, then exact order-independent fixed-point accumulation
+              const float s1 = x0 * v0 + x1 * v1;
+              const float s2 = fmaf(x0 * v0, x0, x1 * v1 * x1);
+              // (64-bit shared atomics are CAS loops; two native 32-bit adds on disjoint bit ranges are not)
+              const long long f1 = __float2ll_rn(s1 * 4294967296.f), f2 = __float2ll_rn(s2 * 16777216.f);
+              atomicAdd(sacc + 4 * d + 0, static_cast<int>(f1 >> 24));
+              atomicAdd(sacc + 4 * d + 1, static_cast<int>(f1 & 0xffffff));
+              atomicAdd(sacc + 4 * d + 2, static_cast<int>(f2 >> 24));
+              atomicAdd(sacc + 4 * d + 3, static_cast<int>(f2 & 0xffffff));
+            }
+            if (kFancy) {
+              if (p.norm_mean) { const float nm = p.norm_mean[d]; x0 -= nm; x1 -= nm; }
+              if (p.norm_std) { const float ns = p.norm_std[d]; x0 /= ns; x1 /= ns; }
+              bool fm = false;
+              for (int q = 0; q < n_fmask; ++q) {
+                const int ps = m_fpos[b * n_fmask + q], ln = m_flen[b * n_fmask + q];
+                fm |= (d >= ps) && (d < ps + ln);
+              }
+              if (fm || tm0) x0 = fillv;
+              if (fm || tm1) x1 = fillv;
+            }
+            float* o = mel_row + d;
+            if (w0) o[0] = x0;
+            if (w1) o[D] = x1;
           }
-          if (w0) mel_row[d] = x0;
-          if (w1) mel_row[D + d] = x1;
         }
+      };
+      using T1 = std::true_type;
+      using T0 = std::false_type;
+      switch ((p.mel_log ? 1 : 0) | (p.stats ? 2 : 0) | (fancy ? 4 : 0)) {
+        case 0: mel_stage(T0{}, T0{}, T0{}); break;
+        case 1: mel_stage(T1{}, T0{}, T0{}); break;
+        case 2: mel_stage(T0{}, T1{}, T0{}); break;
+        case 3: mel_stage(T1{}, T1{}, T0{}); break;
+        case 4: mel_stage(T0{}, T0{}, T1{}); break;
+        case 5: mel_stage(T1{}, T0{}, T1{}); break;
+        case 6: mel_stage(T0{}, T1{}, T1{}); break;
+        default: mel_stage(T1{}, T1{}, T1{}); break;
       }
     }
 
