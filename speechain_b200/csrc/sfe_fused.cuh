@@ -535,18 +535,26 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
       const long long o_start = static_cast<long long>(t0) * hop + p.off;
       const float* row = p.wav + static_cast<long long>(b) * p.pitch;
       const int n = (TILE_F - 1) * hop + win;
-      for (int i = tid; i < n; i += NTHREADS) {
-        long long o = o_start + i;
-        if (p.center) {
-          if (o < 0) o = -o;
-          if (o >= p.T_max) o = 2 * (p.T_max - 1) - o;
+      // eight independent loads (sixteen with pre-emphasis) in flight per thread: the gather is pure latency
+      for (int i0 = tid; i0 < n; i0 += NTHREADS * 8) {
+        float v[8], pv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * NTHREADS;
+          long long o = o_start + i;
+          if (p.center) {
+            if (o < 0) o = -o;
+            if (o >= p.T_max) o = 2 * (p.T_max - 1) - o;
+          }
+          const bool ok = (i < n) && (o >= 0) && (o < len);
+          v[u] = ok ? __ldg(row + o) : 0.f;
+          pv[u] = (ok && p.has_pre && o > 0) ? __ldg(row + o - 1) : 0.f;
         }
-        float v = 0.f;
-        if (o >= 0 && o < len) {
-          v = __ldg(row + o);
-          if (p.has_pre && o > 0) v = fmaf(-p.pre, __ldg(row + o - 1), v);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * NTHREADS;
+          if (i < n) stage[EDGE_SHIFT + i] = fmaf(-p.pre, pv[u], v[u]);
         }
-        stage[EDGE_SHIFT + i] = v;
       }
       if (tid == 0) stage[EDGE_SHIFT - 1] = 0.f;  // read (times a zero coefficient) as the predecessor of sample 0
       __syncthreads();
