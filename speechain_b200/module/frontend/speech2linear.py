@@ -91,6 +91,33 @@ class Speech2LinearSpec(Module):
                 wav = (wav - lo) / (hi - lo) * 2 - 1
         return wav, len_dev, len_host, in_kernel
 
+    def _kernel_lengths(self, wav, len_dev, in_kernel):
+        """After a waveform pre-normalisation the padding is no longer silence (min_max maps 0 to a constant),
+        and the reference's STFT sees it: let the kernel read whole rows.  (The kernel otherwise defines
+        samples beyond a length as zero.)"""
+        return len_dev if in_kernel else torch.full_like(len_dev, wav.size(1))
+
+    def _fix_padded_rows(self, out, len_dev, in_kernel, plan):
+        """Rare pre_stft_norm path: the kernel ran with full-row lengths, so rows t >= feat_len still hold
+        spectra of the padding; reset them like speech2linear.py:226-233 / linear2mel.py:177-187 do."""
+        if in_kernel:
+            return
+        n = len_dev + 2 * (self.n_fft // 2) if self.stft_config["center"] else len_dev
+        feat_len = torch.div(n - self.n_fft, self.hop_length, rounding_mode="floor") + 1
+        F = next(v for k, v in out.items() if k in ("mel", "lin") and v is not None).size(1)
+        pad = torch.arange(F, device=len_dev.device)[None, :] >= feat_len[:, None]
+        if out.get("mel") is not None:
+            out["mel"].masked_fill_(pad[..., None], plan.pad_mel)
+        if out.get("lin") is not None:
+            import math
+            pad_lin = 0.0
+            if self.logging:
+                pad_lin = math.log(self.clamp) / (math.log(self.log_base) if self.log_base is not None else 1.0)
+            out["lin"].masked_fill_(pad[..., None], pad_lin)
+        if out.get("energy") is not None:
+            out["energy"].masked_fill_(pad, 0.0)
+        out["feat_len"] = feat_len
+
     def _feat_len_host(self, len_host):
         """numpy int64 feature lengths from numpy sample lengths (speech2linear.py:201-212)."""
         n = len_host + 2 * (self.n_fft // 2) if self.stft_config["center"] else len_host
@@ -108,7 +135,9 @@ class Speech2LinearSpec(Module):
         (linear_spec, feat_len, energy (batch, F), energy_len)."""
         wav, len_dev, len_host, in_kernel = self._prepare(speech, speech_len)
         plan = self._plan(wav.device, preemph=in_kernel)
-        out = plan.forward(wav, len_dev, want_mel=False, want_lin=True, want_energy=self.return_energy)
+        out = plan.forward(wav, self._kernel_lengths(wav, len_dev, in_kernel), want_mel=False, want_lin=True,
+                           want_energy=self.return_energy)
+        self._fix_padded_rows(out, len_dev, in_kernel, plan)
         feat_len = out["feat_len"]
         HostLengths.remember(feat_len, self._feat_len_host(len_host))
         if self.return_energy:

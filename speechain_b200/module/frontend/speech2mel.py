@@ -47,7 +47,11 @@ class Speech2MelSpec(Module):
         s2l = self.speech2linear
         wav, len_dev, len_host, in_kernel = s2l._prepare(speech, speech_len)
         plan = s2l._plan(wav.device, preemph=in_kernel, mel=self.linear2mel.mel_conf())
-        out = plan.forward(wav, len_dev, want_mel=True, want_energy=self.return_energy, **kernel_kw)
+        if not in_kernel and kernel_kw.get("want_stats"):
+            kernel_kw = dict(kernel_kw, want_stats=False)  # sums of the padded rows would be wrong on this path
+        out = plan.forward(wav, s2l._kernel_lengths(wav, len_dev, in_kernel), want_mel=True,
+                           want_energy=self.return_energy, **kernel_kw)
+        s2l._fix_padded_rows(out, len_dev, in_kernel, plan)
         out["feat_len_host"] = s2l._feat_len_host(len_host)
         out["pad_value"] = plan.pad_mel
         HostLengths.remember(out["feat_len"], out["feat_len_host"])
@@ -61,7 +65,7 @@ class Speech2MelSpec(Module):
         feat, feat_len = out["mel"], out["feat_len"]
         if self.delta_order is not None:
             feat, feat_len = self.delta(feat, feat_len)
-        elif stats:
+        elif stats and out.get("stats") is not None:
             # side channel for FeatureNormalization (valid while `feat` is not modified in place)
             feat._sfe_stats = (feat._version, out["stats"])
         if self.return_energy:

@@ -134,6 +134,10 @@ def main():
     frontend_case("fe_nfft256", [3000, 2000, 999], 1242, dict(n_mels=40, n_fft=256, win_length=200, hop_length=80, sr=8000))
     frontend_case("fe_nfft2048", [12000, 7000], 1243, dict(n_mels=128, n_fft=2048, win_length=1200, hop_length=300, sr=24000))
     frontend_case("fe_delta2", [4000, 2500], 1244, dict(C1, delta_order=2), port_check=True)
+    # waveform pre-normalisation (no shipped recipe uses it): min_max for a batch, mean_std for one utterance
+    frontend_case("fe_prenorm_minmax", [4000, 2600, 1700], 1246, dict(C1, preemphasis=0.97, pre_stft_norm="min_max"),
+                  port_check=False)
+    frontend_case("fe_prenorm_meanstd", [4000], 1247, dict(C1, pre_stft_norm="mean_std"), port_check=False)
     # odd T_max / odd lengths: row pitch not a multiple of 4 samples
     frontend_case("fe_oddpitch", [5003, 5003, 4999, 1234, 161], 1245, dict(C1, preemphasis=0.97))
 

@@ -20,6 +20,9 @@ FE_CASES = {
     "fe_delta2": dict(n_mels=80, n_fft=512, win_length=0.025, hop_length=0.010, delta_order=2),
     "fe_oddpitch": dict(n_mels=80, n_fft=512, win_length=0.025, hop_length=0.010, preemphasis=0.97),
     "chain_c2_fe": dict(n_mels=80, n_fft=512, win_length=0.025, hop_length=0.010, preemphasis=0.97),
+    "fe_prenorm_minmax": dict(n_mels=80, n_fft=512, win_length=0.025, hop_length=0.010, preemphasis=0.97,
+                              pre_stft_norm="min_max"),
+    "fe_prenorm_meanstd": dict(n_mels=80, n_fft=512, win_length=0.025, hop_length=0.010, pre_stft_norm="mean_std"),
 }
 
 
