@@ -39,7 +39,7 @@ class LinearSpec2MelSpec(Module):
                     weight=self.mel_fbanks.weight)
 
     def _plan(self, device) -> FrontendPlan:
-        key = str(device)
+        key = (str(device), self.mel_fbanks.weight._version)
         plan = self._plans.get(key)
         if plan is None:
             plan = FrontendPlan(n_fft=self.n_fft, win_length=self.n_fft, hop_length=1, window=torch.ones(self.n_fft),

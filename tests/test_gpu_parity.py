@@ -452,3 +452,17 @@ def test_c5_style_linear_and_mel_from_one_launch_with_running_global_norm():
         ref = O.specaug_apply(ref, flen, d, feat_norm=True)
         assert_close(y.cpu().numpy(), ref, what=f"mel {step}")
         assert int(gn.global_batch.item()) == step + 1
+
+
+def test_checkpoint_load_rebuilds_the_plan():
+    # load_state_dict copies into the filterbank buffer in place: the cached plan must not go stale
+    g = load_golden("fe_c1")
+    m = Speech2MelSpec(**FE_CASES["fe_c1"]).to(DEV)
+    wav, wl = cu(g["wav"])[..., None], cu(g["wav_len"])
+    a, _ = m(wav, wl)
+    sd = m.state_dict()
+    sd["linear2mel.mel_fbanks.weight"] = sd["linear2mel.mel_fbanks.weight"] * 2.0
+    m.load_state_dict(sd, strict=True)
+    b, _ = m(wav, wl)
+    valid = int(g["feat_len"][0])
+    assert torch.allclose(b[0, :valid][a[0, :valid] > -9.9], a[0, :valid][a[0, :valid] > -9.9] + np.log10(2.0), atol=1e-4)
