@@ -133,12 +133,17 @@ int sfe_frontend_forward(const sfe_plan* plan, const float* wav, int64_t wav_pit
  *   norm_mode 1  statistics known up front (mean/std vectors (n_mels,), either may be NULL): one
  *                launch, (x-mean)/std and masks in the epilogue         (feat_norm.py:327-336)
  *   norm_mode 2  utterance statistics: launch 1 writes the valid rows and the fixed-point sums into
- *                stats_ws (B, n_mels, 2) int64, launch 2 normalises in place, synthesises the padded
- *                rows and applies the masks                             (feat_norm.py:137-139)
+ *                one half of stats_ws, launch 2 normalises in place, synthesises the padded rows,
+ *                applies the masks and clears the other half for the next call (feat_norm.py:137-139).
+ *                stats_ws is a (2, B, n_mels, 2) int64 scratch, ALL ZERO before its first use and kept
+ *                by the caller between calls; ws_half (0/1) names the half this call accumulates into
+ *                and must alternate from call to call on the same scratch; after a failed call zero
+ *                the scratch again.
  * mean_out/std_out (B, n_mels), optional: the per-utterance statistics of norm_mode 2. */
 int sfe_chain_forward(const sfe_plan* plan, const float* wav, int64_t wav_pitch,
                       const int64_t* wav_len, int32_t B, int64_t T_max, float* mel,
-                      int64_t* feat_len, int64_t* stats_ws, int32_t norm_mode, const float* mean,
+                      int64_t* feat_len, int64_t* stats_ws, int32_t ws_half, int32_t norm_mode,
+                      const float* mean,
                       const float* std, float clamp, int32_t use_mean, int32_t use_std,
                       float* mean_out, float* std_out, const sfe_masks* masks, void* stream);
 

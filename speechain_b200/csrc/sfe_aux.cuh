@@ -160,6 +160,7 @@ struct NormParams {
   float fill;
   const float* fill_dev;
   int frames_per_cta;
+  long long* zero_sums;  // optional (B, D, 2) sums buffer to clear for the next step (double-buffered scratch)
 };
 
 __device__ __forceinline__ void cubic_w(float t, float (&w)[4]) {
@@ -192,6 +193,10 @@ __global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ 
       if (blockIdx.x == 0) {
         if (p.mean_out) p.mean_out[static_cast<long long>(b) * D + d] = m;
         if (p.std_out) p.std_out[static_cast<long long>(b) * D + d] = s;
+        if (p.zero_sums) {
+          p.zero_sums[(static_cast<long long>(b) * D + d) * 2] = 0;
+          p.zero_sums[(static_cast<long long>(b) * D + d) * 2 + 1] = 0;
+        }
       }
       if (!p.use_mean) m = 0.f;
       if (!p.use_std) s = 1.f;

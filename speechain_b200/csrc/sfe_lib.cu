@@ -405,10 +405,23 @@ static int fill_masks(const sfe_masks* m, int B, MaskDesc* out, float* fill, con
   return SFE_OK;
 }
 
+static int frontend_forward_impl(const sfe_plan* pl, const float* wav, int64_t wav_pitch, const int64_t* wav_len,
+                                 int32_t B, int64_t T_max, float* mel, float* lin, float* energy, int64_t* feat_len,
+                                 int64_t* stats, const float* norm_mean, const float* norm_std, const sfe_masks* masks,
+                                 int32_t skip_pad, void* stream, bool zero_stats);
+
 extern "C" int sfe_frontend_forward(const sfe_plan* pl, const float* wav, int64_t wav_pitch, const int64_t* wav_len,
                                     int32_t B, int64_t T_max, float* mel, float* lin, float* energy, int64_t* feat_len,
                                     int64_t* stats, const float* norm_mean, const float* norm_std,
                                     const sfe_masks* masks, int32_t skip_pad, void* stream) {
+  return frontend_forward_impl(pl, wav, wav_pitch, wav_len, B, T_max, mel, lin, energy, feat_len, stats, norm_mean,
+                               norm_std, masks, skip_pad, stream, true);
+}
+
+static int frontend_forward_impl(const sfe_plan* pl, const float* wav, int64_t wav_pitch, const int64_t* wav_len,
+                                 int32_t B, int64_t T_max, float* mel, float* lin, float* energy, int64_t* feat_len,
+                                 int64_t* stats, const float* norm_mean, const float* norm_std, const sfe_masks* masks,
+                                 int32_t skip_pad, void* stream, bool zero_stats) {
   if (!pl) return fail(SFE_ERR_BAD_ARG, "sfe_frontend_forward: NULL plan");
   if (!wav || !wav_len) return fail(SFE_ERR_BAD_ARG, "sfe_frontend_forward: wav / wav_len is NULL");
   if (B <= 0 || T_max <= 0 || wav_pitch < T_max) return fail(SFE_ERR_BAD_ARG, "sfe_frontend_forward: bad B / T_max / pitch");
@@ -446,7 +459,8 @@ extern "C" int sfe_frontend_forward(const sfe_plan* pl, const float* wav, int64_
   P.norm_std = norm_std;
   P.skip_pad = skip_pad;
   if (int rc = fill_masks(masks, B, &P.mk, &P.fill, &P.fill_dev)) return rc;
-  if (stats) SFE_CUDA(cudaMemsetAsync(stats, 0, static_cast<size_t>(B) * pl->cfg.n_mels * 2 * sizeof(int64_t), st));
+  if (stats && zero_stats)
+    SFE_CUDA(cudaMemsetAsync(stats, 0, static_cast<size_t>(B) * pl->cfg.n_mels * 2 * sizeof(int64_t), st));
   int grid = pl->n_sm * pl->ctas_per_sm;
   if (grid > P.num_tiles) grid = P.num_tiles;
   pl->fft->fn[pl->cfg.has_preemphasis ? 1 : 0]<<<grid, NTHREADS, pl->smem_bytes, st>>>(P);
@@ -526,11 +540,26 @@ extern "C" int sfe_running_update(const float* packed, int32_t D, float weight, 
   return SFE_OK;
 }
 
+static int normalize_impl(const float* src, float* dst, const int64_t* feat_len, int32_t B, int64_t F, int32_t D,
+                          const void* stats, int32_t stats_fixed, float clamp, int32_t use_mean, int32_t use_std,
+                          const float* mean, const float* std, int32_t per_utt, float* mean_out, float* std_out,
+                          int32_t src_has_pad, float pad_value, const sfe_warp* warp, const sfe_masks* masks,
+                          void* stream, int64_t* zero_sums);
+
 extern "C" int sfe_normalize(const float* src, float* dst, const int64_t* feat_len, int32_t B, int64_t F, int32_t D,
                              const void* stats, int32_t stats_fixed, float clamp, int32_t use_mean, int32_t use_std,
                              const float* mean,
                              const float* std, int32_t per_utt, float* mean_out, float* std_out, int32_t src_has_pad,
                              float pad_value, const sfe_warp* warp, const sfe_masks* masks, void* stream) {
+  return normalize_impl(src, dst, feat_len, B, F, D, stats, stats_fixed, clamp, use_mean, use_std, mean, std, per_utt,
+                        mean_out, std_out, src_has_pad, pad_value, warp, masks, stream, nullptr);
+}
+
+static int normalize_impl(const float* src, float* dst, const int64_t* feat_len, int32_t B, int64_t F, int32_t D,
+                          const void* stats, int32_t stats_fixed, float clamp, int32_t use_mean, int32_t use_std,
+                          const float* mean, const float* std, int32_t per_utt, float* mean_out, float* std_out,
+                          int32_t src_has_pad, float pad_value, const sfe_warp* warp, const sfe_masks* masks,
+                          void* stream, int64_t* zero_sums) {
   if (!src || !dst || !feat_len) return fail(SFE_ERR_BAD_ARG, "sfe_normalize: NULL argument");
   if (B <= 0 || F <= 0 || D <= 0 || D > 4096) return fail(SFE_ERR_BAD_ARG, "sfe_normalize: bad shape");
   const bool warp_on = warp && warp->enabled;
@@ -560,6 +589,7 @@ extern "C" int sfe_normalize(const float* src, float* dst, const int64_t* feat_l
   P.std_out = std_out;
   P.src_has_pad = src_has_pad;
   P.pad_value = pad_value;
+  P.zero_sums = reinterpret_cast<long long*>(zero_sums);
   if (warp_on) {
     P.warp_on = 1;
     P.warp_center = warp->center;
@@ -580,7 +610,7 @@ extern "C" int sfe_normalize(const float* src, float* dst, const int64_t* feat_l
 
 extern "C" int sfe_chain_forward(const sfe_plan* pl, const float* wav, int64_t wav_pitch, const int64_t* wav_len,
                                  int32_t B, int64_t T_max, float* mel, int64_t* feat_len, int64_t* stats_ws,
-                                 int32_t norm_mode, const float* mean, const float* std, float clamp,
+                                 int32_t ws_half, int32_t norm_mode, const float* mean, const float* std, float clamp,
                                  int32_t use_mean, int32_t use_std, float* mean_out, float* std_out,
                                  const sfe_masks* masks, void* stream) {
   if (!pl) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: NULL plan");
@@ -594,12 +624,20 @@ extern "C" int sfe_chain_forward(const sfe_plan* pl, const float* wav, int64_t w
   if (norm_mode != 2) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: norm_mode must be 0, 1 or 2");
   if (!stats_ws) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: norm_mode 2 needs stats_ws");
   if (!pl->cfg.mel_logging) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: norm_mode 2 needs a log-mel plan");
-  if (int rc = sfe_frontend_forward(pl, wav, wav_pitch, wav_len, B, T_max, mel, nullptr, nullptr, feat_len, stats_ws,
-                                    nullptr, nullptr, nullptr, 1, stream))
+  // stats_ws holds TWO (B, n_mels, 2) buffers, both zero before the first call: this call accumulates into half
+  // `ws_half` and its normalise launch clears the other half for the next call (which must pass 1 - ws_half),
+  // so no memset launch is needed
+  const size_t half = static_cast<size_t>(B) * pl->cfg.n_mels * 2;
+  int64_t* cur = stats_ws + (ws_half ? half : 0);
+  int64_t* other = stats_ws + (ws_half ? 0 : half);
+  if (int rc = frontend_forward_impl(pl, wav, wav_pitch, wav_len, B, T_max, mel, nullptr, nullptr, feat_len, cur,
+                                     nullptr, nullptr, nullptr, 1, stream, false))
     return rc;
-  return sfe_normalize(mel, mel, feat_len, B, sfe_plan_num_frames(pl, T_max), pl->cfg.n_mels, stats_ws, 1, clamp,
-                       use_mean, use_std, nullptr, nullptr, 0, mean_out, std_out, 0, pl->proto.pad_mel, nullptr, masks,
-                       stream);
+  if (int rc = normalize_impl(mel, mel, feat_len, B, sfe_plan_num_frames(pl, T_max), pl->cfg.n_mels, cur, 1, clamp,
+                              use_mean, use_std, nullptr, nullptr, 0, mean_out, std_out, 0, pl->proto.pad_mel, nullptr,
+                              masks, stream, other))
+    return rc;
+  return SFE_OK;
 }
 
 extern "C" int sfe_upload_waveforms(const float* wav_host, int64_t host_pitch, const int64_t* len_host, int32_t B,

@@ -225,20 +225,25 @@ class FrontendPlan:
         F = self.num_frames(T)
         mel = torch.empty((B, F, self.n_mels), dtype=torch.float32, device=dev)
         feat_len = torch.empty((B,), dtype=torch.int64, device=dev)
-        ws = None
+        ws, half = None, 0
         if norm_mode == 2:
-            ws = self._ws.get(B)
-            if ws is None:
-                ws = self._ws[B] = torch.empty((B, self.n_mels, 2), dtype=torch.int64, device=dev)
+            # double-buffered fixed-point sums (include/sfe.h): zeroed once, then the kernels keep them clean
+            ent = self._ws.get(B)
+            if ent is None or ent[1] < 0:
+                ent = self._ws[B] = [torch.zeros((2, B, self.n_mels, 2), dtype=torch.int64, device=dev), 0]
+            ws, half = ent
+            ent[1] = -1  # marks the scratch dirty until the call below has been enqueued completely
         ms = masks.struct() if masks is not None else None
         with _on_device(dev):
             rc = self._lib.sfe_chain_forward(
                 self._h, wav.data_ptr(), wav.stride(0), wav_len.data_ptr(), B, T, mel.data_ptr(), feat_len.data_ptr(),
-                ws.data_ptr() if ws is not None else None, norm_mode,
+                ws.data_ptr() if ws is not None else None, half, norm_mode,
                 mean.data_ptr() if mean is not None else None, std.data_ptr() if std is not None else None,
                 clamp, int(use_mean), int(use_std), None, None, C.byref(ms) if ms is not None else None, _stream())
         if rc:
             _lib.check(rc)
+        if ws is not None:
+            self._ws[B][1] = 1 - half
         return mel, feat_len
 
     def linear2mel(self, lin: torch.Tensor) -> torch.Tensor:
