@@ -334,15 +334,17 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    h0 = time.perf_counter()
     for i in range(steps):
         step(i)
+    host_ms = (time.perf_counter() - h0) * 1e3   # time the host needed to enqueue the steps (no sync inside)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, host_ms, -ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total, host_ms_max, ms_min = float(t[0].item()), float(t[1].item()), -float(t[2].item())
 
     # ---- (2) the dominant kernel alone (fused frontend), same arguments as inside the step ----
     two_pass = w["normalize"] is not None
@@ -434,6 +436,8 @@ def main():
                    "padded_len": T, "frames": F, "sharding": "utterance stride [W-1-r::W], no data-path collective",
                    "cache": f"ring of {ring} distinct batches ({ring * (in_bytes_padded + out_bytes) / 1e6:.0f} MB) > 3x L2"},
         "clocks": clocks,
+        "host": {"enqueue_ms_per_step_max_over_ranks": host_ms_max / steps, "device_ms_per_step_min_over_ranks": ms_min / steps,
+                 "cpus": os.cpu_count(), "affinity": len(os.sched_getaffinity(0))},
         "e2e": {"value": total_audio * e2e_steps / (e2e_ms * 1e-3), "unit": "audio-s/s",
                 "h2d_bytes_per_step": 4 * S + 8 * B, "d2h_bytes_per_step": 8 * B, "steps": e2e_steps,
                 "note": "pinned host (B,T,1) waveforms -> ops.upload_waveforms (valid samples only) -> public API "
