@@ -320,12 +320,21 @@ enum { TILE_PAD = 0, TILE_BULK = 1, TILE_EDGE = 2 };
 // log_b(max(x, clamp)) through the SFU: MUFU.LG2 is accurate to 2^-22 absolute on [0.5, 2] and 2 ulp
 // elsewhere — three orders of magnitude inside the 1e-4 / 1e-3 tolerance of the features — and costs 3
 // instructions where logf + an IEEE division cost ~45.
-__device__ __forceinline__ float fast_log(float x, float clampv, float lmul) { return __log2f(fmaxf(x, clampv)) * lmul; }
+// The clamp floor is a normal number (sfe_plan_create rejects smaller ones), so the flush-to-zero form is
+// exact here and drops the denormal pre-scaling that __log2f carries (3 instructions instead of 7).
+__device__ __forceinline__ float fast_log(float x, float clampv, float lmul) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(x, clampv)));
+  return r * lmul;
+}
 
 template <class PL, bool PRE>
 __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int M = PL::M, G = PL::G, Q = PL::PADQ;
+  // magnitude spectra (mag_spec, no shipped recipe): sqrt in one sweep after the unpack where the spectrum
+  // aliases the FFT scratch, inside the unpack loop elsewhere — whichever measured faster for the power path
+  constexpr bool MAG_SWEEP = PL::ALIAS_P2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane / G, l = lane % G;
 
@@ -355,11 +364,6 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
   {
     int* acc = reinterpret_cast<int*>(smem + p.sm_acc);
     for (int i = tid; i < NSTAGE * 4 * p.D; i += NTHREADS) acc[i] = 0;
-    if (!PL::ALIAS_P2) {
-      // zero-weight padding taps of the mel filter read past bin K-1 (aliased layouts redo this per frame)
-      float* p2 = reinterpret_cast<float*>(wbase + p.sm_p2_off);
-      for (int i = lane; i < (p.mel_tail + 2) * FPW; i += 32) p2[p.K * FPW + i] = 0.f;
-    }
   }
   __syncthreads();               // barrier inits are visible before anyone waits on them
   mbar_wait(bar0 + 16, 0u);      // tables have landed
@@ -603,7 +607,6 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
         }
         if (PL::ALIAS_P2) __syncwarp();  // every lane has its Z values: the buffer may now hold P2
       }
-      const float live = (t < flen) ? 1.f : 0.f;
       float es = 0.f;
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
@@ -615,20 +618,31 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
           const cpx O = f2add(make_float2(a.y, -a.x), make_float2(bb.y, bb.x));
           const cpx Tt = cmul(O, w);
           const cpx X = f2add(E, Tt), Y = f2sub(E, Tt);
-          const float2 pp2 = f2mul(make_float2(fmaf(X.x, X.x, X.y * X.y), fmaf(Y.x, Y.x, Y.y * Y.y)), make_float2(live, live));
-          float pk = pp2.x, pm = pp2.y;
+          float pk = fmaf(X.x, X.x, X.y * X.y), pm = fmaf(Y.x, Y.x, Y.y * Y.y);
           es += pk;
           if (2 * k != M) es += pm;
-          if (p.mag) { pk = sqrtf(pk); pm = sqrtf(pm); }
+          if (!MAG_SWEEP && p.mag) { pk = sqrtf(pk); pm = sqrtf(pm); }
           P2[k * FPW + slot] = pk;
           P2[(M - k) * FPW + slot] = pm;
         }
       }
-      esum[sub] = es;
-      if (PL::ALIAS_P2) {
-        // the zero-weight padding taps of the mel filter read past bin K-1: keep that tail clean
-        for (int i = lane; i < (p.mel_tail + 2) * FPW; i += 32) P2[K * FPW + i] = 0.f;
+      if (t >= flen) {
+        // a frame beyond the utterance (last tile only): its spectrum is defined as zero
+        es = 0.f;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          const int k = l + i * G;
+          if (i < NI - 1 || k <= M / 2) {
+            P2[k * FPW + slot] = 0.f;
+            P2[(M - k) * FPW + slot] = 0.f;
+          }
+        }
       }
+      esum[sub] = es;
+      __syncwarp();
+    }
+    if (MAG_SWEEP && p.mag) {  // magnitude spectrum: one extra sweep, off the power-spectrum path every recipe takes
+      for (int i = lane; i < K * FPW; i += 32) P2[i] = sqrtf(P2[i]);
       __syncwarp();
     }
 

@@ -1,6 +1,7 @@
 // libsfe.so — C ABI (include/sfe.h) over the sm_100a kernels.  No torch, no exceptions across
 // the boundary, no per-call allocation: a plan owns its constant tables and two scheduler words.
 #include <cuda_runtime.h>
+#include <float.h>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -108,6 +109,10 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
   if (cfg->n_mels < 0 || cfg->n_mels > 32 * MAX_MEL_ROUNDS)
     return fail(SFE_ERR_BAD_CONFIG, "n_mels must be in [0, 256]");
   if (cfg->n_mels > 0 && !cfg->mel_weight_host) return fail(SFE_ERR_BAD_CONFIG, "mel_weight_host is NULL");
+  // the kernels take logarithms with the flush-to-zero SFU form, exact only above the smallest normal float
+  if ((cfg->n_mels > 0 && cfg->mel_logging && !(cfg->mel_clamp >= FLT_MIN)) ||
+      (cfg->lin_logging && !(cfg->lin_clamp >= FLT_MIN)))
+    return fail(SFE_ERR_BAD_CONFIG, "clamp must be >= 1.17549435e-38 when logging is on");
   const FftEntry* fe = nullptr;
   for (const auto& e : registry())
     if (e.n_fft == cfg->n_fft && (e.win == 0 || e.win == cfg->win_length) && (!fe || e.win != 0)) fe = &e;
@@ -187,7 +192,7 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
     items.push_back(Item{d, pair ? (mnt[d] + 1) / 2 : mnt[d], pair});
   }
   std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.size > b.size; });
-  struct Lane { int start, ntaps, d, out; };  // out: -1 none, else d | combine flag
+  struct Lane { int start, ntaps, d, out; int lead = 0; };  // out: -1 none, else d | combine flag
   std::vector<std::vector<Lane>> phases;
   for (const Item& it : items) {
     if (phases.empty()) phases.emplace_back();
@@ -215,6 +220,17 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
     memcpy(&f, &v, 4);
     tab.push_back(f);
   };
+  // every lane of a phase walks the phase's tap count: a unit that would run past bin K-1 starts earlier
+  // and leads with zero weights instead, so no lane ever reads beyond the power spectrum
+  for (auto& ph : phases) {
+    int nt = 0;
+    for (auto& ln : ph) nt = ln.ntaps > nt ? ln.ntaps : nt;
+    nt = round_up(nt, 2);
+    for (auto& ln : ph) {
+      ln.lead = (ln.start + nt > K) ? ln.start + nt - K : 0;
+      ln.start -= ln.lead;
+    }
+  }
   P.o_mstart = static_cast<int>(tab.size());
   for (auto& ph : phases)
     for (auto& ln : ph) push_int(ln.start);
@@ -229,12 +245,12 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
     for (auto& ln : phases[i]) nt = ln.ntaps > nt ? ln.ntaps : nt;
     nt = round_up(nt, 2);
     P.mel_taps[i] = nt;
-    if (nt > P.mel_tail) P.mel_tail = nt;
     for (int q2 = 0; q2 < nt / 2; ++q2)
       for (auto& ln : phases[i])
         for (int e = 0; e < 2; ++e) {
           const int q = q2 * 2 + e;
-          tab.push_back((ln.d >= 0 && q < ln.ntaps) ? cfg->mel_weight_host[static_cast<size_t>(ln.d) * K + ln.start + q] : 0.f);
+          tab.push_back((ln.d >= 0 && q >= ln.lead && q < ln.lead + ln.ntaps)
+                            ? cfg->mel_weight_host[static_cast<size_t>(ln.d) * K + ln.start + q] : 0.f);
         }
   }
   align4();
@@ -251,6 +267,12 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
     cudaDeviceProp pr;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&pr, dev) == cudaSuccess)
       smem_limit = static_cast<int>(pr.sharedMemPerBlockOptin);
+    // the opt-in limit covers static + dynamic shared memory: leave room for the kernel's static part
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(fe->fn[cfg->has_preemphasis ? 1 : 0])) == cudaSuccess)
+      smem_limit -= static_cast<int>(fa.sharedSizeBytes);
+    else
+      smem_limit -= 4096;
   }
   for (P.nstage = NSTAGE; P.nstage >= 1; --P.nstage) {
     int o = round_up(P.tab_floats * 4, 16);
@@ -306,7 +328,7 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
   cudaError_t e = cudaGetDevice(&pl->device);
   cudaDeviceProp prop;
   if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, pl->device);
-  if (e == cudaSuccess && pl->smem_bytes > static_cast<int>(prop.sharedMemPerBlockOptin)) {
+  if (e == cudaSuccess && pl->smem_bytes > smem_limit) {
     delete pl;
     return fail(SFE_ERR_BAD_CONFIG, "configuration needs more shared memory per CTA than the device offers");
   }

@@ -115,6 +115,10 @@ def test_unsupported_inputs_raise():
     with pytest.raises(ValueError):
         Speech2MelSpec(n_mels=80, hop_length=100, win_length=300, n_fft=300).to(DEV)(
             torch.zeros(1, 4000, 1, device=DEV), torch.tensor([4000], device=DEV))
+    # a log floor below the smallest normal float would not be exact on the SFU path: refused, not approximated
+    with pytest.raises(ValueError):
+        Speech2MelSpec(n_mels=80, hop_length=160, win_length=400, n_fft=512, clamp=1e-40).to(DEV)(
+            torch.zeros(1, 4000, 1, device=DEV), torch.tensor([4000], device=DEV))
     m = Speech2MelSpec(n_mels=80, hop_length=160, win_length=400, n_fft=512)
     with pytest.raises(RuntimeError):
         m(torch.zeros(2, 4000, 2, device=DEV), torch.tensor([4000, 4000], device=DEV))
