@@ -397,9 +397,9 @@ struct L2MParams {
   int mel_log;
   float mel_clamp, mel_div, mel_lmul;
   const float* tables;
-  int tab_floats, o_mstart, o_mout, o_mw, mel_rounds, mel_tail;
+  int tab_floats, o_mtab, o_mw, mel_rounds, mel_tail;
   unsigned int mel_split_mask;
-  int mel_taps[MAX_MEL_ROUNDS];
+  int2 mel_ph[MAX_MEL_ROUNDS];
   int sm_warp, sm_warp_bytes;
 };
 
@@ -412,8 +412,7 @@ __global__ void __launch_bounds__(NTHREADS) linear2mel_kernel(const __grid_const
   const int p2_floats = (p.K + p.mel_tail + 2) * FPW;
   for (int i = lane; i < p2_floats; i += 32) P2[i] = 0.f;
   __syncthreads();
-  const int* mstart = reinterpret_cast<const int*>(tab + p.o_mstart);
-  const int* mout = reinterpret_cast<const int*>(tab + p.o_mout);
+  const int2* mtab = reinterpret_cast<const int2*>(tab + p.o_mtab) + lane;
   const float2* mw2 = reinterpret_cast<const float2*>(tab + p.o_mw);
   const float2* P2v = reinterpret_cast<const float2*>(P2);
   const long long pairs = (p.n_rows + FPW - 1) / FPW;
@@ -426,13 +425,12 @@ __global__ void __launch_bounds__(NTHREADS) linear2mel_kernel(const __grid_const
       for (int k = lane; k < p.K; k += 32) P2[k * FPW + s] = (r < p.n_rows) ? __ldg(p.lin + r * p.K + k) : 0.f;
     }
     __syncwarp();
-    int wofs = 0;
     for (int ph = 0; ph < p.mel_rounds; ++ph) {
-      const int st = mstart[ph * 32 + lane];
-      const int oinfo = mout[ph * 32 + lane];
-      const float2* pp = P2v + st;
-      const int n2 = p.mel_taps[ph] >> 1;
-      const float2* wp = mw2 + wofs + lane;
+      const int2 so = mtab[ph * 32];
+      const int oinfo = so.y;
+      const float2* pp = P2v + so.x;
+      const int n2 = p.mel_ph[ph].x;
+      const float2* wp = mw2 + p.mel_ph[ph].y + lane;
       float a0 = 0.f, a1 = 0.f;
       for (int q = 0; q < n2; ++q) {
         const float2 wq = wp[q * 32];
@@ -440,7 +438,6 @@ __global__ void __launch_bounds__(NTHREADS) linear2mel_kernel(const __grid_const
         a0 = fmaf(wq.x, p0.x, a0); a1 = fmaf(wq.x, p0.y, a1);
         a0 = fmaf(wq.y, p1.x, a0); a1 = fmaf(wq.y, p1.y, a1);
       }
-      wofs += n2 * 32;
       if ((p.mel_split_mask >> ph) & 1u) {
         const float o0 = __shfl_xor_sync(0xffffffffu, a0, 1), o1 = __shfl_xor_sync(0xffffffffu, a1, 1);
         if (oinfo & 0x10000) { a0 += o0; a1 += o1; }

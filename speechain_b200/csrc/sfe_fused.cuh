@@ -81,9 +81,9 @@ struct FwdParams {
   // tables (device blob, float units) and shared-memory carve-up (byte offsets)
   const float* tables;
   int tab_floats;
-  int o_win, o_tw2, o_tw3, o_wpost, o_mstart, o_mout, o_mw;  // float offsets into the blob
+  int o_win, o_tw2, o_tw3, o_wpost, o_mtab, o_mw;  // float offsets into the blob
   int mel_rounds;                                    // phases of 32 filter units
-  int mel_taps[MAX_MEL_ROUNDS];                      // taps per phase (multiples of 2)
+  int2 mel_ph[MAX_MEL_ROUNDS];                       // per phase: {pairs of taps, float2 offset of its weights}
   unsigned int mel_split_mask;                       // phases that hold bins split over two lanes
   int mel_tail;                                      // max taps of any phase (P2 tail padding)
   int sm_stage, sm_stage_floats, sm_warp, sm_warp_bytes, sm_p2_off, sm_acc, sm_bar;
@@ -397,8 +397,7 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
   const cpx* tw2 = reinterpret_cast<const cpx*>(tab + p.o_tw2);
   const cpx* tw3 = reinterpret_cast<const cpx*>(tab + p.o_tw3);
   const cpx* wpost = reinterpret_cast<const cpx*>(tab + p.o_wpost);
-  const int* mstart = reinterpret_cast<const int*>(tab + p.o_mstart);
-  const int* mout = reinterpret_cast<const int*>(tab + p.o_mout);
+  const int2* mtab = reinterpret_cast<const int2*>(tab + p.o_mtab) + lane;  // {first bin, output info} per (phase, lane)
   const float2* mw2 = reinterpret_cast<const float2*>(tab + p.o_mw);
   const int hop = p.hop, win = p.win, D = p.D, K = p.K;
   const bool base_aligned = ((reinterpret_cast<uintptr_t>(p.wav) & 15) == 0);
@@ -706,14 +705,12 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
         constexpr bool kLog = decltype(kLogT)::value, kStats = decltype(kStatsT)::value,
                        kFancy = decltype(kFancyT)::value;
         const float clampv = p.mel_clamp, lmul = p.mel_lmul;
-        int wofs = 0;  // in float2 units
-        const int nph = p.mel_rounds;
-        for (int ph = 0; ph < nph; ++ph) {
-          const int st = mstart[ph * 32 + lane];
-          const int oinfo = mout[ph * 32 + lane];
-          const float2* pp = P2v + st;
-          const int n2 = p.mel_taps[ph] >> 1;
-          const float2* wp = mw2 + wofs + lane;
+        const float2* wl = mw2 + lane;
+        float* mel_row1 = mel_row + D;
+        auto phase = [&](const int ph, const int n2, const int wofs) {
+          const int2 so = mtab[ph * 32];   // .x first bin of this lane's unit, .y output info
+          const float2* pp = P2v + so.x;
+          const float2* wp = wl + wofs;
           float2 accA = make_float2(0.f, 0.f), accB = make_float2(0.f, 0.f);  // (frame 0, frame 1) pairs
 #pragma unroll 2
           for (int q = 0; q < n2; ++q) {
@@ -723,13 +720,11 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
             accB = f2fma(make_float2(wq.y, wq.y), p1, accB);
           }
           float2 acc = f2add(accA, accB);
-          wofs += n2 * 32;
-          if ((p.mel_split_mask >> ph) & 1u) {  // bins wider than a unit: add the partner lane's half
-            const float o0 = __shfl_xor_sync(0xffffffffu, acc.x, 1), o1 = __shfl_xor_sync(0xffffffffu, acc.y, 1);
-            if (oinfo & 0x10000) acc = f2add(acc, make_float2(o0, o1));
-          }
-          if (oinfo >= 0) {  // this lane publishes bin d
-            const int d = oinfo & 0xffff;
+          // bins wider than a unit: add the partner lane's half (cheaper done always than tested per phase)
+          const float o0 = __shfl_xor_sync(0xffffffffu, acc.x, 1), o1 = __shfl_xor_sync(0xffffffffu, acc.y, 1);
+          if (so.y & 0x10000) acc = f2add(acc, make_float2(o0, o1));
+          if (so.y >= 0) {  // this lane publishes bin d
+            const int d = so.y & 0xffff;
             float x0 = acc.x, x1 = acc.y;
             if (kLog) {
               x0 = fast_log(x0, clampv, lmul);
@@ -757,10 +752,18 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
               if (fm || tm0) x0 = fillv;
               if (fm || tm1) x1 = fillv;
             }
-            float* o = mel_row + d;
-            if (w0) o[0] = x0;
-            if (w1) o[D] = x1;
+            if (w0) mel_row[d] = x0;
+            if (w1) mel_row1[d] = x1;
           }
+        };
+        const int nph = p.mel_rounds;
+        if (nph <= 4) {
+          // the usual filterbanks need at most four phases: straight-line code, every table offset an immediate
+#pragma unroll
+          for (int ph = 0; ph < 4; ++ph)
+            if (ph < nph) phase(ph, p.mel_ph[ph].x, p.mel_ph[ph].y);
+        } else {
+          for (int ph = 0; ph < nph; ++ph) phase(ph, p.mel_ph[ph].x, p.mel_ph[ph].y);
         }
       };
       using T1 = std::true_type;

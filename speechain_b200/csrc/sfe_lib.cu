@@ -184,28 +184,52 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
     }
     if (mnt[d] > maxn) maxn = mnt[d];
   }
-  const int ucap = maxn > 8 ? (maxn + 1) / 2 : maxn;  // taps a single lane takes at most
-  struct Item { int d, size; bool pair; };
-  std::vector<Item> items;
-  for (int d = 0; d < D; ++d) {
-    const bool pair = mnt[d] > ucap;
-    items.push_back(Item{d, pair ? (mnt[d] + 1) / 2 : mnt[d], pair});
-  }
-  std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.size > b.size; });
+  // A bin wider than `ucap` taps is split over two neighbouring lanes.  Every phase costs a fixed prologue
+  // and epilogue (~75 instructions) on top of ~9 per pair of taps of its widest unit, so the split threshold
+  // is the one that minimises that estimate (80 mel / 257 bins: 3 phases of 12+8+4 taps instead of 4).
   struct Lane { int start, ntaps, d, out; int lead = 0; };  // out: -1 none, else d | combine flag
-  std::vector<std::vector<Lane>> phases;
-  for (const Item& it : items) {
-    if (phases.empty()) phases.emplace_back();
-    if (it.pair && (phases.back().size() & 1)) phases.back().push_back(Lane{0, 0, -1, -1});
-    if (phases.back().size() + (it.pair ? 2 : 1) > 32) phases.emplace_back();
-    std::vector<Lane>& ph = phases.back();
-    if (it.pair) {
-      const int n1 = (mnt[it.d] + 1) / 2;
-      ph.push_back(Lane{mst[it.d], n1, it.d, it.d | 0x10000});
-      ph.push_back(Lane{mst[it.d] + n1, mnt[it.d] - n1, it.d, -1});
-      P.mel_split_mask |= 1u << (phases.size() - 1);
-    } else {
-      ph.push_back(Lane{mst[it.d], mnt[it.d], it.d, it.d});
+  auto pack = [&](int ucap, unsigned int* split_mask) {
+    struct Item { int d, size; bool pair; };
+    std::vector<Item> items;
+    for (int d = 0; d < D; ++d) {
+      const bool pair = mnt[d] > ucap;
+      items.push_back(Item{d, pair ? (mnt[d] + 1) / 2 : mnt[d], pair});
+    }
+    std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.size > b.size; });
+    std::vector<std::vector<Lane>> phs;
+    *split_mask = 0;
+    for (const Item& it : items) {
+      if (phs.empty()) phs.emplace_back();
+      if (it.pair && (phs.back().size() & 1)) phs.back().push_back(Lane{0, 0, -1, -1});
+      if (phs.back().size() + (it.pair ? 2 : 1) > 32) phs.emplace_back();
+      std::vector<Lane>& ph = phs.back();
+      if (it.pair) {
+        const int n1 = (mnt[it.d] + 1) / 2;
+        ph.push_back(Lane{mst[it.d], n1, it.d, it.d | 0x10000});
+        ph.push_back(Lane{mst[it.d] + n1, mnt[it.d] - n1, it.d, -1});
+        if (phs.size() <= 32) *split_mask |= 1u << (phs.size() - 1);
+      } else {
+        ph.push_back(Lane{mst[it.d], mnt[it.d], it.d, it.d});
+      }
+    }
+    return phs;
+  };
+  auto cost = [](const std::vector<std::vector<Lane>>& phs) {
+    int c = 0;
+    for (auto& ph : phs) {
+      int nt = 0;
+      for (auto& ln : ph) nt = ln.ntaps > nt ? ln.ntaps : nt;
+      c += 75 + 9 * ((nt + 1) / 2);
+    }
+    return c;
+  };
+  std::vector<std::vector<Lane>> phases = pack(maxn, &P.mel_split_mask);
+  for (int ucap = maxn - 1; ucap >= (maxn + 1) / 2 && ucap >= 1; --ucap) {
+    unsigned int sm = 0;
+    std::vector<std::vector<Lane>> cand = pack(ucap, &sm);
+    if (cost(cand) < cost(phases)) {
+      phases.swap(cand);
+      P.mel_split_mask = sm;
     }
   }
   if (static_cast<int>(phases.size()) > MAX_MEL_ROUNDS) {
@@ -231,20 +255,19 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
       ln.start -= ln.lead;
     }
   }
-  P.o_mstart = static_cast<int>(tab.size());
+  P.o_mtab = static_cast<int>(tab.size());  // int2 {first bin, output info} per (phase, lane)
   for (auto& ph : phases)
-    for (auto& ln : ph) push_int(ln.start);
-  align4();
-  P.o_mout = static_cast<int>(tab.size());
-  for (auto& ph : phases)
-    for (auto& ln : ph) push_int(ln.out);
+    for (auto& ln : ph) {
+      push_int(ln.start);
+      push_int(ln.out);
+    }
   align4();
   P.o_mw = static_cast<int>(tab.size());
   for (size_t i = 0; i < phases.size(); ++i) {
     int nt = 0;
     for (auto& ln : phases[i]) nt = ln.ntaps > nt ? ln.ntaps : nt;
     nt = round_up(nt, 2);
-    P.mel_taps[i] = nt;
+    P.mel_ph[i] = make_int2(nt / 2, (static_cast<int>(tab.size()) - P.o_mw) / 2);
     for (int q2 = 0; q2 < nt / 2; ++q2)
       for (auto& ln : phases[i])
         for (int e = 0; e < 2; ++e) {
@@ -507,13 +530,12 @@ extern "C" int sfe_linear2mel_forward(const sfe_plan* pl, const float* lin, int6
   P.mel_lmul = pl->proto.mel_lmul;
   P.tables = pl->d_tables;
   P.tab_floats = pl->proto.tab_floats;
-  P.o_mstart = pl->proto.o_mstart;
-  P.o_mout = pl->proto.o_mout;
+  P.o_mtab = pl->proto.o_mtab;
   P.o_mw = pl->proto.o_mw;
   P.mel_split_mask = pl->proto.mel_split_mask;
   P.mel_rounds = pl->proto.mel_rounds;
   P.mel_tail = pl->proto.mel_tail;
-  for (int i = 0; i < MAX_MEL_ROUNDS; ++i) P.mel_taps[i] = pl->proto.mel_taps[i];
+  for (int i = 0; i < MAX_MEL_ROUNDS; ++i) P.mel_ph[i] = pl->proto.mel_ph[i];
   P.sm_warp = pl->l2m_sm_warp;
   P.sm_warp_bytes = pl->l2m_warp_bytes;
   long long pairs = (n_rows + FPW - 1) / FPW;
