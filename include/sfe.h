@@ -207,6 +207,31 @@ int sfe_delta(const float* feat, int32_t B, int64_t F, int32_t D, int32_t order,
  * feat_norm=False). */
 int sfe_mean_all(const float* x, int64_t n, float* out, void* stream);
 
+/* LinearSpec2MelSpec.recover (linear2mel.py:191-224): (log-)mel (B, F, D) -> linear spectrogram (B, F, K).
+ * Undoes the logarithm (pow(base, x); log_mode 0 none, 1 natural, 2 base `log_base`), applies the
+ * minimum-norm least-squares solution of  W x = mel  (what torch.linalg.lstsq(driver="gels") returns for the
+ * full-rank n_mels x K filterbank W) as the product with `pinv_t` = pinv(W)^T laid out (D, K), zeroes rows
+ * f >= feat_len[b] of every utterance shorter than `max_len` (the reference's rule, :215-218) and clamps to
+ * `clamp` (1e-10, :221).  The caller computes pinv(W) once per filterbank on the host. */
+int sfe_mel2linear(const float* mel, const int64_t* feat_len, int32_t B, int64_t F, int32_t D, int32_t K,
+                   const float* pinv_t, int32_t log_mode, float log_base, int64_t max_len, float clamp,
+                   float* lin, void* stream);
+
+/* Speech2LinearSpec.recover (speech2linear.py:252-351): linear spectrogram -> waveform by Griffin-Lim
+ * (torchaudio.transforms.GriffinLim as configured at :281-292: n_iter 32, momentum 0.99, random initial
+ * phase), inverse pre-emphasis over a sliding window of `inv_preemph_taps` samples (:297-344, skipped when the
+ * plan has no pre-emphasis or taps == 0) and silence beyond wav_len[b] = (feat_len[b] - 1) * hop (:346-348).
+ *   spec        (B, F, K) power (or magnitude when the plan has mag_spec) spectrogram, F = padded batch length
+ *   init_angles (B, F, K, 2) initial complex phase estimate — the caller draws it (torch.rand of the
+ *               reference's (B, K, F) shape, transposed) so that a seeded run reproduces the reference; NULL: ones
+ *   work        sfe_griffinlim_workspace(plan, B, F) bytes of device scratch
+ *   wav         (B, hop * (F - 1)) output;  wav_len (B,) int64 output or NULL
+ * Needs center=True and hop * (F - 1) > n_fft / 2 (torch's reflect padding has the same requirement). */
+int64_t sfe_griffinlim_workspace(const sfe_plan* plan, int32_t B, int64_t F);
+int sfe_griffinlim(sfe_plan* plan, const float* spec, const int64_t* feat_len, int32_t B, int64_t F,
+                   int32_t n_iter, float momentum, const float* init_angles, int32_t inv_preemph_taps,
+                   void* work, int64_t work_bytes, float* wav, int64_t* wav_len, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -257,6 +257,86 @@ def linear2mel(spec: np.ndarray, weight: np.ndarray, clamp: float = 1e-10, loggi
     return mel
 
 
+def mel2linear(mel: np.ndarray, flen: Sequence[int], weight: np.ndarray, logging: bool = True,
+               log_base: Optional[float] = 10.0, clamp: float = 1e-10) -> np.ndarray:
+    """LinearSpec2MelSpec.recover (linear2mel.py:191-224): undo the log, minimum-norm least squares
+    ``W x = mel`` per frame (what lstsq(driver="gels") returns for the full-row-rank n_mels x K filterbank),
+    silence rows >= len of every utterance shorter than the longest, clamp at 1e-10.  fp64."""
+    x = mel.astype(np.float64)
+    if logging:
+        x = np.power(np.e if log_base is None else float(log_base), x)
+    W = weight.astype(np.float64)
+    pinv = W.T @ np.linalg.inv(W @ W.T)  # (K, D)
+    lin = x @ pinv.T
+    flen = np.asarray(flen)
+    for i, n in enumerate(flen):
+        if n != flen.max():
+            lin[i, n:] = 0.0
+    return np.maximum(lin, clamp)
+
+
+def griffinlim(spec: np.ndarray, n_fft: int, hop: int, win: int, window: np.ndarray, power: float,
+               angles0: Optional[np.ndarray], n_iter: int = 32, momentum: float = 0.99) -> np.ndarray:
+    """torchaudio.functional.griffinlim (torchaudio 2.x; the reference calls it through
+    transforms.GriffinLim at speech2linear.py:281-293) restated with numpy FFTs in fp64.
+
+    spec (B, F, K) power (power=2) or magnitude (power=1) spectrogram; angles0 (B, F, K) complex initial
+    estimate (torch.rand: NOT unit length) or None for ones.  Returns (B, hop*(F-1)).
+    torch.istft: irfft of every frame, times the (centrally zero-padded) window, overlap-add, divide by the
+    overlap-added squared window, trim n_fft/2 per side.  torch.stft: reflect-pad n_fft/2, frame, window, rfft."""
+    B, F, K = spec.shape
+    mag = spec.astype(np.float64) ** (1.0 / power)
+    mom = momentum / (1.0 + momentum)
+    wpad = np.zeros(n_fft)
+    lp = (n_fft - win) // 2
+    wpad[lp:lp + win] = window.astype(np.float64)
+    L = hop * (F - 1)
+
+    def istft(S):
+        S = S.copy()
+        S[..., 0] = S[..., 0].real  # C2R transforms ignore the imaginary parts of DC and Nyquist
+        S[..., -1] = S[..., -1].real
+        fr = np.fft.irfft(S, n=n_fft, axis=-1) * wpad
+        out = np.zeros((B, n_fft + L))
+        env = np.zeros(n_fft + L)
+        for t in range(F):
+            out[:, t * hop:t * hop + n_fft] += fr[:, t]
+            env[t * hop:t * hop + n_fft] += wpad ** 2
+        return out[:, n_fft // 2:n_fft // 2 + L] / env[n_fft // 2:n_fft // 2 + L]
+
+    def stft(x):
+        xp = np.pad(x, ((0, 0), (n_fft // 2, n_fft // 2)), mode="reflect")
+        idx = np.arange(n_fft)[None, :] + hop * np.arange(F)[:, None]
+        return np.fft.rfft(xp[:, idx] * wpad, axis=-1)
+
+    angles = np.ones((B, F, K), np.complex128) if angles0 is None else angles0.astype(np.complex128)
+    tprev = 0.0
+    for _ in range(n_iter):
+        rebuilt = stft(istft(mag * angles))
+        angles = rebuilt - mom * tprev
+        angles = angles / (np.abs(angles) + 1e-16)
+        tprev = rebuilt
+    return istft(mag * angles)
+
+
+def speech2linear_recover(spec: np.ndarray, flen: Sequence[int], n_fft: int, hop: int, win: int, window: np.ndarray,
+                          mag_spec: bool, preemphasis: Optional[float], angles0: Optional[np.ndarray],
+                          inv_preemph_winlen: int = 100):
+    """Speech2LinearSpec.recover (speech2linear.py:252-351): Griffin-Lim, inverse pre-emphasis over a sliding
+    window of `inv_preemph_winlen` samples (y[n] = sum_j a^j x[n-j]), silence beyond (len-1)*hop."""
+    wav = griffinlim(spec, n_fft, hop, win, window, 1.0 if mag_spec else 2.0, angles0)
+    wav_len = (np.asarray(flen) - 1) * hop
+    if preemphasis is not None:
+        taps = np.float32(preemphasis) ** np.arange(inv_preemph_winlen, dtype=np.float32)  # fp32 like torch.pow
+        y = np.zeros_like(wav)
+        for j, a in enumerate(taps.astype(np.float64)):
+            y[:, j:] += a * wav[:, :wav.shape[1] - j]
+        wav = y
+    for i, n in enumerate(wav_len):
+        wav[i, n:] = 0.0
+    return wav, wav_len
+
+
 def delta_feature(feat: np.ndarray, order: int, N: int = 2) -> np.ndarray:
     """Delta / delta-delta by a (2N+1)-tap FIR along time with zero padding, concatenated
     on the feature axis (delta_feat.py:34-78)."""

@@ -66,6 +66,9 @@ SYMBOLS = {
     "sfe_upload_waveforms": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _i64, _vp]),
     "sfe_delta": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _i32, _vp, _vp]),
     "sfe_mean_all": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "sfe_mel2linear": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _i32, _f32, _i64, _f32, _vp, _vp]),
+    "sfe_griffinlim_workspace": (_i64, [_vp, _i32, _i64]),
+    "sfe_griffinlim": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i32, _f32, _vp, _i32, _vp, _i64, _vp, _vp, _vp]),
 }
 
 _lock = threading.Lock()

@@ -456,4 +456,60 @@ __global__ void __launch_bounds__(NTHREADS) linear2mel_kernel(const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// mel -> linear recovery (TTS inference): rows of exp'd mel features times pinv(W)^T.
+// One CTA owns M2L_ROWS rows: their features sit in shared memory transposed ([d][row]) so that the inner
+// loop reads four rows per LDS.128 broadcast; thread <-> output bin k, pinv_t (D, K) read coalesced from L2.
+// ---------------------------------------------------------------------------------------------
+constexpr int M2L_ROWS = 32;
+constexpr int M2L_THREADS = 288;
+
+__global__ void __launch_bounds__(M2L_THREADS) mel2linear_kernel(const float* __restrict__ mel, const long long* __restrict__ feat_len,
+                                                                long long n_rows, long long F, int D, int K,
+                                                                const float* __restrict__ pinv_t, int log_mode, float log_base,
+                                                                long long max_len, float clampv, float* __restrict__ lin) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  float* E = reinterpret_cast<float*>(smem);  // [D][M2L_ROWS]
+  const long long r0 = static_cast<long long>(blockIdx.x) * M2L_ROWS;
+  for (int i = threadIdx.x; i < D * M2L_ROWS; i += M2L_THREADS) {
+    const int r = i % M2L_ROWS, d = i / M2L_ROWS;
+    float v = 0.f;
+    if (r0 + r < n_rows) {
+      v = __ldg(mel + (r0 + r) * D + d);
+      if (log_mode == 1) v = expf(v);
+      else if (log_mode == 2) v = powf(log_base, v);
+    }
+    E[i] = v;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += M2L_THREADS) {
+    float acc[M2L_ROWS];
+#pragma unroll
+    for (int r = 0; r < M2L_ROWS; ++r) acc[r] = 0.f;
+    for (int d = 0; d < D; ++d) {
+      const float w = __ldg(pinv_t + static_cast<long long>(d) * K + k);
+      const float4* e4 = reinterpret_cast<const float4*>(E + d * M2L_ROWS);
+#pragma unroll
+      for (int q = 0; q < M2L_ROWS / 4; ++q) {
+        const float4 e = e4[q];
+        acc[4 * q + 0] = fmaf(e.x, w, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(e.y, w, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(e.z, w, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(e.w, w, acc[4 * q + 3]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < M2L_ROWS; ++r) {
+      const long long row = r0 + r;
+      if (row < n_rows) {
+        const long long b = row / F, f = row - b * F;
+        const long long len = feat_len[b];
+        float v = acc[r];
+        if (f >= len && len != max_len) v = 0.f;  // only utterances shorter than the longest are silenced
+        lin[row * K + k] = fmaxf(v, clampv);
+      }
+    }
+  }
+}
+
 }  // namespace sfe

@@ -13,6 +13,7 @@
 #include "../../include/sfe.h"
 #include "sfe_aux.cuh"
 #include "sfe_fused.cuh"
+#include "sfe_gl.cuh"
 
 using namespace sfe;
 
@@ -33,16 +34,24 @@ static int fail(int code, const std::string& msg) {
 // ---------------------------------------------------------------------------------------------
 typedef void (*fused_fn)(const FwdParams);
 
+typedef void (*gl_fn)(const GlParams);
 struct FftEntry {
   int n_fft, win;  // win == 0: any window length (run-time tests)
   int M, G, R1, R2, R3, MP, C;
   fused_fn fn[2];  // [0] no pre-emphasis, [1] pre-emphasis applied while loading
+  gl_fn gl_stft, gl_istft;  // Griffin-Lim transforms (generic-window entries only)
 };
 
 template <int M, int G, int R1, int R2, int R3, int PADQ = R1, int WIN = 0>
 static FftEntry make_entry() {
   typedef FftPlan<M, G, R1, R2, R3, PADQ, WIN> PL;
-  return FftEntry{2 * M, WIN, M, G, R1, R2, R3, PL::MP, PL::C, {&fused_frontend_kernel<PL, false>, &fused_frontend_kernel<PL, true>}};
+  FftEntry e{2 * M, WIN, M, G, R1, R2, R3, PL::MP, PL::C, {&fused_frontend_kernel<PL, false>, &fused_frontend_kernel<PL, true>},
+             nullptr, nullptr};
+  if constexpr (WIN == 0) {
+    e.gl_stft = &gl_stft_kernel<PL>;
+    e.gl_istft = &gl_istft_kernel<PL>;
+  }
+  return e;
 }
 
 static const std::vector<FftEntry>& registry() {
@@ -80,6 +89,10 @@ struct sfe_plan {
   // standalone mel kernel
   int l2m_smem;
   int l2m_sm_warp, l2m_warp_bytes;
+  // Griffin-Lim (built on first use)
+  std::vector<float> h_window;  // the caller's window (win_length floats)
+  float* d_gl = nullptr;        // [ones | synthesis window / n_fft | window^2 | inverse pre-emphasis taps]
+  int gl_o_synth = 0, gl_o_wsq = 0, gl_o_pw = 0, gl_taps = -1;
 };
 
 extern "C" int sfe_abi_version(void) { return SFE_ABI_VERSION; }
@@ -125,6 +138,7 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
   sfe_plan* pl = new sfe_plan();
   memset(&pl->proto, 0, sizeof(FwdParams));
   pl->cfg = *cfg;
+  pl->h_window.assign(cfg->window_host, cfg->window_host + cfg->win_length);
   pl->cfg.window_host = nullptr;
   pl->cfg.mel_weight_host = nullptr;
   pl->fft = fe;
@@ -393,6 +407,7 @@ extern "C" void sfe_plan_destroy(sfe_plan* pl) {
   cudaFree(pl->d_tables);
   cudaFree(pl->d_sched);
   cudaFree(pl->d_acc);
+  cudaFree(pl->d_gl);
   delete pl;
 }
 
@@ -730,6 +745,131 @@ extern "C" int sfe_mean_all(const float* x, int64_t n, float* out, void* stream)
   if (blocks > 148 * 8) blocks = 148 * 8;
   sum_all_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, n, acc);
   mean_finish_kernel<<<1, 1, 0, st>>>(acc, n, out);
+  SFE_CUDA(cudaGetLastError());
+  return SFE_OK;
+}
+
+extern "C" int sfe_mel2linear(const float* mel, const int64_t* feat_len, int32_t B, int64_t F, int32_t D, int32_t K,
+                              const float* pinv_t, int32_t log_mode, float log_base, int64_t max_len, float clamp,
+                              float* lin, void* stream) {
+  if (!mel || !feat_len || !pinv_t || !lin || B < 0 || F < 0 || D <= 0 || K <= 0 || log_mode < 0 || log_mode > 2)
+    return fail(SFE_ERR_BAD_ARG, "sfe_mel2linear: bad argument");
+  if (D > 32 * MAX_MEL_ROUNDS) return fail(SFE_ERR_BAD_ARG, "sfe_mel2linear: n_mels must be <= 512");
+  const long long n_rows = static_cast<long long>(B) * F;
+  if (n_rows == 0) return SFE_OK;
+  const int smem = D * M2L_ROWS * static_cast<int>(sizeof(float));
+  if (smem > 48 * 1024)
+    SFE_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(&mel2linear_kernel),
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const long long grid = (n_rows + M2L_ROWS - 1) / M2L_ROWS;
+  if (grid > 0x7fffffffLL) return fail(SFE_ERR_BAD_ARG, "sfe_mel2linear: too many rows");
+  mel2linear_kernel<<<static_cast<unsigned>(grid), M2L_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+      mel, reinterpret_cast<const long long*>(feat_len), n_rows, F, D, K, pinv_t, log_mode, log_base, max_len, clamp, lin);
+  SFE_CUDA(cudaGetLastError());
+  return SFE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Griffin-Lim
+// ---------------------------------------------------------------------------------------------
+static size_t al256(size_t x) { return (x + 255) / 256 * 256; }
+
+extern "C" int64_t sfe_griffinlim_workspace(const sfe_plan* pl, int32_t B, int64_t F) {
+  if (!pl || B < 0 || F < 0) return -1;
+  const size_t n = static_cast<size_t>(B) * F * (pl->cfg.n_fft / 2 + 1);
+  const size_t L = F > 0 ? static_cast<size_t>(pl->cfg.hop_length) * (F - 1) : 0;
+  return static_cast<int64_t>(al256(n * 4) + 2 * al256(n * 8) + al256(static_cast<size_t>(B) * F * pl->cfg.n_fft * 4) +
+                              al256(static_cast<size_t>(B) * L * 4));
+}
+
+extern "C" int sfe_griffinlim(sfe_plan* pl, const float* spec_in, const int64_t* feat_len, int32_t B, int64_t F,
+                              int32_t n_iter, float momentum, const float* init_angles, int32_t inv_preemph_taps,
+                              void* work, int64_t work_bytes, float* wav, int64_t* wav_len, void* stream) {
+  if (!pl || !spec_in || !feat_len || !work || !wav || B <= 0 || n_iter < 0 || !(momentum >= 0.f && momentum < 1.f) ||
+      inv_preemph_taps < 0)
+    return fail(SFE_ERR_BAD_ARG, "sfe_griffinlim: bad argument");
+  const int n_fft = pl->cfg.n_fft, hop = pl->cfg.hop_length, win = pl->cfg.win_length, K = n_fft / 2 + 1;
+  if (!pl->cfg.center) return fail(SFE_ERR_BAD_CONFIG, "sfe_griffinlim: needs center=True (torch.istft trims n_fft/2 per side)");
+  const long long L = static_cast<long long>(hop) * (F - 1);
+  if (F < 2 || L <= n_fft / 2)
+    return fail(SFE_ERR_BAD_ARG, "sfe_griffinlim: too few frames (reflect padding needs hop*(F-1) > n_fft/2)");
+  if (work_bytes < sfe_griffinlim_workspace(pl, B, F)) return fail(SFE_ERR_BAD_ARG, "sfe_griffinlim: workspace too small");
+  const FftEntry* fe = nullptr;
+  for (const auto& e : registry())
+    if (e.n_fft == n_fft && e.win == 0) fe = &e;
+  if (!fe || !fe->gl_stft || fe->R1 != pl->fft->R1 || fe->R2 != pl->fft->R2 || fe->R3 != pl->fft->R3 || fe->MP != pl->fft->MP)
+    return fail(SFE_ERR_UNSUPPORTED_NFFT, "sfe_griffinlim: no generic-window plan for this n_fft");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool preemph = pl->cfg.has_preemphasis && inv_preemph_taps > 0;
+
+  // ---- constant tables, once per plan (and per tap count) ----
+  const int ones_floats = round_up(n_fft + n_fft / 2 + 8, 4);
+  if (!pl->d_gl || pl->gl_taps != inv_preemph_taps) {
+    std::vector<float> t(ones_floats, 1.f);
+    pl->gl_o_synth = static_cast<int>(t.size());
+    const int lp = (n_fft - win) / 2;
+    for (int j = 0; j < n_fft; ++j) t.push_back((j >= lp && j < lp + win) ? pl->h_window[j - lp] / static_cast<float>(n_fft) : 0.f);
+    pl->gl_o_wsq = static_cast<int>(t.size());
+    for (int j = 0; j < n_fft; ++j) t.push_back((j >= lp && j < lp + win) ? pl->h_window[j - lp] * pl->h_window[j - lp] : 0.f);
+    pl->gl_o_pw = static_cast<int>(t.size());
+    for (int j = 0; j < inv_preemph_taps; ++j) t.push_back(powf(pl->cfg.preemphasis, static_cast<float>(j)));
+    if (pl->d_gl) {
+      SFE_CUDA(cudaStreamSynchronize(st));
+      SFE_CUDA(cudaFree(pl->d_gl));
+      pl->d_gl = nullptr;
+    }
+    SFE_CUDA(cudaMalloc(&pl->d_gl, t.size() * sizeof(float)));
+    SFE_CUDA(cudaMemcpy(pl->d_gl, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+    pl->gl_taps = inv_preemph_taps;
+  }
+
+  // ---- workspace carve-up ----
+  const size_t n = static_cast<size_t>(B) * F * K;
+  unsigned char* w = static_cast<unsigned char*>(work);
+  float* mag = reinterpret_cast<float*>(w); w += al256(n * 4);
+  float2* tprev = reinterpret_cast<float2*>(w); w += al256(n * 8);
+  float2* spec = reinterpret_cast<float2*>(w); w += al256(n * 8);
+  float* frames = reinterpret_cast<float*>(w); w += al256(static_cast<size_t>(B) * F * n_fft * 4);
+  float* tmp = reinterpret_cast<float*>(w);
+
+  GlParams P;
+  memset(&P, 0, sizeof(P));
+  P.B = B; P.F = static_cast<int>(F); P.K = K; P.n_fft = n_fft; P.win = win; P.hop = hop;
+  P.L = L;
+  P.n_frames = static_cast<long long>(B) * F;
+  P.tables = pl->d_tables;
+  P.tab_floats = pl->proto.o_mtab;  // window, Stockham twiddles, unpack twiddles (everything before the mel tables)
+  P.o_win = pl->proto.o_win; P.o_tw2 = pl->proto.o_tw2; P.o_tw3 = pl->proto.o_tw3; P.o_wpost = pl->proto.o_wpost;
+  P.gl_tab = pl->d_gl;
+  P.o_ones = 0; P.o_synth = pl->gl_o_synth; P.o_wsq = pl->gl_o_wsq;
+  P.wav = tmp; P.mag = mag; P.tprev = tprev; P.spec = spec; P.frames = frames;
+  P.momentum = momentum / (1.f + momentum);
+  P.stage_floats = ones_floats;
+  P.sm_warp = round_up(P.tab_floats * 4, 16);
+  P.sm_stage_off = round_up(fe->C * fe->MP * 8, 16);
+  P.sm_warp_bytes = P.sm_stage_off + round_up(fe->C * P.stage_floats * 4, 16);
+  const int smem = P.sm_warp + GL_WARPS * P.sm_warp_bytes;
+  SFE_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fe->gl_stft), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  SFE_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fe->gl_istft), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const long long groups = (P.n_frames + fe->C - 1) / fe->C;
+  long long gridf = (groups + GL_WARPS - 1) / GL_WARPS;
+  if (gridf > pl->n_sm * 8LL) gridf = pl->n_sm * 8LL;
+  const unsigned grid_n = static_cast<unsigned>((n + 255) / 256);
+  const long long BL = static_cast<long long>(B) * L;
+  const unsigned grid_w = static_cast<unsigned>(((BL > B ? BL : B) + 255) / 256);
+
+  gl_init_kernel<<<grid_n, 256, 0, st>>>(spec_in, reinterpret_cast<const float2*>(init_angles), static_cast<long long>(n),
+                                         pl->cfg.mag_spec ? 0 : 1, mag, spec);
+  for (int it = 0; it <= n_iter; ++it) {
+    fe->gl_istft<<<static_cast<unsigned>(gridf), GL_THREADS, smem, st>>>(P);
+    gl_ola_kernel<<<grid_w, 256, 0, st>>>(frames, pl->d_gl + pl->gl_o_wsq, B, static_cast<int>(F), n_fft, hop, L, tmp);
+    if (it == n_iter) break;
+    P.first = (it == 0) ? 1 : 0;
+    fe->gl_stft<<<static_cast<unsigned>(gridf), GL_THREADS, smem, st>>>(P);
+  }
+  gl_finish_kernel<<<grid_w, 256, 0, st>>>(tmp, preemph ? pl->d_gl + pl->gl_o_pw : nullptr, inv_preemph_taps,
+                                           reinterpret_cast<const long long*>(feat_len), hop, B, L, wav,
+                                           reinterpret_cast<long long*>(wav_len));
   SFE_CUDA(cudaGetLastError());
   return SFE_OK;
 }

@@ -246,6 +246,31 @@ class FrontendPlan:
             self._ws[B][1] = 1 - half
         return mel, feat_len
 
+    def griffinlim(self, spec: torch.Tensor, feat_len: torch.Tensor, *, n_iter: int = 32, momentum: float = 0.99,
+                   init_angles: Optional[torch.Tensor] = None, inv_preemph_taps: int = 0):
+        """(B, F, K) power/magnitude spectrogram -> (waveform (B, hop*(F-1)), wav_len (B,)); see sfe_griffinlim.
+        `init_angles` (B, F, K) complex64 on the device, or None for an all-ones start."""
+        _need_cuda(spec, "feat")
+        spec = spec.contiguous()
+        B, F, K = spec.shape
+        if K != self.n_bins:
+            raise RuntimeError(f"expected {self.n_bins} linear bins, got feat.shape={tuple(spec.shape)}")
+        dev = spec.device
+        ang = None
+        if init_angles is not None:
+            ang = torch.view_as_real(init_angles.to(dev, torch.complex64).contiguous())
+        nbytes = self._lib.sfe_griffinlim_workspace(self._h, B, F)
+        if nbytes < 0:
+            raise RuntimeError("sfe_griffinlim_workspace failed")
+        work = torch.empty((max(int(nbytes), 1),), dtype=torch.uint8, device=dev)
+        wav = torch.empty((B, self.hop_length * max(F - 1, 0)), dtype=torch.float32, device=dev)
+        wav_len = torch.empty((B,), dtype=torch.int64, device=dev)
+        with _on_device(dev):
+            _lib.check(self._lib.sfe_griffinlim(self._h, _ptr(spec), _ptr(feat_len), B, F, int(n_iter), float(momentum),
+                                                _ptr(ang), int(inv_preemph_taps), _ptr(work), int(nbytes), _ptr(wav),
+                                                _ptr(wav_len), _stream()))
+        return wav, wav_len
+
     def linear2mel(self, lin: torch.Tensor) -> torch.Tensor:
         _need_cuda(lin, "feat")
         lin = lin.contiguous()
@@ -356,3 +381,17 @@ def upload_waveforms(wav_host: torch.Tensor, len_host: torch.Tensor, out: Option
     with _on_device(out.device):
         _lib.check(_lib.load().sfe_upload_waveforms(wav_host.data_ptr(), T, len_host.data_ptr(), B, out.data_ptr(), T, _stream()))
     return out
+
+
+def mel2linear(mel: torch.Tensor, feat_len: torch.Tensor, pinv_t: torch.Tensor, *, log_mode: int, log_base: float,
+               max_len: int, clamp: float = 1e-10) -> torch.Tensor:
+    """(B, F, D) (log-)mel -> (B, F, K) linear spectrogram through pinv(W)^T (D, K); see sfe_mel2linear."""
+    _need_cuda(mel, "feat")
+    mel = mel.contiguous()
+    B, F, D = mel.shape
+    K = pinv_t.shape[1]
+    lin = torch.empty((B, F, K), dtype=torch.float32, device=mel.device)
+    with _on_device(mel.device):
+        _lib.check(_lib.load().sfe_mel2linear(_ptr(mel), _ptr(feat_len), B, F, D, K, _ptr(pinv_t), int(log_mode),
+                                              float(log_base), int(max_len), float(clamp), _ptr(lin), _stream()))
+    return lin

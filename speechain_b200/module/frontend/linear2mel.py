@@ -1,7 +1,7 @@
 """Linear spectrogram -> (log-)mel.  API mirror of speechain/module/frontend/linear2mel.py."""
 import torch
 
-from ...host.ops import FrontendPlan
+from ...host.ops import FrontendPlan, HostLengths, mel2linear
 from ..abs import Module
 from ._common import ConstHolder, as_float, mel_filterbank
 
@@ -52,6 +52,7 @@ class LinearSpec2MelSpec(Module):
         # compiled plans hold raw library handles: never pickle / deepcopy them
         d = self.__dict__.copy()
         d["_plans"] = {}
+        d.pop("_pinv", None)
         return d
 
     def forward(self, feat: torch.Tensor, feat_len: torch.Tensor):
@@ -62,9 +63,30 @@ class LinearSpec2MelSpec(Module):
             raise RuntimeError("speechain_b200 frontend: `feat` must be a CUDA tensor — there is no CPU path.")
         return self._plan(feat.device).linear2mel(feat.float()), feat_len
 
+    def _pinv_t(self, device) -> torch.Tensor:
+        """pinv(W)^T (n_mels, n_fft//2+1) on `device`.  For the full-row-rank filterbank this is the
+        minimum-norm solution operator that ``torch.linalg.lstsq(W, ·, driver="gels")`` applies
+        (linear2mel.py:209-214); computed once per weight version in fp64 on the host."""
+        w = self.mel_fbanks.weight
+        key = (str(device), w._version)
+        hit = self._pinv.get(key) if hasattr(self, "_pinv") else None
+        if hit is None:
+            self._pinv = {key: torch.linalg.pinv(w.detach().to("cpu", torch.float64)).T.contiguous().float().to(device)}
+            hit = self._pinv[key]
+        return hit
+
     def recover(self, feat: torch.Tensor, feat_len: torch.Tensor):
-        raise NotImplementedError("mel -> linear least-squares recovery (linear2mel.py:191-224) is a later row of the "
-                                  "scope table (SURVEY.md §8 f4).")
+        """(log-)mel (batch, F, n_mels) -> linear spectrogram (batch, F, n_fft//2+1), clamped at 1e-10; rows
+        beyond the length of every utterance shorter than the longest are silenced first (linear2mel.py:191-224)."""
+        if not feat.is_cuda:
+            raise RuntimeError("speechain_b200 frontend: `feat` must be a CUDA tensor — there is no CPU path.")
+        if feat.size(-1) != self.n_mels:
+            raise RuntimeError(f"expected {self.n_mels} mel bins, got feat.shape={tuple(feat.shape)}")
+        len_host = HostLengths.get(feat_len)
+        len_dev = feat_len if feat_len.is_cuda else feat_len.to(feat.device, non_blocking=True)
+        mode = 0 if not self.logging else (1 if self.log_base is None else 2)
+        return mel2linear(feat.float(), len_dev.long(), self._pinv_t(feat.device), log_mode=mode,
+                          log_base=self.log_base or 0.0, max_len=int(len_host.max()) if len(len_host) else 0)
 
     def __repr__(self) -> str:
         return (f"{self.__class__.__name__}(\n"

@@ -47,13 +47,14 @@ class Speech2LinearSpec(Module):
         self._plans = {}
 
     # ------------------------------------------------------------------------------------
-    def _plan(self, device, preemph: bool = True, mel: Optional[dict] = None) -> FrontendPlan:
+    def _plan(self, device, preemph: bool = True, mel: Optional[dict] = None, plain_window: bool = False) -> FrontendPlan:
         # (a checkpoint load copies into the filterbank buffer in place: the version counter catches that)
-        key = (str(device), preemph, None if mel is None else (id(mel["weight"]), mel["weight"]._version))
+        key = (str(device), preemph, None if mel is None else (id(mel["weight"]), mel["weight"]._version), plain_window)
         plan = self._plans.get(key)
         if plan is None:
             c = self.stft_config
-            win = make_window(c["window"], self.win_length, self.n_fft, c["normalized"])
+            # (Griffin-Lim in the reference always runs un-normalised STFTs, whatever `normalized` says)
+            win = make_window(c["window"], self.win_length, self.n_fft, c["normalized"] and not plain_window)
             kw = dict(n_fft=self.n_fft, win_length=self.win_length, hop_length=self.hop_length, center=c["center"],
                       preemphasis=self.preemphasis if preemph else None, mag_spec=self.mag_spec,
                       lin_logging=self.logging, lin_clamp=self.clamp, lin_log_base=self.log_base, window=win,
@@ -145,9 +146,32 @@ class Speech2LinearSpec(Module):
             return out["lin"], feat_len, out["energy"], feat_len
         return out["lin"], feat_len
 
+    # torchaudio.transforms.GriffinLim defaults the reference relies on (speech2linear.py:281-292)
+    GL_N_ITER, GL_MOMENTUM = 32, 0.99
+
     def recover(self, feat: torch.Tensor, feat_len: torch.Tensor, inv_preemph_winlen: int = 100):
-        raise NotImplementedError("Griffin-Lim recovery (speech2linear.py:252-351) is a later row of the scope table "
-                                  "(SURVEY.md §8 f4); it is not part of the accelerated forward path.")
+        """Linear spectrogram (batch, F, n_fft//2+1) -> (waveform, wav_len) by Griffin-Lim, inverse pre-emphasis over a
+        sliding window and silencing of the padding (speech2linear.py:252-351).  Returns the reference's shapes:
+        (batch, L, 1) when a pre-emphasis is undone, (batch, L) otherwise, with L = hop_length * (F - 1).
+
+        The initial phase is drawn exactly like torchaudio does on the CPU — ``torch.rand`` of the (batch, bins,
+        frames) complex tensor on the global CPU generator — so a seeded call reproduces the reference's CPU result."""
+        if not feat.is_cuda:
+            raise RuntimeError("speechain_b200 frontend: `feat` must be a CUDA tensor — there is no CPU path.")
+        assert self.pre_stft_norm is None, "waveform pre-stft normalization cannot be recovered for TTS synthesis."
+        B, F, K = feat.shape
+        len_host = HostLengths.get(feat_len)
+        assert int(len_host.max()) == F, "Something wrong happens when calculating the length of synthetic utterances."
+        len_dev = feat_len if feat_len.is_cuda else feat_len.to(feat.device, non_blocking=True)
+        angles = torch.rand((B, K, F), dtype=torch.complex64).transpose(1, 2).contiguous()
+        plan = self._plan(feat.device, preemph=True, plain_window=bool(self.stft_config["normalized"]))
+        wav, wav_len = plan.griffinlim(feat.float(), len_dev.long(), n_iter=self.GL_N_ITER, momentum=self.GL_MOMENTUM,
+                                       init_angles=angles.pin_memory().to(feat.device, non_blocking=True),
+                                       inv_preemph_taps=inv_preemph_winlen if self.preemphasis is not None else 0)
+        HostLengths.remember(wav_len, (len_host - 1) * self.hop_length)
+        if self.preemphasis is not None:
+            wav = wav.unsqueeze(-1)
+        return wav, wav_len
 
     def get_sample_rate(self):
         return self.sr

@@ -67,7 +67,12 @@ def make_wave(seed, lens, zero_seg=None, scale=0.1):
     return wav, torch.tensor(lens, dtype=torch.int64)
 
 
+ONLY = [a for a in sys.argv[1:] if not a.startswith("-")]  # optional: write only fixtures whose name starts with one of these
+
+
 def save(name, **arrs):
+    if ONLY and not any(name.startswith(o) for o in ONLY):
+        return
     out = {}
     for k, v in arrs.items():
         if isinstance(v, torch.Tensor):
@@ -157,6 +162,51 @@ def main():
     m = LinearSpec2MelSpec(n_fft=512, n_mels=80)
     mel, _ = m(spec, torch.tensor([30, 20]))
     save("l2m", spec=spec, mel=mel, mel_weight=m.mel_fbanks.weight)
+
+    print("mel -> linear recovery (LinearSpec2MelSpec.recover, linear2mel.py:191-224)")
+    flen = torch.tensor([30, 20])
+    rec = m.recover(mel.clone(), flen.clone())
+    save("m2l_log10", mel=mel, feat_len=flen, lin=rec, mel_weight=m.mel_fbanks.weight)
+    g = torch.Generator().manual_seed(1261)
+    spec2 = torch.rand(3, 24, 513, generator=g) ** 3 * 5
+    m2 = LinearSpec2MelSpec(n_fft=1024, n_mels=80, sr=22050, fmin=0, fmax=8000, clamp=1e-5, log_base=None)
+    flen2 = torch.tensor([24, 24, 11])
+    mel2, _ = m2(spec2, flen2.clone())
+    rec2 = m2.recover(mel2.clone(), flen2.clone())
+    save("m2l_ln_tts", mel=mel2, feat_len=flen2, lin=rec2, mel_weight=m2.mel_fbanks.weight,
+         conf=np.array([1024, 80, 22050, 8000]))
+    m3 = LinearSpec2MelSpec(n_fft=512, n_mels=80, logging=False)
+    mel3, _ = m3(spec, flen.clone())
+    rec3 = m3.recover(mel3.clone(), flen.clone())
+    save("m2l_nolog", mel=mel3, feat_len=flen, lin=rec3, mel_weight=m3.mel_fbanks.weight)
+
+    print("Griffin-Lim recovery (Speech2LinearSpec.recover / Speech2MelSpec.recover)")
+    import math
+
+    def gl_case(name, conf, lens, seed, mel=False):
+        sr = conf.get("sr", 16000)
+        T = max(lens)
+        t = torch.arange(T) / sr
+        gg = torch.Generator().manual_seed(seed)
+        base = 0.3 * torch.sin(2 * math.pi * 220 * t) + 0.2 * torch.sin(2 * math.pi * 1333 * t) + 0.02 * torch.randn(T, generator=gg)
+        wav = torch.stack([base * (0.9 ** i) if i % 2 == 0 else base.flip(0) * 0.7 for i in range(len(lens))])[..., None]
+        wl = torch.tensor(lens)
+        for i, n in enumerate(lens):
+            wav[i, n:] = 0
+        cls = Speech2MelSpec if mel else Speech2LinearSpec
+        feat, fl = cls(**conf)(wav.clone(), wl.clone())[:2]
+        fresh = cls(**conf)  # recover() only works on a module whose forward never ran (it re-reads stft_config["window"])
+        K = (conf.get("n_fft") or conf["win_length"]) // 2 + 1
+        torch.manual_seed(seed)
+        angles = torch.rand(len(lens), K, feat.shape[1], dtype=torch.cfloat)
+        torch.manual_seed(seed)
+        rec, rl = fresh.recover(feat.clone(), fl.clone())
+        save(name, feat=feat, feat_len=fl, angles=angles.transpose(1, 2).contiguous(), wav=rec, wav_len=rl, seed=np.array(seed))
+
+    gl_case("gl_lin_512", dict(hop_length=160, win_length=400, n_fft=512, sr=16000), [8000, 6400], 11)
+    gl_case("gl_lin_pre_400", dict(hop_length=160, win_length=400, sr=16000, preemphasis=0.97, mag_spec=True), [6400, 6400, 3200], 12)
+    gl_case("gl_mel_tts_1024", dict(n_mels=80, hop_length=256, win_length=1024, sr=22050, fmin=0, fmax=8000, clamp=1e-5,
+                                     log_base=None, preemphasis=0.97), [11025, 8000], 13, mel=True)
 
     print("utterance norm + SpecAugment (C2 chain)")
     wav, wl, feat, fl = frontend_case("chain_c2_fe", [9600, 8000, 6400, 4800, 3300, 3300], 1270, dict(C1, preemphasis=0.97))

@@ -30,3 +30,16 @@ def assert_close(a, b, rtol=RTOL, atol=ATOL, what=""):
         f"{what}: max abs err {err.max():.3e}, worst excess {excess.max():.3e} at "
         f"{np.unravel_index(np.argmax(excess), a.shape)}")
     return float(err.max())
+
+
+def assert_gl_close(wav, ref, what=""):
+    """Waveforms out of Griffin-Lim: rms error <= 5e-4 of the peak, max error <= 5e-3 of the peak."""
+    wav = np.asarray(wav, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert wav.shape == ref.shape, f"{what}: shape {wav.shape} vs {ref.shape}"
+    assert np.isfinite(wav).all(), f"{what}: non-finite samples"
+    peak = np.abs(ref).max()
+    err = np.abs(wav - ref)
+    rms = np.sqrt((err ** 2).mean())
+    assert err.max() <= 5e-3 * peak and rms <= 5e-4 * peak, (
+        f"{what}: max err {err.max():.3e}, rms err {rms:.3e}, peak {peak:.3e}")

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import frontend_np as O
-from sfe_testutil import assert_close, load_golden
+from sfe_testutil import assert_close, assert_gl_close, load_golden
 from test_oracle_golden import FE_CASES, SA_CASES
 
 pytestmark = pytest.mark.gpu
@@ -101,6 +101,112 @@ def test_linear2mel_golden():
     m = LinearSpec2MelSpec(n_fft=512, n_mels=80).to(DEV)
     mel, _ = m(cu(g["spec"]), cu(np.array([30, 20])))
     assert_close(mel.cpu().numpy(), g["mel"], what="l2m")
+
+
+@pytest.mark.parametrize("name,conf", [
+    ("m2l_log10", dict(n_fft=512, n_mels=80)),
+    ("m2l_ln_tts", dict(n_fft=1024, n_mels=80, sr=22050, fmin=0, fmax=8000, clamp=1e-5, log_base=None)),
+    ("m2l_nolog", dict(n_fft=512, n_mels=80, logging=False)),
+])
+def test_mel2linear_recover_golden(name, conf):
+    """LinearSpec2MelSpec.recover against the reference's lstsq output (relative to each frame's largest bin:
+    the least-squares solution cancels inside a frame) and against the fp64 oracle."""
+    g = load_golden(name)
+    m = LinearSpec2MelSpec(**conf).to(DEV)
+    assert np.array_equal(m.mel_fbanks.weight.cpu().numpy(), g["mel_weight"])
+    for flen in (cu(g["feat_len"]), torch.from_numpy(g["feat_len"])):   # device or host lengths
+        lin = m.recover(cu(g["mel"]), flen).cpu().numpy()
+        scale = np.maximum(g["lin"].max(axis=-1, keepdims=True), 1e-10)
+        assert_close(lin / scale, g["lin"] / scale, rtol=0, atol=1e-5, what=name)
+        ref = O.mel2linear(g["mel"], g["feat_len"], g["mel_weight"], logging=conf.get("logging", True),
+                           log_base=conf.get("log_base", 10.0))
+        assert_close(lin / scale, ref / scale, rtol=0, atol=1e-5, what=name + " vs oracle")
+        assert lin.min() >= 1e-10
+        fl = g["feat_len"]
+        for i, n in enumerate(fl):
+            if n != fl.max():
+                assert (lin[i, n:] == np.float32(1e-10)).all()
+
+
+def test_mel2linear_roundtrip_full_size():
+    """Size-independent property at a C2-like size: mel(recover(mel)) == mel, because W pinv(W) = I."""
+    torch.manual_seed(5)
+    m = LinearSpec2MelSpec(n_fft=512, n_mels=80).to(DEV)
+    mel = torch.randn(16, 1200, 80, device=DEV) * 2 - 3      # log10 mel energies
+    flen = torch.full((16,), 1200, dtype=torch.int64, device=DEV)
+    lin = m.recover(mel, flen)
+    assert lin.shape == (16, 1200, 257)
+    # the clamp at 1e-10 only touches bins the unconstrained solution drives negative: undo it for the check
+    pinv_t = m._pinv_t(mel.device)
+    raw = torch.pow(10.0, mel.double()) @ pinv_t.double()
+    back = raw.float() @ m.mel_fbanks.weight.T
+    assert_close(back.cpu().numpy(), torch.pow(10.0, mel).cpu().numpy(), rtol=2e-4, atol=1e-6, what="W pinv(W) = I")
+    assert_close(lin.cpu().numpy(), raw.clamp(min=1e-10).float().cpu().numpy(), rtol=1e-4,
+                 atol=1e-5 * float(raw.max()), what="kernel vs fp64 product")
+
+
+GL_GPU_CASES = {
+    "gl_lin_512": (Speech2LinearSpec, dict(hop_length=160, win_length=400, n_fft=512, sr=16000)),
+    "gl_lin_pre_400": (Speech2LinearSpec, dict(hop_length=160, win_length=400, sr=16000, preemphasis=0.97, mag_spec=True)),
+    "gl_mel_tts_1024": (Speech2MelSpec, dict(n_mels=80, hop_length=256, win_length=1024, sr=22050, fmin=0, fmax=8000,
+                                             clamp=1e-5, log_base=None, preemphasis=0.97)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(GL_GPU_CASES))
+def test_griffinlim_recover_golden(name):
+    """recover() (Griffin-Lim + inverse pre-emphasis) against the reference's CPU output: the module draws the
+    initial phase from the global CPU generator exactly like torchaudio, so seeding reproduces the reference."""
+    g = load_golden(name)
+    cls, conf = GL_GPU_CASES[name]
+    m = cls(**conf).to(DEV)
+    torch.manual_seed(int(g["seed"]))
+    wav, wav_len = m.recover(cu(g["feat"]), cu(g["feat_len"]))
+    assert tuple(wav.shape) == tuple(g["wav"].shape)          # (B, L, 1) with pre-emphasis, (B, L) without
+    assert np.array_equal(wav_len.cpu().numpy(), g["wav_len"])
+    assert_gl_close(wav.cpu().numpy(), g["wav"], what=name)
+    w = wav.cpu().numpy().reshape(len(g["wav_len"]), -1)
+    for i, n in enumerate(g["wav_len"]):
+        assert (w[i, n:] == 0).all()
+
+
+def test_griffinlim_single_iteration_matches_oracle():
+    """One STFT/ISTFT round trip at every compiled FFT size against the fp64 oracle (tight tolerance: no chaos yet)."""
+    from speechain_b200.host.ops import FrontendPlan
+    rng = np.random.default_rng(7)
+    for n_fft, win, hop in [(128, 128, 32), (200, 200, 50), (256, 200, 64), (320, 320, 80), (400, 400, 160), (480, 400, 120),
+                            (512, 400, 160), (640, 640, 160), (800, 800, 200), (1024, 1024, 256), (2048, 1200, 300)]:
+        B, F, K = 2, 12, n_fft // 2 + 1
+        window = torch.hann_window(win)
+        plan = FrontendPlan(n_fft=n_fft, win_length=win, hop_length=hop, window=window, device=DEV)
+        spec = rng.random((B, F, K)).astype(np.float32) ** 2 + 1e-3
+        ang = (rng.random((B, F, K)) + 1j * rng.random((B, F, K))).astype(np.complex64)
+        flen = np.array([F, F - 3])
+        for n_iter in (0, 2):
+            wav, wl = plan.griffinlim(cu(spec), cu(flen), n_iter=n_iter, momentum=0.99, init_angles=torch.from_numpy(ang))
+            ref = O.griffinlim(spec, n_fft, hop, win, window.numpy(), 2.0, ang, n_iter=n_iter)
+            for i, n in enumerate((flen - 1) * hop):
+                ref[i, n:] = 0
+            assert np.array_equal(wl.cpu().numpy(), (flen - 1) * hop)
+            assert_close(wav.cpu().numpy(), ref, rtol=0, atol=2e-5 * np.abs(ref).max(), what=f"n_fft {n_fft} n_iter {n_iter}")
+
+
+def test_griffinlim_spectral_convergence_full_size():
+    """Size-independent property at a TTS-batch size: the recovered waveform's spectrogram approaches the input
+    magnitudes (spectral convergence well below the random-phase start) and the output is finite."""
+    conf = dict(hop_length=256, win_length=1024, sr=22050, mag_spec=True)
+    fe = Speech2LinearSpec(**conf).to(DEV)
+    torch.manual_seed(3)
+    t = torch.arange(22050 * 4, device=DEV) / 22050
+    wav = torch.stack([0.4 * torch.sin(2 * np.pi * (110 * (i + 1)) * t) * torch.sin(2 * np.pi * 3 * t) for i in range(16)])[..., None]
+    wl = torch.full((16,), wav.size(1), dtype=torch.int64, device=DEV)
+    spec, fl = fe(wav, wl)
+    rec, rl = Speech2LinearSpec(**conf).to(DEV).recover(spec, fl)
+    assert torch.isfinite(rec).all()
+    spec2, _ = fe(rec[..., None] if rec.dim() == 2 else rec, rl)
+    F = min(spec.size(1), spec2.size(1))
+    sc = (torch.linalg.norm(spec[:, :F] - spec2[:, :F]) / torch.linalg.norm(spec[:, :F])).item()
+    assert sc < 0.1, sc
 
 
 def test_delta_matches_oracle():

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import frontend_np as O
-from sfe_testutil import assert_close, load_golden
+from sfe_testutil import assert_gl_close, assert_close, load_golden
 
 FE_CASES = {
     "fe_c1": dict(n_mels=80, n_fft=512, win_length=0.025, hop_length=0.010),
@@ -86,6 +86,60 @@ def test_linear2mel_standalone():
     g = load_golden("l2m")
     mel = O.linear2mel(g["spec"].astype(np.float64), g["mel_weight"].astype(np.float64))
     assert_close(mel, g["mel"], what="l2m")
+
+
+M2L_CASES = {
+    "m2l_log10": dict(logging=True, log_base=10.0),
+    "m2l_ln_tts": dict(logging=True, log_base=None),
+    "m2l_nolog": dict(logging=False, log_base=10.0),
+}
+
+
+@pytest.mark.parametrize("name", sorted(M2L_CASES))
+def test_mel2linear_recover(name):
+    """mel -> linear least squares (linear2mel.py:191-224).  The solution cancels heavily inside a frame, so
+    the comparison is relative to the frame's largest bin (fp32 lstsq noise of the reference ~5e-7 of it)."""
+    g = load_golden(name)
+    lin = O.mel2linear(g["mel"], g["feat_len"], g["mel_weight"], **M2L_CASES[name])
+    scale = np.maximum(g["lin"].max(axis=-1, keepdims=True), 1e-10)
+    assert_close(lin / scale, g["lin"] / scale, rtol=0, atol=1e-5, what=name)
+    # silence rule: only utterances shorter than the longest are zeroed (-> clamp floor)
+    fl = g["feat_len"]
+    for i, n in enumerate(fl):
+        if n != fl.max():
+            assert (lin[i, n:] == 1e-10).all()
+
+
+GL_CASES = {
+    "gl_lin_512": dict(n_fft=512, hop=160, win=400, mag_spec=False, preemphasis=None),
+    "gl_lin_pre_400": dict(n_fft=400, hop=160, win=400, mag_spec=True, preemphasis=0.97),
+    "gl_mel_tts_1024": dict(n_fft=1024, hop=256, win=1024, mag_spec=False, preemphasis=0.97),
+}
+
+
+def hann_periodic(n):
+    return (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(n) / n)).astype(np.float32)
+
+
+@pytest.mark.parametrize("name", sorted(GL_CASES))
+def test_griffinlim_recover(name):
+    """Griffin-Lim (32 iterations with momentum) started from the reference's own random phase.  The iteration
+    amplifies rounding differences at the few bins whose phase is ill-conditioned, so two correct
+    implementations (fp64 here, fp32 in the reference) agree to ~1e-4 of the peak in rms with isolated samples
+    up to ~1e-3: asserted as rms <= 5e-4 peak and max <= 5e-3 peak (sfe_testutil.assert_gl_close)."""
+    g = load_golden(name)
+    c = GL_CASES[name]
+    spec = g["feat"]
+    if name.startswith("gl_mel"):
+        W = O.mel_filterbank(22050, 1024, 80, 0.0, 8000.0).astype(np.float32)
+        spec = O.mel2linear(spec, g["feat_len"], W, logging=True, log_base=None)
+    wav, wav_len = O.speech2linear_recover(spec, g["feat_len"], c["n_fft"], c["hop"], c["win"], hann_periodic(c["win"]),
+                                           c["mag_spec"], c["preemphasis"], g["angles"])
+    ref = g["wav"].reshape(wav.shape)
+    assert np.array_equal(wav_len, g["wav_len"])
+    assert_gl_close(wav, ref, what=name)
+    for i, n in enumerate(wav_len):
+        assert (wav[i, n:] == 0).all()
 
 
 def test_preemphasis_known_answer():
