@@ -146,9 +146,9 @@ def test_mel2linear_roundtrip_full_size():
 
 
 GL_GPU_CASES = {
-    "gl_lin_512": (Speech2LinearSpec, dict(hop_length=160, win_length=400, n_fft=512, sr=16000)),
-    "gl_lin_pre_400": (Speech2LinearSpec, dict(hop_length=160, win_length=400, sr=16000, preemphasis=0.97, mag_spec=True)),
-    "gl_mel_tts_1024": (Speech2MelSpec, dict(n_mels=80, hop_length=256, win_length=1024, sr=22050, fmin=0, fmax=8000,
+    "gl_lin_512": ("Speech2LinearSpec", dict(hop_length=160, win_length=400, n_fft=512, sr=16000)),
+    "gl_lin_pre_400": ("Speech2LinearSpec", dict(hop_length=160, win_length=400, sr=16000, preemphasis=0.97, mag_spec=True)),
+    "gl_mel_tts_1024": ("Speech2MelSpec", dict(n_mels=80, hop_length=256, win_length=1024, sr=22050, fmin=0, fmax=8000,
                                              clamp=1e-5, log_base=None, preemphasis=0.97)),
 }
 
@@ -159,7 +159,7 @@ def test_griffinlim_recover_golden(name):
     initial phase from the global CPU generator exactly like torchaudio, so seeding reproduces the reference."""
     g = load_golden(name)
     cls, conf = GL_GPU_CASES[name]
-    m = cls(**conf).to(DEV)
+    m = globals()[cls](**conf).to(DEV)
     torch.manual_seed(int(g["seed"]))
     wav, wav_len = m.recover(cu(g["feat"]), cu(g["feat_len"]))
     assert tuple(wav.shape) == tuple(g["wav"].shape)          # (B, L, 1) with pre-emphasis, (B, L) without
