@@ -1,18 +1,32 @@
-"""Build libsfe.so (and the oracle's helpers) with nvcc for sm_100a.  In-tree, no JIT cache."""
+"""Build libsfe.so with nvcc for sm_100a.  In-tree, no JIT cache.
+
+The library is one object for the C ABI / small kernels (sfe_lib.cu) plus one object per FFT plan
+(sfe_plans.cu compiled with -DSFE_PLAN_TU=i), compiled in parallel and linked into one shared library.
+SFE_DEV_PLANS="12,13" (development only) recompiles just those plan objects when only kernel headers changed.
+"""
 import os
+import re
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["sfe_lib.cu"]
-HEADERS = ["sfe_fft.cuh", "sfe_fused.cuh", "sfe_aux.cuh", os.path.join("..", "..", "include", "sfe.h")]
+HEADERS = ["sfe_fft.cuh", "sfe_fused.cuh", "sfe_aux.cuh", "sfe_gl.cuh", "sfe_registry.h",
+           os.path.join("..", "..", "include", "sfe.h")]
+SOURCES = ["sfe_lib.cu", "sfe_plans.cu"]
 OUT = os.path.join(HERE, "libsfe.so")
+OBJ = os.path.join(HERE, "build")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
+
+
+def num_plans() -> int:
+    txt = open(os.path.join(HERE, "sfe_registry.h")).read()
+    return len(re.findall(r"^\s*X\(\d+,", txt, flags=re.M))
 
 
 def stale() -> bool:
@@ -22,16 +36,36 @@ def stale() -> bool:
     return any(os.path.getmtime(os.path.join(HERE, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not stale():
-        return OUT
+def _nvcc() -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    if not os.path.exists(nvcc):
-        nvcc = "nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
+    return nvcc if os.path.exists(nvcc) else "nvcc"
+
+
+def _run(cmd):
     print("[build]", " ".join(cmd), flush=True)
     subprocess.run(cmd, cwd=HERE, check=True)
-    return OUT
+
+
+def build(force: bool = False, verbose: bool = False, out: str = OUT) -> str:
+    if not force and out == OUT and not stale():
+        return OUT
+    os.makedirs(OBJ, exist_ok=True)
+    nvcc = _nvcc()
+    extra = ["-Xptxas", "-v"] if verbose else []
+    n = num_plans()
+    objs = [os.path.join(OBJ, "sfe_lib.o")] + [os.path.join(OBJ, f"sfe_plan_{i}.o") for i in range(n)]
+    jobs = [[nvcc] + NVCC_FLAGS + extra + ["-c", "sfe_lib.cu", "-o", objs[0]]]
+    for i in range(n):
+        jobs.append([nvcc] + NVCC_FLAGS + extra + [f"-DSFE_PLAN_TU={i}", "-c", "sfe_plans.cu", "-o", objs[1 + i]])
+    dev = os.environ.get("SFE_DEV_PLANS")
+    if dev:  # development shortcut: the other objects must already exist
+        keep = {int(x) for x in dev.split(",") if x.strip()}
+        jobs = [j for k, j in enumerate(jobs) if (k == 0 and "lib" in dev) or (k - 1) in keep or not os.path.exists(objs[k])]
+    workers = int(os.environ.get("SFE_BUILD_JOBS", str(os.cpu_count() or 4)))
+    with ThreadPoolExecutor(max_workers=max(1, workers)) as ex:
+        list(ex.map(_run, jobs))
+    _run([nvcc] + NVCC_FLAGS + ["-shared", "-o", out] + objs)
+    return out
 
 
 if __name__ == "__main__":

@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(GL_THREADS) gl_istft_kernel(const __grid_const
   }
 }
 
+#ifndef SFE_PLAN_TU  // not templated on the plan: defined once, in sfe_lib.cu
 // ---------------------------------------------------------------------------------------------
 // frames -> waveform (overlap-add as a gather; torch.istft's window-envelope normalisation and centre trim)
 // ---------------------------------------------------------------------------------------------
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(256) gl_ola_kernel(const float* __restrict__ f
   }
   wav[i] = (env > 1e-11f) ? sum / env : sum;
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // waveform -> rebuilt spectrum -> phase update -> next spectrum
@@ -253,6 +255,7 @@ __global__ void __launch_bounds__(GL_THREADS) gl_stft_kernel(const __grid_consta
   }
 }
 
+#ifndef SFE_PLAN_TU  // not templated on the plan: defined once, in sfe_lib.cu
 // ---------------------------------------------------------------------------------------------
 // small elementwise kernels
 // ---------------------------------------------------------------------------------------------
@@ -268,7 +271,9 @@ __global__ void __launch_bounds__(256) gl_init_kernel(const float* __restrict__ 
   const float2 a = angles ? angles[i] : make_float2(1.f, 0.f);
   spec[i] = make_float2(a.x * m, a.y * m);
 }
+#endif
 
+#ifndef SFE_PLAN_TU  // not templated on the plan: defined once, in sfe_lib.cu
 // inverse pre-emphasis over a sliding window (speech2linear.py:297-344): y[n] = sum_j a^j x[n-j], j < taps;
 // then silence beyond wav_len[b] = (feat_len[b] - 1) * hop (:346-348).  pw[j] = a^j (nullptr: no filter).
 __global__ void __launch_bounds__(256) gl_finish_kernel(const float* __restrict__ x, const float* __restrict__ pw, int taps,
@@ -291,5 +296,6 @@ __global__ void __launch_bounds__(256) gl_finish_kernel(const float* __restrict_
   }
   y[i] = v;
 }
+#endif
 
 }  // namespace sfe

@@ -14,6 +14,7 @@
 #include "sfe_aux.cuh"
 #include "sfe_fused.cuh"
 #include "sfe_gl.cuh"
+#include "sfe_registry.h"
 
 using namespace sfe;
 
@@ -32,46 +33,13 @@ static int fail(int code, const std::string& msg) {
 // ---------------------------------------------------------------------------------------------
 // FFT plan registry: n_fft -> template instance
 // ---------------------------------------------------------------------------------------------
-typedef void (*fused_fn)(const FwdParams);
-
-typedef void (*gl_fn)(const GlParams);
-struct FftEntry {
-  int n_fft, win;  // win == 0: any window length (run-time tests)
-  int M, G, R1, R2, R3, MP, C;
-  fused_fn fn[2];  // [0] no pre-emphasis, [1] pre-emphasis applied while loading
-  gl_fn gl_stft, gl_istft;  // Griffin-Lim transforms (generic-window entries only)
-};
-
-template <int M, int G, int R1, int R2, int R3, int PADQ = R1, int WIN = 0>
-static FftEntry make_entry() {
-  typedef FftPlan<M, G, R1, R2, R3, PADQ, WIN> PL;
-  FftEntry e{2 * M, WIN, M, G, R1, R2, R3, PL::MP, PL::C, {&fused_frontend_kernel<PL, false>, &fused_frontend_kernel<PL, true>},
-             nullptr, nullptr};
-  if constexpr (WIN == 0) {
-    e.gl_stft = &gl_stft_kernel<PL>;
-    e.gl_istft = &gl_istft_kernel<PL>;
-  }
-  return e;
-}
-
+// (the kernel instances live in sfe_plans.cu, one translation unit per FFT plan so they compile in parallel)
 static const std::vector<FftEntry>& registry() {
-  static const std::vector<FftEntry> r = {
-      make_entry<64, 16, 8, 8, 1>(),      // n_fft 128
-      make_entry<100, 16, 4, 5, 5>(),     // n_fft 200
-      make_entry<128, 16, 8, 16, 1>(),    // n_fft 256
-      make_entry<160, 16, 8, 5, 4>(),     // n_fft 320  (20 ms @ 16 kHz)
-      make_entry<200, 16, 8, 5, 5>(),     // n_fft 400  (25 ms @ 16 kHz: the ASR recipes' default)
-      make_entry<240, 16, 16, 5, 3>(),    // n_fft 480
-      make_entry<256, 16, 16, 16, 1>(),   // n_fft 512
-      make_entry<320, 32, 16, 5, 4>(),    // n_fft 640
-      make_entry<400, 32, 16, 5, 5>(),    // n_fft 800
-      make_entry<512, 32, 4, 8, 16, 16>(),  // n_fft 1024 (TTS recipes): last radix-16 pass stays in registers
-      make_entry<1024, 32, 16, 8, 8>(),   // n_fft 2048
-      // window length fixed at compile time for the (n_fft, win_length) pairs of the shipped recipes
-      make_entry<200, 16, 8, 5, 5, 8, 400>(),      // 25 ms window @16 kHz, n_fft = win (ASR recipe default)
-      make_entry<256, 16, 16, 16, 1, 16, 400>(),   // 25 ms window @16 kHz in a 512-point FFT (BASELINE C1/C2)
-      make_entry<512, 32, 4, 8, 16, 16, 1024>(),   // 1024/1024 (TTS recipes, BASELINE C3)
-  };
+  static const std::vector<FftEntry> r = [] {
+    std::vector<FftEntry> v;
+    for (int i = 0; i < kNumPlanTus; ++i) v.push_back(kPlanTus[i]());
+    return v;
+  }();
   return r;
 }
 
