@@ -25,9 +25,10 @@ struct GlParams {
   const float* tables;
   int tab_floats;
   int o_win, o_tw2, o_tw3, o_wpost;
-  // Griffin-Lim tables: [ones (n_fft * 3 / 2 + 8) | synthesis window / n_fft (n_fft) | window^2 (n_fft)]
+  // Griffin-Lim tables: [ones (n_fft * 3 / 2 + 8) | synthesis window / n_fft (n_fft) | window^2 (n_fft) |
+  //                       inverse pre-emphasis taps | analysis window x 1/2 centred in n_fft (n_fft)]
   const float* gl_tab;
-  int o_ones, o_synth, o_wsq;
+  int o_ones, o_synth, o_wsq, o_awin;
   // data
   const float* wav;     // (B, L)
   const float* mag;     // (B, F, K)
@@ -166,12 +167,14 @@ __global__ void __launch_bounds__(GL_THREADS) gl_stft_kernel(const __grid_consta
   float *stage_w, *stage_g;
   gl_setup<PL>(p, smem, g, l, Zw, stage_w, stage_g);
   const float* tab = reinterpret_cast<const float*>(smem);
-  const float* wtab = tab + p.o_win;
+  // Phase matters here (unlike the frontend, whose window sits at [0, win) of the FFT buffer): the window is
+  // centred in n_fft like torch.stft does, so the frame is n_fft samples starting at t*hop - n_fft/2.
+  const float* wtab = p.gl_tab + p.o_awin;
   const cpx* tw2 = reinterpret_cast<const cpx*>(tab + p.o_tw2);
   const cpx* tw3 = reinterpret_cast<const cpx*>(tab + p.o_tw3);
   const cpx* wpost = reinterpret_cast<const cpx*>(tab + p.o_wpost);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int lead = (p.n_fft - p.win) / 2 - p.n_fft / 2;  // first window sample of frame t sits at t*hop + lead
+  const int lp = (p.n_fft - p.win) / 2;
 
   for (long long f0 = (static_cast<long long>(blockIdx.x) * GL_WARPS + warp) * C; f0 < p.n_frames;
        f0 += static_cast<long long>(gridDim.x) * GL_WARPS * C) {
@@ -183,19 +186,19 @@ __global__ void __launch_bounds__(GL_THREADS) gl_stft_kernel(const __grid_consta
       if (fi < p.n_frames) {
         const long long b = fi / p.F, t = fi - b * p.F;
         const float* row = p.wav + b * p.L;
-        const long long base = t * p.hop + lead;
-        for (int j = lane; j < p.win; j += 32) {
+        const long long base = t * p.hop - p.n_fft / 2;
+        for (int j = lane; j < p.n_fft; j += 32) {
           long long o = base + j;
           if (o < 0) o = -o;
           if (o >= p.L) o = 2 * (p.L - 1) - o;
-          st[j] = __ldg(row + o);
+          st[j] = (j >= lp && j < lp + p.win) ? __ldg(row + o) : 0.f;
         }
       } else {
-        for (int j = lane; j < p.win; j += 32) st[j] = 0.f;
+        for (int j = lane; j < p.n_fft; j += 32) st[j] = 0.f;
       }
     }
     __syncwarp();
-    fft_frame<PL, true, false>(Zw, tw2, tw3, l, stage_g, wtab, p.win, 0.f);
+    fft_frame<PL, true, false>(Zw, tw2, tw3, l, stage_g, wtab, p.n_fft, 0.f);
 
     // real-FFT unpack exactly as in the frontend kernel: X[k] = E + W^k O, X[M-k] = conj(E - W^k O)
     constexpr int RL = PL::RL;

@@ -60,7 +60,7 @@ struct sfe_plan {
   // Griffin-Lim (built on first use)
   std::vector<float> h_window;  // the caller's window (win_length floats)
   float* d_gl = nullptr;        // [ones | synthesis window / n_fft | window^2 | inverse pre-emphasis taps]
-  int gl_o_synth = 0, gl_o_wsq = 0, gl_o_pw = 0, gl_taps = -1;
+  int gl_o_synth = 0, gl_o_wsq = 0, gl_o_pw = 0, gl_o_awin = 0, gl_taps = -1;
 };
 
 extern "C" int sfe_abi_version(void) { return SFE_ABI_VERSION; }
@@ -781,6 +781,9 @@ extern "C" int sfe_griffinlim(sfe_plan* pl, const float* spec_in, const int64_t*
     for (int j = 0; j < n_fft; ++j) t.push_back((j >= lp && j < lp + win) ? pl->h_window[j - lp] * pl->h_window[j - lp] : 0.f);
     pl->gl_o_pw = static_cast<int>(t.size());
     for (int j = 0; j < inv_preemph_taps; ++j) t.push_back(powf(pl->cfg.preemphasis, static_cast<float>(j)));
+    while (t.size() % 4) t.push_back(0.f);
+    pl->gl_o_awin = static_cast<int>(t.size());  // analysis window x 1/2 at its centred position (phase matters here)
+    for (int j = 0; j < n_fft; ++j) t.push_back((j >= lp && j < lp + win) ? 0.5f * pl->h_window[j - lp] : 0.f);
     if (pl->d_gl) {
       SFE_CUDA(cudaStreamSynchronize(st));
       SFE_CUDA(cudaFree(pl->d_gl));
@@ -809,7 +812,7 @@ extern "C" int sfe_griffinlim(sfe_plan* pl, const float* spec_in, const int64_t*
   P.tab_floats = pl->proto.o_mtab;  // window, Stockham twiddles, unpack twiddles (everything before the mel tables)
   P.o_win = pl->proto.o_win; P.o_tw2 = pl->proto.o_tw2; P.o_tw3 = pl->proto.o_tw3; P.o_wpost = pl->proto.o_wpost;
   P.gl_tab = pl->d_gl;
-  P.o_ones = 0; P.o_synth = pl->gl_o_synth; P.o_wsq = pl->gl_o_wsq;
+  P.o_ones = 0; P.o_synth = pl->gl_o_synth; P.o_wsq = pl->gl_o_wsq; P.o_awin = pl->gl_o_awin;
   P.wav = tmp; P.mag = mag; P.tprev = tprev; P.spec = spec; P.frames = frames;
   P.momentum = momentum / (1.f + momentum);
   P.stage_floats = ones_floats;
