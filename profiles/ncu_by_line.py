@@ -15,8 +15,12 @@ rep, so, ksub = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)
-cubin = glob.glob(os.path.join(tmp, "*.cubin"))[0]
-dis = subprocess.run(["nvdisasm", "--print-line-info", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
+dis = []
+for cubin in sorted(glob.glob(os.path.join(tmp, "*.cubin"))):  # one cubin per translation unit
+    out = subprocess.run(["nvdisasm", "--print-line-info", "-c", cubin], capture_output=True, text=True).stdout
+    if ksub in out:
+        dis = out.splitlines()
+        break
 # collect (instruction order -> source line) for the wanted function
 lines, cur_line, infn = [], None, False
 for ln in dis:

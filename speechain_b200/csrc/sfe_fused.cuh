@@ -1,17 +1,19 @@
 // Fused waveform -> (log-)mel / linear spectrogram kernel for sm_100a.
 //
-// One persistent CTA per resident slot.  A CTA repeatedly claims a *tile* of TILE_F consecutive
-// frames of one utterance (dynamic atomic scheduler, claimed one tile ahead), stages the
-// (TILE_F-1)*hop + n_fft samples the tile touches into shared memory with ONE 1-D bulk async copy
-// (cp.async.bulk -> UBLKCP, completion on an mbarrier; double buffered, so the copy of tile i+1
-// runs under the arithmetic of tile i) — every sample is read from HBM once although it belongs
-// to win/hop frames — and then each warp turns two frames into features:
+// Every WARP runs its own pipeline; there is no CTA-wide barrier after the one-time setup.  The work is cut
+// into *units* of FPW = 2 consecutive frames of one utterance.  The units of the batch (utterance major;
+// units that hold only frames past an utterance's length are either skipped or cost 1/8 of a real one) are
+// split into equal-cost contiguous ranges, one per resident warp — no scheduler state, no atomics.  A warp
 //
-//   window (+ pre-emphasis on the fly)  ->  real FFT as an n_fft/2-point complex Stockham FFT
-//   (radix 16/8/5/4/3/2 butterflies in registers, passes exchanged through a warp-private,
-//   padded shared-memory buffer)  ->  real-FFT unpack + |X|^2  ->  banded (sparse) mel filter
-//   ->  clamp/log  ->  [global (x-mean)/std]  ->  [SpecAugment masks]  ->  coalesced stores,
-//   plus fp64 per-utterance sum / sum-of-squares accumulation for the normaliser.
+//   stages the hop + win samples its unit touches into a warp-private shared-memory buffer with ONE 1-D bulk
+//   async copy (cp.async.bulk -> UBLKCP, completion on a warp-private mbarrier); the copy of unit i+1 is
+//   issued as soon as the first FFT pass of unit i has consumed the buffer, so it flies under the rest of
+//   unit i.  Neighbouring units overlap by win - hop samples: those re-reads hit L2, HBM is read once.
+//   -> window (+ pre-emphasis on the fly) -> real FFT as an n_fft/2-point complex Stockham FFT (radix
+//   16/8/5/4/3/2 butterflies in registers, passes exchanged through a warp-private padded shared buffer)
+//   -> real-FFT unpack + |X|^2 -> banded (sparse) mel filter -> clamp/log -> [global (x-mean)/std]
+//   -> [SpecAugment masks] -> coalesced stores, plus exact fixed-point per-utterance sum / sum-of-squares
+//   accumulation for the normaliser in warp-private shared memory (flushed when the utterance changes).
 //
 // Reference arithmetic replaced: speechain/module/frontend/speech2linear.py:165-245,
 // linear2mel.py:177-187 (see include/sfe.h).
@@ -23,15 +25,21 @@
 
 #include "sfe_fft.cuh"
 
+// Timing experiments only (tools/variant.py): SFE_ABLATE=1 no mel stage, 2 no unpack either, 3 first FFT pass only,
+// 4 staging only.  Never defined in the shipped build.
+#ifndef SFE_ABLATE
+#define SFE_ABLATE 0
+#endif
+
 namespace sfe {
 
-constexpr int NWARPS = 8;
+constexpr int NWARPS = 8;                 // warps per CTA of the small standalone kernels
 constexpr int NTHREADS = NWARPS * 32;
-constexpr int FPW = 2;                    // frames per warp per tile
-constexpr int TILE_F = NWARPS * FPW;      // frames per tile
+constexpr int FPW = 2;                    // frames per unit (per warp step)
 constexpr int MAX_MEL_ROUNDS = 16;        // phases of 32 filter units (n_mels <= 256)
-constexpr int NSTAGE = 2;                 // staging buffers
 constexpr int MASK_INLINE_MAX = 768;      // SFE_MASK_INLINE_MAX
+constexpr int UNIT_TABLE_MAX_B = 256;     // batches up to this size get a per-utterance cost table
+constexpr int REAL_UNIT_COST = 8;         // a unit with real frames costs this many pad-only units
 
 // SpecAugment interval descriptors: device arrays, or (small batches) carried in the parameter block
 struct MaskDesc {
@@ -53,8 +61,7 @@ struct FwdParams {
   int B;
   long long T_max;
   int F;
-  int tiles_per_utt;
-  int num_tiles;
+  int units_per_utt;       // ceil(F / FPW)
   // outputs
   float* mel;
   float* lin;
@@ -86,10 +93,9 @@ struct FwdParams {
   int2 mel_ph[MAX_MEL_ROUNDS];                       // per phase: {pairs of taps, float2 offset of its weights}
   unsigned int mel_split_mask;                       // phases that hold bins split over two lanes
   int mel_tail;                                      // max taps of any phase (P2 tail padding)
-  int sm_stage, sm_stage_floats, sm_warp, sm_warp_bytes, sm_p2_off, sm_acc, sm_bar;
-  int nstage;  // 2: the bulk copy of tile i+1 runs under tile i; 1 (large n_fft): copy at the tile's own turn
-  // scheduler
-  unsigned int* sched;  // [0] next tile, [1] CTAs done
+  // per-CTA: [tables | table mbarrier | warp 0 | warp 1 | ...]; per warp: [FFT scratch (P2 may alias it) | P2 |
+  // staging | sums | mbarrier]
+  int sm_tbar, sm_warp, sm_warp_bytes, sm_p2_off, sm_stage_off, sm_acc_off, sm_bar_off;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -142,7 +148,8 @@ struct FftPlan {
   static constexpr int MP = M_ + M_ / PADQ_ + 1;
   // the power spectrum may overwrite the FFT scratch only if no later FFT of the tile needs it
   static constexpr bool ALIAS_P2 = (S == 1);
-  static constexpr int MINB = (M_ == 256 || M_ == 240) ? 3 : ((M_ <= 512) ? 2 : 1);  // resident CTAs per SM aimed for
+  // one CTA per SM; warps per CTA at most (the register budget per thread follows: 85 / 128 / 255)
+  static constexpr int MAXW = (M_ <= 256) ? 24 : ((M_ <= 512) ? 16 : 8);
   static constexpr int RL = (R3_ > 1) ? R3_ : R2_;               // radix of the last pass
   // the last pass leaves Z[l + G*r] in register r of lane l: the real-FFT unpack then pairs k with M-k
   // by one shuffle instead of a shared-memory round trip
@@ -304,15 +311,18 @@ __device__ __forceinline__ void fft_frame(cpx* Zw, const cpx* tw2, const cpx* tw
   }
 }
 
-// per-tile metadata published by thread 0 one tile ahead
-struct TileInfo {
-  int tile;    // >= num_tiles: no more work
-  int kind;    // 0 pad tile, 1 interior (bulk copy in flight / landed), 2 edge (gather at its turn)
-  int shift;   // staging index of the first sample of frame t0 (interior tiles)
-  int b, t0, flen;
-  long long len;
-};
-enum { TILE_PAD = 0, TILE_BULK = 1, TILE_EDGE = 2 };
+// the passes after the first one (the staging buffer is free again once the first pass has returned)
+template <class PL>
+__device__ __forceinline__ void fft_rest(cpx* Zw, const cpx* tw2, const cpx* tw3, int l) {
+  if (PL::R3 > 1) {
+    stockham_pass<PL, PL::R2, PL::R1, false, false, false>(Zw, tw2, l, nullptr, nullptr, 0, 0.f);
+    if (!PL::LASTREG)
+      stockham_pass<PL, (PL::R3 > 1 ? PL::R3 : 2), PL::R1 * PL::R2, false, false, false>(Zw, tw3, l, nullptr, nullptr,
+                                                                                         0, 0.f);
+  } else if (!PL::LASTREG) {
+    stockham_pass<PL, PL::R2, PL::R1, false, false, false>(Zw, tw2, l, nullptr, nullptr, 0, 0.f);
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // the kernel
@@ -329,7 +339,7 @@ __device__ __forceinline__ float fast_log(float x, float clampv, float lmul) {
 }
 
 template <class PL, bool PRE>
-__global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(const __grid_constant__ FwdParams p) {
+__global__ void __launch_bounds__(PL::MAXW * 32, 1) fused_frontend_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int M = PL::M, G = PL::G, Q = PL::PADQ;
   // magnitude spectra (mag_spec, no shipped recipe): sqrt in one sweep after the unpack where the spectrum
@@ -341,57 +351,66 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
   float* tab = reinterpret_cast<float*>(smem);
   unsigned char* wbase = smem + p.sm_warp + warp * p.sm_warp_bytes;
   cpx* Zw = reinterpret_cast<cpx*>(wbase) + g * PL::MP;
-  float* P2 = reinterpret_cast<float*>(wbase + p.sm_p2_off);    // [k][FPW] interleaved
-  unsigned long long* barp = reinterpret_cast<unsigned long long*>(smem + p.sm_bar);
-  __shared__ TileInfo s_info[NSTAGE];
-  constexpr int COMPACT_MAX_B = 256;
-  __shared__ int s_cum[COMPACT_MAX_B + 1];  // compact mode: first tile index of every utterance
-  __shared__ int s_ntiles;
+  float* P2 = reinterpret_cast<float*>(wbase + p.sm_p2_off);          // [k][FPW] interleaved
+  float* stage = reinterpret_cast<float*>(wbase + p.sm_stage_off);    // this warp's samples
+  long long* wacc = reinterpret_cast<long long*>(wbase + p.sm_acc_off);  // [D][2] fixed-point sums of the current utterance
+  const uint32_t bar = smem_u32(wbase + p.sm_bar_off);                // this warp's copy barrier
+  const uint32_t tbar = smem_u32(smem + p.sm_tbar);                   // tables
+  __shared__ int s_cum[UNIT_TABLE_MAX_B + 1];  // cost coordinate at which every utterance starts
+  __shared__ int s_next;                       // next chunk of this CTA's range
 
-  // ---- one-time setup: mbarriers, tables -> smem with one bulk copy, zero what must be zero ----
+  const int hop = p.hop, win = p.win, D = p.D, K = p.K, F = p.F, B = p.B;
+  const int upu = p.units_per_utt;
+  // Units that hold only frames past an utterance's length have nothing to compute.  When they have nothing
+  // to write either (the normalise pass synthesises those rows) they are not enumerated at all.
+  const bool compact = p.skip_pad && !p.lin && !p.energy;
+  const bool tabled = (B <= UNIT_TABLE_MAX_B);
+  auto frames_of = [&](long long len) -> long long {
+    return (p.center ? (len + 2 * (p.n_fft / 2)) - p.n_fft : len - p.n_fft) / hop + 1;
+  };
+  auto clampF = [&](long long fl) -> int { return static_cast<int>(fl < 0 ? 0 : (fl > F ? F : fl)); };
+
+  // ---- one-time setup: barriers, tables -> smem with one bulk copy, cost table, zeroed sums ----
   // (the staging buffers need no initialisation: every read of them is either covered by a copy or
   //  replaced by a select, see the first Stockham pass)
-  const uint32_t bar0 = smem_u32(barp);
   if (tid == 0) {
-    mbar_init(bar0, 1);
-    mbar_init(bar0 + 8, 1);
-    mbar_init(bar0 + 16, 1);
+    s_next = 0;
+    mbar_init(tbar, 1);
     fence_mbar_init();
     const uint32_t bytes = static_cast<uint32_t>(p.tab_floats) * 4u;
-    mbar_expect_tx(bar0 + 16, bytes);
-    bulk_g2s(smem_u32(tab), p.tables, bytes, bar0 + 16);
+    mbar_expect_tx(tbar, bytes);
+    bulk_g2s(smem_u32(tab), p.tables, bytes, tbar);
   }
-  {
-    int* acc = reinterpret_cast<int*>(smem + p.sm_acc);
-    for (int i = tid; i < NSTAGE * 4 * p.D; i += NTHREADS) acc[i] = 0;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
   }
-  __syncthreads();               // barrier inits are visible before anyone waits on them
-  mbar_wait(bar0 + 16, 0u);      // tables have landed
-  uint32_t parity[NSTAGE] = {0u, 0u};
-
-  // Tiles that hold only frames past an utterance's length have nothing to compute.  When they have
-  // nothing to write either (the normalise pass synthesises those rows), enumerate real tiles only:
-  // tile -> (utterance, frame block) through a per-utterance prefix sum kept in shared memory.
-  const bool compact = (p.B <= COMPACT_MAX_B) && p.skip_pad && !p.lin && !p.energy;
-  if (compact) {
-    for (int b = tid; b < p.B; b += NTHREADS) {
-      const long long len = __ldg(p.len + b);
-      const long long fl = (p.center ? (len + 2 * (p.n_fft / 2)) - p.n_fft : len - p.n_fft) / p.hop + 1;
-      const long long fc = fl < 0 ? 0 : (fl > p.F ? p.F : fl);
-      s_cum[b + 1] = static_cast<int>((fc + TILE_F - 1) / TILE_F);
-      if (blockIdx.x == 0 && p.feat_len) p.feat_len[b] = fl;
+  for (int i = lane; i < 2 * D; i += 32) wacc[i] = 0;
+  if (blockIdx.x == 0 && p.feat_len)
+    for (int b = tid; b < B; b += blockDim.x) p.feat_len[b] = frames_of(__ldg(p.len + b));
+  if (tabled && warp == 0) {
+    // exclusive scan of the utterances' costs (warp shuffles, 32 utterances per round)
+    int carry = 0;
+    for (int b0 = 0; b0 < B; b0 += 32) {
+      const int b = b0 + lane;
+      int c = 0;
+      if (b < B) {
+        const int nr = (clampF(frames_of(__ldg(p.len + b))) + FPW - 1) / FPW;
+        c = REAL_UNIT_COST * nr + (compact ? 0 : upu - nr);
+      }
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (b < B) s_cum[b] = carry + incl - c;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
     }
-    __syncthreads();
-    if (tid == 0) {
-      s_cum[0] = 0;
-      for (int b = 0; b < p.B; ++b) s_cum[b + 1] += s_cum[b];
-      s_ntiles = s_cum[p.B];
-    }
-  } else if (tid == 0) {
-    s_ntiles = p.num_tiles;
+    if (lane == 0) s_cum[B] = carry;
   }
-  __syncthreads();
-  const int num_tiles = s_ntiles;
+  __syncthreads();               // barrier inits and the cost table are visible
+  mbar_wait(tbar, 0u);           // tables have landed
 
   const float* wtab = tab + p.o_win;
   const cpx* tw2 = reinterpret_cast<const cpx*>(tab + p.o_tw2);
@@ -399,97 +418,171 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
   const cpx* wpost = reinterpret_cast<const cpx*>(tab + p.o_wpost);
   const int2* mtab = reinterpret_cast<const int2*>(tab + p.o_mtab) + lane;  // {first bin, output info} per (phase, lane)
   const float2* mw2 = reinterpret_cast<const float2*>(tab + p.o_mw);
-  const int hop = p.hop, win = p.win, D = p.D, K = p.K;
   const bool base_aligned = ((reinterpret_cast<uintptr_t>(p.wav) & 15) == 0);
   const int n_fmask = p.mk.n_fmask, n_tmask = p.mk.n_tmask;
   const int* m_fpos = p.mk.inl_on ? p.mk.inl : p.mk.fpos;
-  const int* m_flen = p.mk.inl_on ? p.mk.inl + p.B * n_fmask : p.mk.flen;
-  const int* m_tpos = p.mk.inl_on ? p.mk.inl + 2 * p.B * n_fmask : p.mk.tpos;
-  const int* m_tlen = p.mk.inl_on ? p.mk.inl + 2 * p.B * n_fmask + p.B * n_tmask : p.mk.tlen;
+  const int* m_flen = p.mk.inl_on ? p.mk.inl + B * n_fmask : p.mk.flen;
+  const int* m_tpos = p.mk.inl_on ? p.mk.inl + 2 * B * n_fmask : p.mk.tpos;
+  const int* m_tlen = p.mk.inl_on ? p.mk.inl + 2 * B * n_fmask + B * n_tmask : p.mk.tlen;
   constexpr int pre1 = PRE ? 1 : 0;
-  constexpr int EDGE_SHIFT = 4;  // edge tiles leave room for the (unused) predecessor sample
+  constexpr int EDGE_SHIFT = 4;  // gathered units leave room for the (unused) predecessor sample
 
-  // thread 0: describe tile `tile`, and if it is an interior tile start its bulk copy into `buf`
-  auto publish = [&](int tile, int buf, bool start_copy) {
-    TileInfo ti;
-    ti.tile = tile;
-    ti.kind = TILE_PAD;
-    ti.shift = 0;
-    ti.b = 0; ti.t0 = 0; ti.flen = 0; ti.len = 0;
-    if (tile < num_tiles) {
-      int tb, b;
-      if (compact) {
-        // utterance major over real tiles: binary search of the prefix sums
-        int lo = 0, hi = p.B - 1;
-        while (lo < hi) {
-          const int mid = (lo + hi + 1) >> 1;
-          if (s_cum[mid] <= tile) lo = mid; else hi = mid - 1;
-        }
-        b = lo;
-        tb = tile - s_cum[b];
-      } else {
-        // frame-block major, utterance minor -> with descending lengths the cheap all-padding tiles come last
-        tb = tile / p.B;
-        b = tile - tb * p.B;
+  // ---- work distribution over the cost axis [0, ctot) ----
+  // One CTA per SM.  The axis is cut into one contiguous, equal-cost range per CTA (SMs are equally fast);
+  // inside a CTA the warps deal the range out among themselves one real unit (REAL_UNIT_COST) at a time
+  // from a shared-memory counter — a ~50-cycle atomic, no global scheduler traffic — so a warp that the
+  // hardware scheduler favours simply takes more units and the tail of an SM is one unit long.
+  const int ctot = tabled ? s_cum[B] : B * upu;
+  const int real_step = tabled ? REAL_UNIT_COST : 1;  // without the table every unit counts the same
+  const int cta_lo = static_cast<int>(static_cast<long long>(ctot) * blockIdx.x / gridDim.x);
+  const int cta_hi = static_cast<int>(static_cast<long long>(ctot) * (blockIdx.x + 1) / gridDim.x);
+  int c_hi = 0;  // end of the chunk this warp is working on
+
+  // The warp's position on the axis lives in a warp-private control block in shared memory, not in
+  // registers: it is needed only at unit boundaries, and the FFT in between has no registers to spare.
+  //   unit tu of utterance b (frames FPW*tu, FPW*tu+1) starts at cost coordinate c; the warp's chunk ends at c_hi
+  struct Ctl {
+    int b, tu, flen, nunit;   // nunit: units the utterance owns
+    int c, c_hi, live, bulk;  // bulk: a real interior unit, its samples arrive by bulk copy (else they are gathered)
+    int shift, inflight;      // staging index of the unit's first sample; its copy has been issued
+    unsigned int bytes, pad_;
+    long long len, ga;        // ga: first float of the bulk copy
+  };
+  static_assert(sizeof(Ctl) == 64, "control block layout");
+  Ctl* ctl = reinterpret_cast<Ctl*>(wbase + p.sm_bar_off + 16);
+
+  // Moves the control block to the unit this warp works on next and starts that unit's bulk copy
+  // (`first`: nothing processed yet).  All lanes compute the same values; lane 0 stores them.
+  auto advance = [&](bool first) {
+    Ctl q;
+    if (first) {
+      q.b = -1; q.tu = 0; q.flen = 0; q.nunit = 0; q.c = 0; q.c_hi = 0; q.len = 0;
+    } else {
+      q = *ctl;
+      q.c += (q.tu * FPW < q.flen) ? real_step : 1;
+      ++q.tu;
+    }
+    auto load_utt = [&]() {
+      q.len = __ldg(p.len + q.b);
+      q.flen = clampF(frames_of(q.len));
+      q.nunit = (compact && tabled) ? (q.flen + FPW - 1) / FPW : upu;
+    };
+    // step over utterances that own no unit (zero frames in compact mode) / past the end of one
+    auto settle = [&]() {
+      while (q.tu >= q.nunit && q.b + 1 < B) {
+        ++q.b;
+        q.tu = 0;
+        load_utt();
+        if (tabled) q.c = s_cum[q.b];
       }
-      const int t0 = tb * TILE_F;
-      const long long len = __ldg(p.len + b);
-      const long long fl = (p.center ? (len + 2 * (p.n_fft / 2)) - p.n_fft : len - p.n_fft) / hop + 1;
-      const int flen = static_cast<int>(fl < 0 ? 0 : (fl > p.F ? p.F : fl));
-      if (t0 == 0 && p.feat_len && !compact) p.feat_len[b] = fl;
-      ti.b = b; ti.t0 = t0; ti.flen = flen; ti.len = len;
-      if (t0 < flen) {
-        const long long o_start = static_cast<long long>(t0) * hop + p.off;
-        const long long o_end = o_start + static_cast<long long>(TILE_F - 1) * hop + win;
-        const long long gi = static_cast<long long>(b) * p.pitch + o_start - pre1;
-        const long long ga = gi & ~3LL;
-        const long long ge = (static_cast<long long>(b) * p.pitch + o_end + 3) & ~3LL;
-        const bool interior = base_aligned && (o_start - pre1 >= 0) && (o_end <= len) && (ge <= p.total_floats);
-        if (interior) {
-          ti.kind = TILE_BULK;
-          ti.shift = static_cast<int>(gi - ga) + pre1;
-          if (start_copy) {
-            const uint32_t bytes = static_cast<uint32_t>((ge - ga) * 4);
-            const uint32_t bar = bar0 + 8 * buf;
-            fence_proxy_async();
-            mbar_expect_tx(bar, bytes);
-            bulk_g2s(smem_u32(smem + p.sm_stage + buf * p.sm_stage_floats * 4), p.wav + ga, bytes, bar);
+    };
+    if (!first) settle();
+    // `q` is the first unit at or after the end of the current chunk: take chunks from the CTA's counter
+    // until `q` lies inside one; the CTA's range may run out first
+    q.live = 1;
+    while (first || !(q.tu < q.nunit && q.c < q.c_hi)) {
+      int k = 0;
+      if (lane == 0) k = atomicAdd(&s_next, 1);
+      k = __shfl_sync(0xffffffffu, k, 0);
+      const long long lo64 = static_cast<long long>(cta_lo) + static_cast<long long>(k) * real_step;
+      if (lo64 >= cta_hi) { q.live = 0; break; }
+      const int c0 = static_cast<int>(lo64);
+      q.c_hi = min(c0 + real_step, cta_hi);
+      // chunks only move forward: either `q` is still the first unit at or after c0, or it lies before it
+      if (first || (q.tu < q.nunit && q.c < c0)) {
+        // first unit whose start coordinate is >= c0; q.b is -1 or an utterance that starts at or before c0
+        if (tabled) {
+          int lo = q.b < 0 ? 0 : q.b;
+          if (lo + 1 < B && s_cum[lo + 1] <= c0) {  // (usually still the same utterance)
+            int hi = B - 1;  // last utterance that starts at or before c0
+            ++lo;
+            while (lo < hi) {
+              const int mid = (lo + hi + 1) >> 1;
+              if (s_cum[mid] <= c0) lo = mid; else hi = mid - 1;
+            }
+          }
+          if (lo != q.b) {
+            q.b = lo;
+            load_utt();
+          }
+          const int nreal = (q.flen + FPW - 1) / FPW;
+          const int off = c0 - s_cum[q.b];
+          const int real_cost = REAL_UNIT_COST * nreal;
+          if (off <= real_cost) {
+            q.tu = (off + REAL_UNIT_COST - 1) / REAL_UNIT_COST;
+            q.c = s_cum[q.b] + q.tu * REAL_UNIT_COST;
+          } else {
+            q.tu = nreal + (off - real_cost);
+            q.c = c0;
           }
         } else {
-          ti.kind = TILE_EDGE;
+          int nb = c0 / upu;
+          if (nb >= B) nb = B - 1;
+          q.tu = c0 - nb * upu;
+          q.c = c0;
+          if (nb != q.b) {
+            q.b = nb;
+            load_utt();
+          }
         }
+        settle();
+      }
+      first = false;
+    }
+    // where the unit's samples come from
+    q.bulk = 0; q.inflight = 0; q.shift = 0; q.bytes = 0; q.ga = 0; q.pad_ = 0;
+    if (q.live && q.tu * FPW < q.flen) {
+      const long long o_start = static_cast<long long>(q.tu) * FPW * hop + p.off;
+      const long long o_end = o_start + static_cast<long long>(FPW - 1) * hop + win;
+      const long long row0 = static_cast<long long>(q.b) * p.pitch;
+      const long long gi = row0 + o_start - pre1;
+      q.ga = gi & ~3LL;
+      const long long ge = (row0 + o_end + 3) & ~3LL;
+      q.bulk = (base_aligned && (o_start - pre1 >= 0) && (o_end <= q.len) && (ge <= p.total_floats)) ? 1 : 0;
+      q.shift = static_cast<int>(gi - q.ga) + pre1;
+      q.bytes = static_cast<uint32_t>((ge - q.ga) * 4);
+      q.inflight = q.bulk;
+    }
+    __syncwarp();  // every lane has read the old block
+    if (lane == 0) {
+      *ctl = q;
+      if (q.bulk) {  // the staging buffer is free (see the call sites): start the copy right away
+        fence_proxy_async();
+        mbar_expect_tx(bar, q.bytes);
+        bulk_g2s(smem_u32(stage), p.wav + q.ga, q.bytes, bar);
       }
     }
-    s_info[buf] = ti;
+    __syncwarp();
+  };
+  auto flush_sums = [&](int bb) {
+    __syncwarp();
+    for (int i = lane; i < 2 * D; i += 32) {
+      const long long v = wacc[i];
+      if (v != 0) {
+        wacc[i] = 0;
+        atomicAdd(p.stats + static_cast<long long>(bb) * D * 2 + i, static_cast<unsigned long long>(v));
+      }
+    }
+    __syncwarp();
   };
 
-  // prologue: claim this CTA's first tile and start its copy
-  unsigned int claimed = 0;  // (thread 0) tile claimed for the next iteration
-  __syncthreads();
-  if (tid == 0) publish(static_cast<int>(atomicAdd(p.sched, 1u)), 0, true);
-  __syncthreads();
+  advance(true);
+  uint32_t parity = 0u;
 
-  for (int it = 0;; ++it) {
-    const int buf = it & 1;
-    const TileInfo ti = s_info[buf];
-    if (ti.tile >= num_tiles) break;
-    // thread 0 claims the next tile now; the answer is consumed in the middle of this tile, where the
-    // next tile is described and its bulk copy started (its staging buffer was released by the barrier
-    // that ended the previous iteration).  Claiming exactly one tile ahead keeps the tail short: a CTA
-    // never sits on more than one tile that an idle CTA could have taken.
-    if (tid == 0) claimed = atomicAdd(p.sched, 1u);
-    const int b = ti.b, t0 = ti.t0, flen = ti.flen;
-    const long long len = ti.len;
-    const int nfr = min(TILE_F, p.F - t0);  // frames of this tile that exist in the output
-    const int sbuf = (p.nstage == 2) ? buf : 0;
-    float* stage = reinterpret_cast<float*>(smem + p.sm_stage) + sbuf * p.sm_stage_floats;
+  while (true) {
+    // the unit being processed (the control block itself moves on in the middle of it)
+    if (!ctl->live) break;
+    const int b = ctl->b, flen = ctl->flen;
+    const int tA = ctl->tu * FPW;
+    const bool real = (tA < flen);
 
-    if (ti.kind == TILE_PAD) {
-      // ---------------- pad tile: nothing to transform ----------------
+    if (!real) {
+      // ---------------- pad unit: nothing to transform ----------------
+      const int nfr = min(FPW, F - tA);
       if (p.mel && !p.skip_pad) {
-        float* dst = p.mel + (static_cast<long long>(b) * p.F + t0) * D;
+        float* dst = p.mel + (static_cast<long long>(b) * F + tA) * D;
         const float fillv = p.fill_dev ? *p.fill_dev : p.fill;
-        for (int i = tid; i < nfr * D; i += NTHREADS) {
+        for (int i = lane; i < nfr * D; i += 32) {
           const int d = i % D;
           float v = p.pad_mel;
           if (p.norm_mean) v -= p.norm_mean[d];
@@ -503,308 +596,281 @@ __global__ void __launch_bounds__(NTHREADS, PL::MINB) fused_frontend_kernel(cons
         }
       }
       if (p.lin) {
-        float* dst = p.lin + (static_cast<long long>(b) * p.F + t0) * K;
-        for (int i = tid; i < nfr * K; i += NTHREADS) dst[i] = p.pad_lin;
+        float* dst = p.lin + (static_cast<long long>(b) * F + tA) * K;
+        for (int i = lane; i < nfr * K; i += 32) dst[i] = p.pad_lin;
       }
-      if (p.energy) {
-        for (int i = tid; i < nfr; i += NTHREADS) p.energy[static_cast<long long>(b) * p.F + t0 + i] = 0.f;
-      }
-      if (tid == 0) publish(static_cast<int>(claimed), buf ^ 1, p.nstage == 2);
-      __syncthreads();
-      continue;
-    }
-
-    // ---------------- samples of this tile ----------------
-    const int shift = (ti.kind == TILE_BULK) ? ti.shift : EDGE_SHIFT;
-    const bool staged_raw = (ti.kind == TILE_BULK);
-    if (staged_raw) {
-      if (p.nstage == 1 && it > 0 && tid == 0) {
-        // single staging buffer: the copy could not start before the previous tile released it
-        const long long o_start = static_cast<long long>(t0) * hop + p.off;
-        const long long o_end = o_start + static_cast<long long>(TILE_F - 1) * hop + win;
-        const long long gi = static_cast<long long>(b) * p.pitch + o_start - pre1;
-        const long long ga = gi & ~3LL;
-        const long long ge = (static_cast<long long>(b) * p.pitch + o_end + 3) & ~3LL;
-        const uint32_t bytes = static_cast<uint32_t>((ge - ga) * 4);
-        fence_proxy_async();
-        mbar_expect_tx(bar0, bytes);
-        bulk_g2s(smem_u32(stage), p.wav + ga, bytes, bar0);
-      }
-      mbar_wait(bar0 + 8 * sbuf, parity[sbuf]);
-      parity[sbuf] ^= 1u;
+      if (p.energy && lane < nfr) p.energy[static_cast<long long>(b) * F + tA + lane] = 0.f;
+      advance(false);
     } else {
-      // edge tile: explicit gather with batch-level reflection, zero beyond the length and
-      // pre-emphasis applied here (staging then holds the final samples)
-      const long long o_start = static_cast<long long>(t0) * hop + p.off;
-      const float* row = p.wav + static_cast<long long>(b) * p.pitch;
-      const int n = (TILE_F - 1) * hop + win;
-      // eight independent loads (sixteen with pre-emphasis) in flight per thread: the gather is pure latency
-      for (int i0 = tid; i0 < n; i0 += NTHREADS * 8) {
-        float v[8], pv[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int i = i0 + u * NTHREADS;
-          long long o = o_start + i;
-          if (p.center) {
-            if (o < 0) o = -o;
-            if (o >= p.T_max) o = 2 * (p.T_max - 1) - o;
-          }
-          const bool ok = (i < n) && (o >= 0) && (o < len);
-          v[u] = ok ? __ldg(row + o) : 0.f;
-          pv[u] = (ok && p.has_pre && o > 0) ? __ldg(row + o - 1) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int i = i0 + u * NTHREADS;
-          if (i < n) stage[EDGE_SHIFT + i] = fmaf(-p.pre, pv[u], v[u]);
-        }
-      }
-      if (tid == 0) stage[EDGE_SHIFT - 1] = 0.f;  // read (times a zero coefficient) as the predecessor of sample 0
-      __syncthreads();
-    }
-
-    // ---------------- per-warp: FFT + |X|^2 of FPW frames ----------------
-    float esum[PL::S];
-#pragma unroll
-    for (int sub = 0; sub < PL::S; ++sub) {
-      const int slot = sub * PL::C + g;
-      const int tl = warp * FPW + slot;   // frame index inside the tile
-      const int t = t0 + tl;
-      const int fo = tl * hop + shift;
-      const float* fr = stage + fo;
-      // edge tiles were pre-emphasised by the gather: same code path with a zero coefficient
-      const float pre = (PRE && staged_raw) ? p.pre : 0.f;
-      if ((fo & 1) == 0) fft_frame<PL, true, PRE>(Zw, tw2, tw3, l, fr, wtab, win, pre);
-      else fft_frame<PL, false, PRE>(Zw, tw2, tw3, l, fr, wtab, win, pre);
-
-      // real-FFT unpack: X[k] = E + W^k O, X[M-k] = conj(E - W^k O); the 1/2 lives in the window.
-      // Lane l owns k = l + G*i (i <= NI-1) and its mirror M-k.
-      constexpr int RL = PL::RL;
-      constexpr int NI = PL::LASTREG ? (RL / 2 + 1) : ((M / 2) / G + 1);
-      cpx za[NI], zb[NI];
-      if constexpr (PL::LASTREG) {
-        cpx u[RL];
-        stockham_last_reg<PL, RL, M / RL>(Zw, (PL::R3 > 1) ? tw3 : tw2, l, u);
-        const int src = (G - l) & (G - 1);
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {
-          za[i] = u[i];
-          const float bx = __shfl_sync(0xffffffffu, u[RL - 1 - i].x, src, G);
-          const float by = __shfl_sync(0xffffffffu, u[RL - 1 - i].y, src, G);
-          zb[i] = (l == 0) ? u[(RL - i) % RL] : make_float2(bx, by);
-        }
-        // (the shuffles are convergence points: every lane has finished reading the scratch)
+      // ---------------- samples of this unit ----------------
+      const bool staged_raw = (ctl->bulk != 0);
+      const int shift = staged_raw ? ctl->shift : EDGE_SHIFT;
+      if (staged_raw) {
+        mbar_wait(bar, parity);   // (the copy was started when the control block moved here)
+        parity ^= 1u;
       } else {
-        const cpx* zl = Zw + padidx<Q>(l);
+        // edge unit: explicit gather with batch-level reflection, zero beyond the length and
+        // pre-emphasis applied here (staging then holds the final samples)
+        const long long len = ctl->len;
+        const long long o_start = static_cast<long long>(tA) * hop + p.off;
+        const float* row = p.wav + static_cast<long long>(b) * p.pitch;
+        const int n = (FPW - 1) * hop + win;
+        for (int i0 = lane; i0 < n; i0 += 32 * 4) {
+          float v[4], pv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 32;
+            long long o = o_start + i;
+            if (p.center) {
+              if (o < 0) o = -o;
+              if (o >= p.T_max) o = 2 * (p.T_max - 1) - o;
+            }
+            const bool ok = (i < n) && (o >= 0) && (o < len);
+            v[u] = ok ? __ldg(row + o) : 0.f;
+            pv[u] = (ok && p.has_pre && o > 0) ? __ldg(row + o - 1) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 32;
+            if (i < n) stage[EDGE_SHIFT + i] = fmaf(-p.pre, pv[u], v[u]);
+          }
+        }
+        if (lane == 0) stage[EDGE_SHIFT - 1] = 0.f;  // read (times a zero coefficient) as the predecessor of sample 0
+        __syncwarp();
+      }
+
+      // the unit after this one is found, and its copy started, as soon as the staging buffer is free
+      auto prefetch_next = [&]() { advance(false); };
+
+      // ---------------- FFT + |X|^2 of FPW frames ----------------
+      float esum[PL::S];
+#pragma unroll
+      for (int sub = 0; sub < ((SFE_ABLATE >= 4) ? 0 : PL::S); ++sub) {
+        const int slot = sub * PL::C + g;   // frame index inside the unit
+        const int t = tA + slot;
+        const int fo = slot * hop + shift;
+        const float* fr = stage + fo;
+        // gathered units were pre-emphasised by the gather: same code path with a zero coefficient
+        const float pre = (PRE && staged_raw) ? p.pre : 0.f;
+        if ((fo & 1) == 0) stockham_pass<PL, PL::R1, 1, true, true, PRE>(Zw, nullptr, l, fr, wtab, win, pre);
+        else stockham_pass<PL, PL::R1, 1, true, false, PRE>(Zw, nullptr, l, fr, wtab, win, pre);
+        // (the pass ends with a __syncwarp: every lane has consumed its samples)
+        if (sub == PL::S - 1) prefetch_next();
+        if (SFE_ABLATE >= 3) { esum[sub] = 0.f; continue; }
+        fft_rest<PL>(Zw, tw2, tw3, l);
+
+        // real-FFT unpack: X[k] = E + W^k O, X[M-k] = conj(E - W^k O); the 1/2 lives in the window.
+        // Lane l owns k = l + G*i (i <= NI-1) and its mirror M-k.
+        constexpr int RL = PL::RL;
+        constexpr int NI = PL::LASTREG ? (RL / 2 + 1) : ((M / 2) / G + 1);
+        cpx za[NI], zb[NI];
+        if constexpr (PL::LASTREG) {
+          cpx u[RL];
+          stockham_last_reg<PL, RL, M / RL>(Zw, (PL::R3 > 1) ? tw3 : tw2, l, u);
+          if (SFE_ABLATE == 2) {
+            float a = 0.f;
+#pragma unroll
+            for (int i = 0; i < RL; ++i) a += u[i].x + u[i].y;
+            __syncwarp();
+            P2[l * FPW + slot] = a;
+            esum[sub] = 0.f;
+            __syncwarp();
+            continue;
+          }
+          const int src = (G - l) & (G - 1);
+#pragma unroll
+          for (int i = 0; i < NI; ++i) {
+            za[i] = u[i];
+            const float bx = __shfl_sync(0xffffffffu, u[RL - 1 - i].x, src, G);
+            const float by = __shfl_sync(0xffffffffu, u[RL - 1 - i].y, src, G);
+            zb[i] = (l == 0) ? u[(RL - i) % RL] : make_float2(bx, by);
+          }
+          // (the shuffles are convergence points: every lane has finished reading the scratch)
+        } else {
+          const cpx* zl = Zw + padidx<Q>(l);
+#pragma unroll
+          for (int i = 0; i < NI; ++i) {
+            const int k = l + i * G;
+            if (i < NI - 1 || k <= M / 2) {
+              za[i] = (G % Q == 0) ? zl[i * (G + G / Q)] : Zw[padidx<Q>(k)];
+              zb[i] = Zw[padidx<Q>(k == 0 ? 0 : M - k)];
+            }
+          }
+          if (PL::ALIAS_P2) __syncwarp();  // every lane has its Z values: the buffer may now hold P2
+        }
+        float es = 0.f;
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
           const int k = l + i * G;
           if (i < NI - 1 || k <= M / 2) {
-            za[i] = (G % Q == 0) ? zl[i * (G + G / Q)] : Zw[padidx<Q>(k)];
-            zb[i] = Zw[padidx<Q>(k == 0 ? 0 : M - k)];
+            const cpx a = za[i], bb = zb[i];
+            const cpx w = wpost[k];
+            const cpx E = f2add(a, make_float2(bb.x, -bb.y));
+            const cpx O = f2add(make_float2(a.y, -a.x), make_float2(bb.y, bb.x));
+            const cpx Tt = cmul(O, w);
+            const cpx X = f2add(E, Tt), Y = f2sub(E, Tt);
+            float pk = fmaf(X.x, X.x, X.y * X.y), pm = fmaf(Y.x, Y.x, Y.y * Y.y);
+            es += pk;
+            if (2 * k != M) es += pm;
+            if (!MAG_SWEEP && p.mag) { pk = sqrtf(pk); pm = sqrtf(pm); }
+            P2[k * FPW + slot] = pk;
+            P2[(M - k) * FPW + slot] = pm;
           }
         }
-        if (PL::ALIAS_P2) __syncwarp();  // every lane has its Z values: the buffer may now hold P2
-      }
-      float es = 0.f;
+        if (t >= flen) {
+          // a frame beyond the utterance (last unit only): its spectrum is defined as zero
+          es = 0.f;
 #pragma unroll
-      for (int i = 0; i < NI; ++i) {
-        const int k = l + i * G;
-        if (i < NI - 1 || k <= M / 2) {
-          const cpx a = za[i], bb = zb[i];
-          const cpx w = wpost[k];
-          const cpx E = f2add(a, make_float2(bb.x, -bb.y));
-          const cpx O = f2add(make_float2(a.y, -a.x), make_float2(bb.y, bb.x));
-          const cpx Tt = cmul(O, w);
-          const cpx X = f2add(E, Tt), Y = f2sub(E, Tt);
-          float pk = fmaf(X.x, X.x, X.y * X.y), pm = fmaf(Y.x, Y.x, Y.y * Y.y);
-          es += pk;
-          if (2 * k != M) es += pm;
-          if (!MAG_SWEEP && p.mag) { pk = sqrtf(pk); pm = sqrtf(pm); }
-          P2[k * FPW + slot] = pk;
-          P2[(M - k) * FPW + slot] = pm;
-        }
-      }
-      if (t >= flen) {
-        // a frame beyond the utterance (last tile only): its spectrum is defined as zero
-        es = 0.f;
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {
-          const int k = l + i * G;
-          if (i < NI - 1 || k <= M / 2) {
-            P2[k * FPW + slot] = 0.f;
-            P2[(M - k) * FPW + slot] = 0.f;
+          for (int i = 0; i < NI; ++i) {
+            const int k = l + i * G;
+            if (i < NI - 1 || k <= M / 2) {
+              P2[k * FPW + slot] = 0.f;
+              P2[(M - k) * FPW + slot] = 0.f;
+            }
           }
         }
+        esum[sub] = es;
+        __syncwarp();
       }
-      esum[sub] = es;
-      __syncwarp();
-    }
-    if (MAG_SWEEP && p.mag) {  // magnitude spectrum: one extra sweep, off the power-spectrum path every recipe takes
-      for (int i = lane; i < K * FPW; i += 32) P2[i] = sqrtf(P2[i]);
-      __syncwarp();
-    }
-
-    // the next tile's claim has long returned: describe it and start its copy under the rest of this tile
-    if (tid == 0) publish(static_cast<int>(claimed), buf ^ 1, p.nstage == 2);
-
-    // ---------------- energy (sum of the power spectrum of each frame) ----------------
-    if (p.energy) {
-#pragma unroll
-      for (int sub = 0; sub < PL::S; ++sub) {
-        float es = esum[sub];
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) es += __shfl_xor_sync(0xffffffffu, es, o);
-        const int slot = sub * PL::C + g;
-        const int t = t0 + warp * FPW + slot;
-        if (l == 0 && t < p.F) p.energy[static_cast<long long>(b) * p.F + t] = (t < flen) ? sqrtf(fmaxf(es, 1e-10f)) : 0.f;
+      if (SFE_ABLATE >= 4) prefetch_next();
+      if (MAG_SWEEP && p.mag) {  // magnitude spectrum: one extra sweep, off the power-spectrum path every recipe takes
+        for (int i = lane; i < K * FPW; i += 32) P2[i] = sqrtf(P2[i]);
+        __syncwarp();
       }
-    }
 
-    // ---------------- linear spectrogram output ----------------
-    if (p.lin) {
+      // ---------------- energy (sum of the power spectrum of each frame) ----------------
+      if (p.energy) {
 #pragma unroll
-      for (int slot = 0; slot < FPW; ++slot) {
-        const int t = t0 + warp * FPW + slot;
-        if (t < p.F) {
-          float* dst = p.lin + (static_cast<long long>(b) * p.F + t) * K;
-          for (int k = lane; k < K; k += 32) {
-            float v = P2[k * FPW + slot];
-            if (p.lin_log) v = fast_log(v, p.lin_clamp, p.lin_lmul);
-            dst[k] = v;
+        for (int sub = 0; sub < PL::S; ++sub) {
+          float es = esum[sub];
+#pragma unroll
+          for (int o = G / 2; o > 0; o >>= 1) es += __shfl_xor_sync(0xffffffffu, es, o);
+          const int t = tA + sub * PL::C + g;
+          if (l == 0 && t < F) p.energy[static_cast<long long>(b) * F + t] = (t < flen) ? sqrtf(fmaxf(es, 1e-10f)) : 0.f;
+        }
+      }
+
+      // ---------------- linear spectrogram output ----------------
+      if (p.lin) {
+#pragma unroll
+        for (int slot = 0; slot < FPW; ++slot) {
+          const int t = tA + slot;
+          if (t < F) {
+            float* dst = p.lin + (static_cast<long long>(b) * F + t) * K;
+            for (int k = lane; k < K; k += 32) {
+              float v = P2[k * FPW + slot];
+              if (p.lin_log) v = fast_log(v, p.lin_clamp, p.lin_lmul);
+              dst[k] = v;
+            }
           }
         }
       }
-    }
 
-    // ---------------- banded mel + log + epilogue ----------------
-    // Filter *units* (a mel bin, or half of a wide one) are spread over phases of 32 lanes with similar
-    // tap counts; a lane walks its unit two taps at a time over both frames of the warp.
-    if (p.mel) {
-      const int tA = t0 + warp * FPW;
-      const bool fancy = (p.norm_mean != nullptr) || (p.norm_std != nullptr) || (n_fmask > 0) || (n_tmask > 0);
-      const float2* P2v = reinterpret_cast<const float2*>(P2);
-      float* mel_row = p.mel + (static_cast<long long>(b) * p.F + tA) * D;
-      const bool w0 = (tA < p.F) && !(p.skip_pad && tA >= flen);          // row tA is written
-      const bool w1 = (tA + 1 < p.F) && !(p.skip_pad && tA + 1 >= flen);  // row tA+1 is written
-      const float v0 = (tA < flen) ? 1.f : 0.f, v1 = (tA + 1 < flen) ? 1.f : 0.f;  // rows that count for the sums
-      int* sacc = reinterpret_cast<int*>(smem + p.sm_acc) + buf * 4 * D;  // [D][s1 hi, s1 lo, s2 hi, s2 lo]
-      float fillv = 0.f;
-      bool tm0 = false, tm1 = false;
-      if (fancy) {
-        fillv = p.fill_dev ? *p.fill_dev : p.fill;
-        for (int q = 0; q < n_tmask; ++q) {
-          const int ps = m_tpos[b * n_tmask + q], ln = m_tlen[b * n_tmask + q];
-          tm0 |= (tA >= ps) && (tA < ps + ln);
-          tm1 |= (tA + 1 >= ps) && (tA + 1 < ps + ln);
+      // ---------------- banded mel + log + epilogue ----------------
+      // Filter *units* (a mel bin, or half of a wide one) are spread over phases of 32 lanes with similar
+      // tap counts; a lane walks its unit two taps at a time over both frames of the warp.
+      if (p.mel && SFE_ABLATE < 1) {
+        const bool fancy = (p.norm_mean != nullptr) || (p.norm_std != nullptr) || (n_fmask > 0) || (n_tmask > 0);
+        const float2* P2v = reinterpret_cast<const float2*>(P2);
+        float* mel_row = p.mel + (static_cast<long long>(b) * F + tA) * D;
+        const bool w0 = (tA < F) && !(p.skip_pad && tA >= flen);          // row tA is written
+        const bool w1 = (tA + 1 < F) && !(p.skip_pad && tA + 1 >= flen);  // row tA+1 is written
+        const float v0 = (tA < flen) ? 1.f : 0.f, v1 = (tA + 1 < flen) ? 1.f : 0.f;  // rows that count for the sums
+        float fillv = 0.f;
+        bool tm0 = false, tm1 = false;
+        if (fancy) {
+          fillv = p.fill_dev ? *p.fill_dev : p.fill;
+          for (int q = 0; q < n_tmask; ++q) {
+            const int ps = m_tpos[b * n_tmask + q], ln = m_tlen[b * n_tmask + q];
+            tm0 |= (tA >= ps) && (tA < ps + ln);
+            tm1 |= (tA + 1 >= ps) && (tA + 1 < ps + ln);
+          }
         }
-      }
-      // The option flags are kernel constants: pick one of eight straight-line variants per tile instead
-      // of testing them for every bin.
-      auto mel_stage = [&](auto kLogT, auto kStatsT, auto kFancyT) {
-        constexpr bool kLog = decltype(kLogT)::value, kStats = decltype(kStatsT)::value,
-                       kFancy = decltype(kFancyT)::value;
-        const float clampv = p.mel_clamp, lmul = p.mel_lmul;
-        const float2* wl = mw2 + lane;
-        float* mel_row1 = mel_row + D;
-        auto phase = [&](const int ph, const int n2, const int wofs) {
-          const int2 so = mtab[ph * 32];   // .x first bin of this lane's unit, .y output info
-          const float2* pp = P2v + so.x;
-          const float2* wp = wl + wofs;
-          float2 accA = make_float2(0.f, 0.f), accB = make_float2(0.f, 0.f);  // (frame 0, frame 1) pairs
+        // The option flags are kernel constants: pick one of eight straight-line variants per unit instead
+        // of testing them for every bin.
+        auto mel_stage = [&](auto kLogT, auto kStatsT, auto kFancyT) {
+          constexpr bool kLog = decltype(kLogT)::value, kStats = decltype(kStatsT)::value,
+                         kFancy = decltype(kFancyT)::value;
+          const float clampv = p.mel_clamp, lmul = p.mel_lmul;
+          const float2* wl = mw2 + lane;
+          float* mel_row1 = mel_row + D;
+          auto phase = [&](const int ph, const int n2, const int wofs) {
+            const int2 so = mtab[ph * 32];   // .x first bin of this lane's unit, .y output info
+            const float2* pp = P2v + so.x;
+            const float2* wp = wl + wofs;
+            float2 accA = make_float2(0.f, 0.f), accB = make_float2(0.f, 0.f);  // (frame 0, frame 1) pairs
 #pragma unroll 2
-          for (int q = 0; q < n2; ++q) {
-            const float2 wq = wp[q * 32];
-            const float2 p0 = pp[2 * q], p1 = pp[2 * q + 1];
-            accA = f2fma(make_float2(wq.x, wq.x), p0, accA);
-            accB = f2fma(make_float2(wq.y, wq.y), p1, accB);
-          }
-          float2 acc = f2add(accA, accB);
-          // bins wider than a unit: add the partner lane's half (cheaper done always than tested per phase)
-          const float o0 = __shfl_xor_sync(0xffffffffu, acc.x, 1), o1 = __shfl_xor_sync(0xffffffffu, acc.y, 1);
-          if (so.y & 0x10000) acc = f2add(acc, make_float2(o0, o1));
-          if (so.y >= 0) {  // this lane publishes bin d
-            const int d = so.y & 0xffff;
-            float x0 = acc.x, x1 = acc.y;
-            if (kLog) {
-              x0 = fast_log(x0, clampv, lmul);
-              x1 = fast_log(x1, clampv, lmul);
+            for (int q = 0; q < n2; ++q) {
+              const float2 wq = wp[q * 32];
+              const float2 p0 = pp[2 * q], p1 = pp[2 * q + 1];
+              accA = f2fma(make_float2(wq.x, wq.x), p0, accA);
+              accB = f2fma(make_float2(wq.y, wq.y), p1, accB);
             }
-            if (kStats) {
-              // pair sums in fp32, then exact order-independent fixed-point accumulation
-              const float s1 = x0 * v0 + x1 * v1;
-              const float s2 = fmaf(x0 * v0, x0, x1 * v1 * x1);
-              // (64-bit shared atomics are CAS loops; two native 32-bit adds on disjoint bit ranges are not)
-              const long long f1 = __float2ll_rn(s1 * 4294967296.f), f2 = __float2ll_rn(s2 * 16777216.f);
-              atomicAdd(sacc + 4 * d + 0, static_cast<int>(f1 >> 24));
-              atomicAdd(sacc + 4 * d + 1, static_cast<int>(f1 & 0xffffff));
-              atomicAdd(sacc + 4 * d + 2, static_cast<int>(f2 >> 24));
-              atomicAdd(sacc + 4 * d + 3, static_cast<int>(f2 & 0xffffff));
-            }
-            if (kFancy) {
-              if (p.norm_mean) { const float nm = p.norm_mean[d]; x0 -= nm; x1 -= nm; }
-              if (p.norm_std) { const float ns = p.norm_std[d]; x0 /= ns; x1 /= ns; }
-              bool fm = false;
-              for (int q = 0; q < n_fmask; ++q) {
-                const int ps = m_fpos[b * n_fmask + q], ln = m_flen[b * n_fmask + q];
-                fm |= (d >= ps) && (d < ps + ln);
+            float2 acc = f2add(accA, accB);
+            // bins wider than a unit: add the partner lane's half (cheaper done always than tested per phase)
+            const float o0 = __shfl_xor_sync(0xffffffffu, acc.x, 1), o1 = __shfl_xor_sync(0xffffffffu, acc.y, 1);
+            if (so.y & 0x10000) acc = f2add(acc, make_float2(o0, o1));
+            if (so.y >= 0) {  // this lane publishes bin d
+              const int d = so.y & 0xffff;
+              float x0 = acc.x, x1 = acc.y;
+              if (kLog) {
+                x0 = fast_log(x0, clampv, lmul);
+                x1 = fast_log(x1, clampv, lmul);
               }
-              if (fm || tm0) x0 = fillv;
-              if (fm || tm1) x1 = fillv;
+              if (kStats) {
+                // pair sums in fp32, then exact order-independent fixed-point accumulation; bin d belongs to
+                // exactly one lane of one phase, so the warp-private sums need no atomics
+                const float s1 = x0 * v0 + x1 * v1;
+                const float s2 = fmaf(x0 * v0, x0, x1 * v1 * x1);
+                longlong2* ap = reinterpret_cast<longlong2*>(wacc) + d;
+                longlong2 a = *ap;
+                a.x += __float2ll_rn(s1 * 4294967296.f);
+                a.y += __float2ll_rn(s2 * 16777216.f);
+                *ap = a;
+              }
+              if (kFancy) {
+                if (p.norm_mean) { const float nm = p.norm_mean[d]; x0 -= nm; x1 -= nm; }
+                if (p.norm_std) { const float ns = p.norm_std[d]; x0 /= ns; x1 /= ns; }
+                bool fm = false;
+                for (int q = 0; q < n_fmask; ++q) {
+                  const int ps = m_fpos[b * n_fmask + q], ln = m_flen[b * n_fmask + q];
+                  fm |= (d >= ps) && (d < ps + ln);
+                }
+                if (fm || tm0) x0 = fillv;
+                if (fm || tm1) x1 = fillv;
+              }
+              if (w0) mel_row[d] = x0;
+              if (w1) mel_row1[d] = x1;
             }
-            if (w0) mel_row[d] = x0;
-            if (w1) mel_row1[d] = x1;
+          };
+          const int nph = p.mel_rounds;
+          if (nph <= 4) {
+            // the usual filterbanks need at most four phases: straight-line code, every table offset an immediate
+#pragma unroll
+            for (int ph = 0; ph < 4; ++ph)
+              if (ph < nph) phase(ph, p.mel_ph[ph].x, p.mel_ph[ph].y);
+          } else {
+            for (int ph = 0; ph < nph; ++ph) phase(ph, p.mel_ph[ph].x, p.mel_ph[ph].y);
           }
         };
-        const int nph = p.mel_rounds;
-        if (nph <= 4) {
-          // the usual filterbanks need at most four phases: straight-line code, every table offset an immediate
-#pragma unroll
-          for (int ph = 0; ph < 4; ++ph)
-            if (ph < nph) phase(ph, p.mel_ph[ph].x, p.mel_ph[ph].y);
-        } else {
-          for (int ph = 0; ph < nph; ++ph) phase(ph, p.mel_ph[ph].x, p.mel_ph[ph].y);
-        }
-      };
-      using T1 = std::true_type;
-      using T0 = std::false_type;
-      switch ((p.mel_log ? 1 : 0) | (p.stats ? 2 : 0) | (fancy ? 4 : 0)) {
-        case 0: mel_stage(T0{}, T0{}, T0{}); break;
-        case 1: mel_stage(T1{}, T0{}, T0{}); break;
-        case 2: mel_stage(T0{}, T1{}, T0{}); break;
-        case 3: mel_stage(T1{}, T1{}, T0{}); break;
-        case 4: mel_stage(T0{}, T0{}, T1{}); break;
-        case 5: mel_stage(T1{}, T0{}, T1{}); break;
-        case 6: mel_stage(T0{}, T1{}, T1{}); break;
-        default: mel_stage(T1{}, T1{}, T1{}); break;
-      }
-    }
-
-    // ---------------- end of tile ----------------
-    __syncthreads();  // every warp is done with this tile's staging buffer and its sums are in smem
-    if (p.stats) {
-      int* sacc = reinterpret_cast<int*>(smem + p.sm_acc) + buf * 4 * D;
-      for (int i = tid; i < 2 * D; i += NTHREADS) {
-        const int hi = sacc[2 * i], lo = sacc[2 * i + 1];
-        if ((hi | lo) != 0) {
-          sacc[2 * i] = 0;  // this buffer is used again two tiles from now, behind the next barrier
-          sacc[2 * i + 1] = 0;
-          const long long v = static_cast<long long>(hi) * 16777216LL + static_cast<long long>(lo);
-          atomicAdd(p.stats + static_cast<long long>(b) * D * 2 + i, static_cast<unsigned long long>(v));
+        using T1 = std::true_type;
+        using T0 = std::false_type;
+        switch ((p.mel_log ? 1 : 0) | (p.stats ? 2 : 0) | (fancy ? 4 : 0)) {
+          case 0: mel_stage(T0{}, T0{}, T0{}); break;
+          case 1: mel_stage(T1{}, T0{}, T0{}); break;
+          case 2: mel_stage(T0{}, T1{}, T0{}); break;
+          case 3: mel_stage(T1{}, T1{}, T0{}); break;
+          case 4: mel_stage(T0{}, T0{}, T1{}); break;
+          case 5: mel_stage(T1{}, T0{}, T1{}); break;
+          case 6: mel_stage(T0{}, T1{}, T1{}); break;
+          default: mel_stage(T1{}, T1{}, T1{}); break;
         }
       }
+      __syncwarp();  // P2 (and the scratch it may alias) is free for the next unit
     }
-  }
 
-  // self-resetting scheduler: the last CTA to leave re-arms the counters for the next launch
-  if (tid == 0) {
-    __threadfence();
-    const unsigned done = atomicAdd(p.sched + 1, 1u);
-    if (done == gridDim.x - 1) {
-      p.sched[0] = 0u;
-      p.sched[1] = 0u;
-      __threadfence();
-    }
+    // ---------------- next unit ----------------
+    if (p.stats && (!ctl->live || ctl->b != b)) flush_sums(b);
   }
 }
 

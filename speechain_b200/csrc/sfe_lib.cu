@@ -1,9 +1,10 @@
 // libsfe.so — C ABI (include/sfe.h) over the sm_100a kernels.  No torch, no exceptions across
-// the boundary, no per-call allocation: a plan owns its constant tables and two scheduler words.
+// the boundary, no per-call allocation: a plan owns its constant tables and nothing else.
 #include <cuda_runtime.h>
 #include <float.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -49,11 +50,11 @@ struct sfe_plan {
   int device;
   int n_sm;
   float* d_tables;
-  unsigned int* d_sched;
   double* d_acc;  // one fp64 scratch word for sfe_mean_all
   FwdParams proto;  // everything that does not change per call
   int smem_bytes;
   int ctas_per_sm;
+  int warps_per_cta;  // warps never synchronise with each other: chosen for the most resident warps per SM
   // standalone mel kernel
   int l2m_smem;
   int l2m_sm_warp, l2m_warp_bytes;
@@ -261,47 +262,52 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
   align4();
   P.tab_floats = static_cast<int>(tab.size());
 
-  // ---- shared-memory carve-up (two staging buffers if they fit, else one) ----
+  // ---- shared-memory carve-up: [tables | table mbarrier | one private region per warp] ----
+  // Warps never synchronise with each other, so the number of warps per CTA is free: take the one that
+  // puts the most warps on an SM (big FFT plans need > 20 KB per warp).
   const bool alias = (fe->C == FPW);  // FftPlan::ALIAS_P2
-  const int stage_floats = round_up((TILE_F - 1) * cfg->hop_length + cfg->n_fft + 16, 4);
+  const int stage_floats = round_up((FPW - 1) * cfg->hop_length + cfg->n_fft + 16, 4);
   const int z_bytes = round_up(fe->C * fe->MP * 8, 16);
   const int p2_bytes = round_up((K + P.mel_tail + 2) * FPW * 4, 16);
-  int smem_limit = 227 * 1024;
+  int smem_limit = 227 * 1024, smem_sm = 228 * 1024, static_bytes = 2048;
   {
     int dev = 0;
     cudaDeviceProp pr;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&pr, dev) == cudaSuccess)
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&pr, dev) == cudaSuccess) {
       smem_limit = static_cast<int>(pr.sharedMemPerBlockOptin);
+      smem_sm = static_cast<int>(pr.sharedMemPerMultiprocessor);
+    }
     // the opt-in limit covers static + dynamic shared memory: leave room for the kernel's static part
     cudaFuncAttributes fa;
     if (cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(fe->fn[cfg->has_preemphasis ? 1 : 0])) == cudaSuccess)
-      smem_limit -= static_cast<int>(fa.sharedSizeBytes);
-    else
-      smem_limit -= 4096;
+      static_bytes = static_cast<int>(fa.sharedSizeBytes);
+    smem_limit -= static_bytes;
   }
-  for (P.nstage = NSTAGE; P.nstage >= 1; --P.nstage) {
+  {
     int o = round_up(P.tab_floats * 4, 16);
-    P.sm_stage = o;
-    P.sm_stage_floats = stage_floats;
-    o += P.nstage * stage_floats * 4;
+    P.sm_tbar = o;
+    o += 16;
     P.sm_warp = o;
-    int warp_bytes;
+    int wb;
     if (alias) {  // the power spectrum overwrites the FFT scratch
       P.sm_p2_off = 0;
-      warp_bytes = z_bytes > p2_bytes ? z_bytes : p2_bytes;
+      wb = z_bytes > p2_bytes ? z_bytes : p2_bytes;
     } else {      // the power spectrum sits behind the FFT scratch
       P.sm_p2_off = z_bytes;
-      warp_bytes = z_bytes + p2_bytes;
+      wb = z_bytes + p2_bytes;
     }
-    P.sm_warp_bytes = round_up(warp_bytes, 16);
-    o += NWARPS * P.sm_warp_bytes;
-    P.sm_acc = round_up(o, 16);  // [NSTAGE][D][2] fixed-point sums of the tile in flight
-    o = P.sm_acc + NSTAGE * (D > 0 ? D : 1) * 4 * 4;
-    P.sm_bar = round_up(o, 16);
-    pl->smem_bytes = P.sm_bar + 32;
-    if (pl->smem_bytes <= smem_limit) break;
+    P.sm_stage_off = wb;
+    wb += stage_floats * 4;
+    P.sm_acc_off = round_up(wb, 16);
+    wb = P.sm_acc_off + (D > 0 ? D : 1) * 16;
+    P.sm_bar_off = round_up(wb, 16);
+    P.sm_warp_bytes = P.sm_bar_off + 16 + 64;  // mbarrier, control block
   }
-  if (P.nstage < 1) P.nstage = 1;
+  // one CTA per SM with as many warps as shared memory and the plan's register budget allow
+  pl->warps_per_cta = (smem_limit - P.sm_warp) / P.sm_warp_bytes;
+  if (pl->warps_per_cta > fe->MAXW) pl->warps_per_cta = fe->MAXW;
+  if (pl->warps_per_cta < 1) pl->warps_per_cta = 1;
+  pl->smem_bytes = P.sm_warp + pl->warps_per_cta * P.sm_warp_bytes;
   // standalone mel kernel: tables + per-warp P2
   pl->l2m_sm_warp = round_up(P.tab_floats * 4, 16);
   pl->l2m_warp_bytes = p2_bytes;
@@ -339,8 +345,6 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
   }
   if (e == cudaSuccess) e = cudaMalloc(&pl->d_tables, tab.size() * sizeof(float));
   if (e == cudaSuccess) e = cudaMemcpy(pl->d_tables, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMalloc(&pl->d_sched, 2 * sizeof(unsigned int));
-  if (e == cudaSuccess) e = cudaMemset(pl->d_sched, 0, 2 * sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMalloc(&pl->d_acc, sizeof(double));
   if (e == cudaSuccess) e = cudaMemset(pl->d_acc, 0, sizeof(double));
   for (int v = 0; v < 2; ++v)
@@ -352,12 +356,11 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
                              cudaFuncAttributeMaxDynamicSharedMemorySize, pl->l2m_smem);
   int occ = 0;
   if (e == cudaSuccess)
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void*>(fe->fn[cfg->has_preemphasis ? 1 : 0]), NTHREADS,
-                                                      pl->smem_bytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void*>(fe->fn[cfg->has_preemphasis ? 1 : 0]),
+                                                      pl->warps_per_cta * 32, pl->smem_bytes);
   if (e != cudaSuccess) {
     std::string msg = std::string("sfe_plan_create: ") + cudaGetErrorString(e);
     cudaFree(pl->d_tables);
-    cudaFree(pl->d_sched);
     cudaFree(pl->d_acc);
     delete pl;
     return fail(SFE_ERR_CUDA, msg);
@@ -365,7 +368,6 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
   pl->n_sm = prop.multiProcessorCount;
   pl->ctas_per_sm = occ < 1 ? 1 : occ;
   P.tables = pl->d_tables;
-  P.sched = pl->d_sched;
   *out = pl;
   return SFE_OK;
 }
@@ -373,7 +375,6 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
 extern "C" void sfe_plan_destroy(sfe_plan* pl) {
   if (!pl) return;
   cudaFree(pl->d_tables);
-  cudaFree(pl->d_sched);
   cudaFree(pl->d_acc);
   cudaFree(pl->d_gl);
   delete pl;
@@ -474,10 +475,9 @@ static int frontend_forward_impl(const sfe_plan* pl, const float* wav, int64_t w
   P.B = B;
   P.T_max = T_max;
   P.F = static_cast<int>(F);
-  P.tiles_per_utt = static_cast<int>((F + TILE_F - 1) / TILE_F);
-  const long long nt = static_cast<long long>(P.tiles_per_utt) * B;
-  if (nt > 0x7fffffffLL) return fail(SFE_ERR_BAD_ARG, "batch too large");
-  P.num_tiles = static_cast<int>(nt);
+  P.units_per_utt = static_cast<int>((F + FPW - 1) / FPW);
+  const long long nu = static_cast<long long>(P.units_per_utt) * B;
+  if (nu * REAL_UNIT_COST > 0x7fffffffLL) return fail(SFE_ERR_BAD_ARG, "batch too large");
   P.mel = mel;
   P.lin = lin;
   P.energy = energy;
@@ -489,9 +489,10 @@ static int frontend_forward_impl(const sfe_plan* pl, const float* wav, int64_t w
   if (int rc = fill_masks(masks, B, &P.mk, &P.fill, &P.fill_dev)) return rc;
   if (stats && zero_stats)
     SFE_CUDA(cudaMemsetAsync(stats, 0, static_cast<size_t>(B) * pl->cfg.n_mels * 2 * sizeof(int64_t), st));
-  int grid = pl->n_sm * pl->ctas_per_sm;
-  if (grid > P.num_tiles) grid = P.num_tiles;
-  pl->fft->fn[pl->cfg.has_preemphasis ? 1 : 0]<<<grid, NTHREADS, pl->smem_bytes, st>>>(P);
+  // one CTA per SM; every CTA takes an equal-cost contiguous range of the batch's units
+  long long grid = static_cast<long long>(pl->n_sm) * pl->ctas_per_sm;
+  if (grid > nu) grid = nu;
+  pl->fft->fn[pl->cfg.has_preemphasis ? 1 : 0]<<<static_cast<unsigned>(grid), pl->warps_per_cta * 32, pl->smem_bytes, st>>>(P);
   SFE_CUDA(cudaGetLastError());
   return SFE_OK;
 }

@@ -22,7 +22,7 @@ SFE_PLAN_LIST(SFE_DEF_PLAN)
 
 template <class PL>
 static FftEntry make_entry() {
-  FftEntry e{2 * PL::M, PL::WIN, PL::M, PL::G, PL::R1, PL::R2, PL::R3, PL::MP, PL::C,
+  FftEntry e{2 * PL::M, PL::WIN, PL::M, PL::G, PL::R1, PL::R2, PL::R3, PL::MP, PL::C, PL::MAXW,
              {&fused_frontend_kernel<PL, false>, &fused_frontend_kernel<PL, true>}, nullptr, nullptr};
   if constexpr (PL::WIN == 0) {
     e.gl_stft = &gl_stft_kernel<PL>;

@@ -12,7 +12,7 @@ typedef void (*gl_fn)(const GlParams);
 
 struct FftEntry {
   int n_fft, win;  // win == 0: any window length (run-time tests)
-  int M, G, R1, R2, R3, MP, C;
+  int M, G, R1, R2, R3, MP, C, MAXW;
   fused_fn fn[2];  // [0] no pre-emphasis, [1] pre-emphasis applied while loading
   gl_fn gl_stft, gl_istft;  // Griffin-Lim transforms (generic-window entries only)
 };
