@@ -409,11 +409,11 @@ __global__ void __launch_bounds__(NTHREADS) linear2mel_kernel(const __grid_const
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* P2 = reinterpret_cast<float*>(smem + p.sm_warp + warp * p.sm_warp_bytes);
   for (int i = tid; i < p.tab_floats; i += NTHREADS) tab[i] = __ldg(p.tables + i);
-  const int p2_floats = (p.K + p.mel_tail + 2) * FPW;
+  const int p2_floats = (p.K + MEL_PAD_BINS) * FPW;  // the pad bins stay zero
   for (int i = lane; i < p2_floats; i += 32) P2[i] = 0.f;
   __syncthreads();
   const int2* mtab = reinterpret_cast<const int2*>(tab + p.o_mtab) + lane;
-  const float2* mw2 = reinterpret_cast<const float2*>(tab + p.o_mw);
+  const float4* mw4 = reinterpret_cast<const float4*>(tab + p.o_mw);
   const float2* P2v = reinterpret_cast<const float2*>(P2);
   const long long pairs = (p.n_rows + FPW - 1) / FPW;
   for (long long pr = static_cast<long long>(blockIdx.x) * NWARPS + warp; pr < pairs;
@@ -428,15 +428,17 @@ __global__ void __launch_bounds__(NTHREADS) linear2mel_kernel(const __grid_const
     for (int ph = 0; ph < p.mel_rounds; ++ph) {
       const int2 so = mtab[ph * 32];
       const int oinfo = so.y;
-      const float2* pp = P2v + so.x;
-      const int n2 = p.mel_ph[ph].x;
-      const float2* wp = mw2 + p.mel_ph[ph].y + lane;
+      const float4* pp = reinterpret_cast<const float4*>(P2v + so.x);  // units start on even bins
+      const int n4 = p.mel_ph[ph].x;
+      const float4* wp = mw4 + p.mel_ph[ph].y + lane;
       float a0 = 0.f, a1 = 0.f;
-      for (int q = 0; q < n2; ++q) {
-        const float2 wq = wp[q * 32];
-        const float2 p0 = pp[2 * q], p1 = pp[2 * q + 1];
-        a0 = fmaf(wq.x, p0.x, a0); a1 = fmaf(wq.x, p0.y, a1);
-        a0 = fmaf(wq.y, p1.x, a0); a1 = fmaf(wq.y, p1.y, a1);
+      for (int q = 0; q < n4; ++q) {
+        const float4 wq = wp[q * 32];
+        const float4 pa = pp[2 * q], pb = pp[2 * q + 1];
+        a0 = fmaf(wq.x, pa.x, a0); a1 = fmaf(wq.x, pa.y, a1);
+        a0 = fmaf(wq.y, pa.z, a0); a1 = fmaf(wq.y, pa.w, a1);
+        a0 = fmaf(wq.z, pb.x, a0); a1 = fmaf(wq.z, pb.y, a1);
+        a0 = fmaf(wq.w, pb.z, a0); a1 = fmaf(wq.w, pb.w, a1);
       }
       if ((p.mel_split_mask >> ph) & 1u) {
         const float o0 = __shfl_xor_sync(0xffffffffu, a0, 1), o1 = __shfl_xor_sync(0xffffffffu, a1, 1);

@@ -37,6 +37,7 @@ constexpr int NWARPS = 8;                 // warps per CTA of the small standalo
 constexpr int NTHREADS = NWARPS * 32;
 constexpr int FPW = 2;                    // frames per unit (per warp step)
 constexpr int MAX_MEL_ROUNDS = 16;        // phases of 32 filter units (n_mels <= 256)
+constexpr int MEL_PAD_BINS = 4;           // zeroed bins behind the power spectrum (filter units read whole 4-tap blocks)
 constexpr int MASK_INLINE_MAX = 768;      // SFE_MASK_INLINE_MAX
 constexpr int UNIT_TABLE_MAX_B = 256;     // batches up to this size get a per-utterance cost table
 constexpr int REAL_UNIT_COST = 8;         // a unit with real frames costs this many pad-only units
@@ -90,9 +91,9 @@ struct FwdParams {
   int tab_floats;
   int o_win, o_tw2, o_tw3, o_wpost, o_mtab, o_mw;  // float offsets into the blob
   int mel_rounds;                                    // phases of 32 filter units
-  int2 mel_ph[MAX_MEL_ROUNDS];                       // per phase: {pairs of taps, float2 offset of its weights}
+  int2 mel_ph[MAX_MEL_ROUNDS];                       // per phase: {blocks of 4 taps, float4 offset of its weights}
   unsigned int mel_split_mask;                       // phases that hold bins split over two lanes
-  int mel_tail;                                      // max taps of any phase (P2 tail padding)
+  int mel_tail;                                      // zeroed bins behind the spectrum (MEL_PAD_BINS)
   // per-CTA: [tables | table mbarrier | warp 0 | warp 1 | ...]; per warp: [FFT scratch (P2 may alias it) | P2 |
   // staging | sums | mbarrier]
   int sm_tbar, sm_warp, sm_warp_bytes, sm_p2_off, sm_stage_off, sm_acc_off, sm_bar_off;
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(PL::MAXW * 32, 1) fused_frontend_kernel(const 
   const cpx* tw3 = reinterpret_cast<const cpx*>(tab + p.o_tw3);
   const cpx* wpost = reinterpret_cast<const cpx*>(tab + p.o_wpost);
   const int2* mtab = reinterpret_cast<const int2*>(tab + p.o_mtab) + lane;  // {first bin, output info} per (phase, lane)
-  const float2* mw2 = reinterpret_cast<const float2*>(tab + p.o_mw);
+  const float4* mw4 = reinterpret_cast<const float4*>(tab + p.o_mw);
   const bool base_aligned = ((reinterpret_cast<uintptr_t>(p.wav) & 15) == 0);
   const int n_fmask = p.mk.n_fmask, n_tmask = p.mk.n_tmask;
   const int* m_fpos = p.mk.inl_on ? p.mk.inl : p.mk.fpos;
@@ -455,13 +456,7 @@ __global__ void __launch_bounds__(PL::MAXW * 32, 1) fused_frontend_kernel(const 
   // (`first`: nothing processed yet).  All lanes compute the same values; lane 0 stores them.
   auto advance = [&](bool first) {
     Ctl q;
-    if (first) {
-      q.b = -1; q.tu = 0; q.flen = 0; q.nunit = 0; q.c = 0; q.c_hi = 0; q.len = 0;
-    } else {
-      q = *ctl;
-      q.c += (q.tu * FPW < q.flen) ? real_step : 1;
-      ++q.tu;
-    }
+    q.b = -1; q.tu = 0; q.flen = 0; q.nunit = 0; q.c = 0; q.c_hi = 0; q.len = 0;
     auto load_utt = [&]() {
       q.len = __ldg(p.len + q.b);
       q.flen = clampF(frames_of(q.len));
@@ -476,58 +471,68 @@ __global__ void __launch_bounds__(PL::MAXW * 32, 1) fused_frontend_kernel(const 
         if (tabled) q.c = s_cum[q.b];
       }
     };
-    if (!first) settle();
-    // `q` is the first unit at or after the end of the current chunk: take chunks from the CTA's counter
-    // until `q` lies inside one; the CTA's range may run out first
+    bool have = false;  // q is a unit inside the warp's current chunk
+    if (!first) {
+      q.b = ctl->b; q.flen = ctl->flen; q.nunit = ctl->nunit; q.len = ctl->len;
+      q.tu = ctl->tu;
+      if (q.tu * FPW >= q.flen) {
+        // after a pad unit the chunk may hold more of them (a real unit always uses its chunk up)
+        q.c = ctl->c + 1;
+        q.c_hi = ctl->c_hi;
+        ++q.tu;
+        settle();
+        have = (q.tu < q.nunit && q.c < q.c_hi);
+      }
+    }
     q.live = 1;
-    while (first || !(q.tu < q.nunit && q.c < q.c_hi)) {
+    while (!have) {
+      // next chunk of the CTA's range
       int k = 0;
-      if (lane == 0) k = atomicAdd(&s_next, 1);
+      if (lane == 0)  // (plain atom.shared: atomicAdd() would wrap it in warp-aggregation code)
+        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(k) : "r"(smem_u32(&s_next)) : "memory");
       k = __shfl_sync(0xffffffffu, k, 0);
       const long long lo64 = static_cast<long long>(cta_lo) + static_cast<long long>(k) * real_step;
       if (lo64 >= cta_hi) { q.live = 0; break; }
       const int c0 = static_cast<int>(lo64);
       q.c_hi = min(c0 + real_step, cta_hi);
-      // chunks only move forward: either `q` is still the first unit at or after c0, or it lies before it
-      if (first || (q.tu < q.nunit && q.c < c0)) {
-        // first unit whose start coordinate is >= c0; q.b is -1 or an utterance that starts at or before c0
-        if (tabled) {
-          int lo = q.b < 0 ? 0 : q.b;
-          if (lo + 1 < B && s_cum[lo + 1] <= c0) {  // (usually still the same utterance)
-            int hi = B - 1;  // last utterance that starts at or before c0
-            ++lo;
-            while (lo < hi) {
-              const int mid = (lo + hi + 1) >> 1;
-              if (s_cum[mid] <= c0) lo = mid; else hi = mid - 1;
-            }
-          }
-          if (lo != q.b) {
-            q.b = lo;
-            load_utt();
-          }
-          const int nreal = (q.flen + FPW - 1) / FPW;
-          const int off = c0 - s_cum[q.b];
-          const int real_cost = REAL_UNIT_COST * nreal;
-          if (off <= real_cost) {
-            q.tu = (off + REAL_UNIT_COST - 1) / REAL_UNIT_COST;
-            q.c = s_cum[q.b] + q.tu * REAL_UNIT_COST;
-          } else {
-            q.tu = nreal + (off - real_cost);
-            q.c = c0;
-          }
-        } else {
-          int nb = c0 / upu;
-          if (nb >= B) nb = B - 1;
-          q.tu = c0 - nb * upu;
-          q.c = c0;
-          if (nb != q.b) {
-            q.b = nb;
-            load_utt();
+      // first unit whose start coordinate is >= c0 (chunks move forward: usually still the same utterance)
+      if (tabled) {
+        int lo = q.b;
+        if (lo < 0 || s_cum[lo] > c0) lo = 0;
+        if (lo + 1 < B && s_cum[lo + 1] <= c0) {
+          int hi = B - 1;  // last utterance that starts at or before c0
+          ++lo;
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_cum[mid] <= c0) lo = mid; else hi = mid - 1;
           }
         }
-        settle();
+        if (lo != q.b) {
+          q.b = lo;
+          load_utt();
+        }
+        const int nreal = (q.flen + FPW - 1) / FPW;
+        const int off = c0 - s_cum[q.b];
+        const int real_cost = REAL_UNIT_COST * nreal;
+        if (off <= real_cost) {
+          q.tu = (off + REAL_UNIT_COST - 1) / REAL_UNIT_COST;
+          q.c = c0 - off + q.tu * REAL_UNIT_COST;
+        } else {
+          q.tu = nreal + (off - real_cost);
+          q.c = c0;
+        }
+      } else {
+        int nb = c0 / upu;
+        if (nb >= B) nb = B - 1;
+        q.tu = c0 - nb * upu;
+        q.c = c0;
+        if (nb != q.b) {
+          q.b = nb;
+          load_utt();
+        }
       }
-      first = false;
+      settle();
+      have = (q.tu < q.nunit && q.c < q.c_hi);
     }
     // where the unit's samples come from
     q.bulk = 0; q.inflight = 0; q.shift = 0; q.bytes = 0; q.ga = 0; q.pad_ = 0;
@@ -733,6 +738,8 @@ __global__ void __launch_bounds__(PL::MAXW * 32, 1) fused_frontend_kernel(const 
         __syncwarp();
       }
       if (SFE_ABLATE >= 4) prefetch_next();
+      if (lane < MEL_PAD_BINS) reinterpret_cast<float2*>(P2)[K + lane] = make_float2(0.f, 0.f);  // (see the mel stage)
+      __syncwarp();
       if (MAG_SWEEP && p.mag) {  // magnitude spectrum: one extra sweep, off the power-spectrum path every recipe takes
         for (int i = lane; i < K * FPW; i += 32) P2[i] = sqrtf(P2[i]);
         __syncwarp();
@@ -792,19 +799,21 @@ __global__ void __launch_bounds__(PL::MAXW * 32, 1) fused_frontend_kernel(const 
           constexpr bool kLog = decltype(kLogT)::value, kStats = decltype(kStatsT)::value,
                          kFancy = decltype(kFancyT)::value;
           const float clampv = p.mel_clamp, lmul = p.mel_lmul;
-          const float2* wl = mw2 + lane;
+          const float4* wl = mw4 + lane;
           float* mel_row1 = mel_row + D;
-          auto phase = [&](const int ph, const int n2, const int wofs) {
-            const int2 so = mtab[ph * 32];   // .x first bin of this lane's unit, .y output info
-            const float2* pp = P2v + so.x;
-            const float2* wp = wl + wofs;
+          auto phase = [&](const int ph, const int n4, const int wofs) {
+            const int2 so = mtab[ph * 32];   // .x first bin of this lane's unit (even), .y output info
+            const float4* pp = reinterpret_cast<const float4*>(P2v + so.x);  // {bin k: frame 0, 1; bin k+1: frame 0, 1}
+            const float4* wp = wl + wofs;
             float2 accA = make_float2(0.f, 0.f), accB = make_float2(0.f, 0.f);  // (frame 0, frame 1) pairs
-#pragma unroll 2
-            for (int q = 0; q < n2; ++q) {
-              const float2 wq = wp[q * 32];
-              const float2 p0 = pp[2 * q], p1 = pp[2 * q + 1];
-              accA = f2fma(make_float2(wq.x, wq.x), p0, accA);
-              accB = f2fma(make_float2(wq.y, wq.y), p1, accB);
+#pragma unroll 1
+            for (int q = 0; q < n4; ++q) {
+              const float4 wq = wp[q * 32];
+              const float4 pa = pp[2 * q], pb = pp[2 * q + 1];
+              accA = f2fma(make_float2(wq.x, wq.x), make_float2(pa.x, pa.y), accA);
+              accB = f2fma(make_float2(wq.y, wq.y), make_float2(pa.z, pa.w), accB);
+              accA = f2fma(make_float2(wq.z, wq.z), make_float2(pb.x, pb.y), accA);
+              accB = f2fma(make_float2(wq.w, wq.w), make_float2(pb.z, pb.w), accB);
             }
             float2 acc = f2add(accA, accB);
             // bins wider than a unit: add the partner lane's half (cheaper done always than tested per phase)

@@ -202,7 +202,7 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
     for (auto& ph : phs) {
       int nt = 0;
       for (auto& ln : ph) nt = ln.ntaps > nt ? ln.ntaps : nt;
-      c += 75 + 9 * ((nt + 1) / 2);
+      c += 60 + 11 * ((nt + 4) / 4);  // (+1 tap: a unit that starts on an odd bin is moved one bin down)
     }
     return c;
   };
@@ -227,18 +227,38 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
     memcpy(&f, &v, 4);
     tab.push_back(f);
   };
-  // every lane of a phase walks the phase's tap count: a unit that would run past bin K-1 starts earlier
-  // and leads with zero weights instead, so no lane ever reads beyond the power spectrum
-  for (auto& ph : phases) {
+  // A lane walks its unit four taps at a time with 128-bit loads: every unit starts on an even bin (one
+  // leading zero weight if need be) and every lane of a phase walks the phase's tap count, a multiple of
+  // four.  The power spectrum is followed by MEL_PAD_BINS zeroed bins; a unit that would run past them
+  // starts earlier and leads with zero weights instead.
+  std::vector<int> phase_nt(phases.size(), 0);
+  for (size_t i = 0; i < phases.size(); ++i) {
     int nt = 0;
-    for (auto& ln : ph) nt = ln.ntaps > nt ? ln.ntaps : nt;
-    nt = round_up(nt, 2);
-    for (auto& ln : ph) {
-      ln.lead = (ln.start + nt > K) ? ln.start + nt - K : 0;
-      ln.start -= ln.lead;
+    for (auto& ln : phases[i]) {
+      if (ln.d < 0) continue;
+      const int a = ln.start & ~1;
+      ln.lead = ln.start - a;
+      ln.start = a;
+      nt = std::max(nt, ln.lead + ln.ntaps);
+    }
+    nt = round_up(nt > 0 ? nt : 4, 4);
+    phase_nt[i] = nt;
+    for (auto& ln : phases[i]) {
+      if (ln.d < 0) { ln.start = 0; ln.lead = 0; continue; }
+      if (ln.start + nt > K + MEL_PAD_BINS) {
+        int sh = round_up(ln.start + nt - (K + MEL_PAD_BINS), 2);
+        if (sh > ln.start) sh = ln.start;
+        ln.start -= sh;
+        ln.lead += sh;
+      }
+    }
+    if (nt > K + MEL_PAD_BINS) {
+      delete pl;
+      return fail(SFE_ERR_BAD_CONFIG, "mel filter wider than the spectrum");
     }
   }
-  P.o_mtab = static_cast<int>(tab.size());  // int2 {first bin, output info} per (phase, lane)
+  P.mel_tail = MEL_PAD_BINS;
+  P.o_mtab = static_cast<int>(tab.size());  // int2 {first bin (even), output info} per (phase, lane)
   for (auto& ph : phases)
     for (auto& ln : ph) {
       push_int(ln.start);
@@ -247,14 +267,12 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
   align4();
   P.o_mw = static_cast<int>(tab.size());
   for (size_t i = 0; i < phases.size(); ++i) {
-    int nt = 0;
-    for (auto& ln : phases[i]) nt = ln.ntaps > nt ? ln.ntaps : nt;
-    nt = round_up(nt, 2);
-    P.mel_ph[i] = make_int2(nt / 2, (static_cast<int>(tab.size()) - P.o_mw) / 2);
-    for (int q2 = 0; q2 < nt / 2; ++q2)
+    const int nt = phase_nt[i];
+    P.mel_ph[i] = make_int2(nt / 4, (static_cast<int>(tab.size()) - P.o_mw) / 4);  // {blocks of 4 taps, float4 offset}
+    for (int q4 = 0; q4 < nt / 4; ++q4)
       for (auto& ln : phases[i])
-        for (int e = 0; e < 2; ++e) {
-          const int q = q2 * 2 + e;
+        for (int e = 0; e < 4; ++e) {
+          const int q = q4 * 4 + e;
           tab.push_back((ln.d >= 0 && q >= ln.lead && q < ln.lead + ln.ntaps)
                             ? cfg->mel_weight_host[static_cast<size_t>(ln.d) * K + ln.start + q] : 0.f);
         }
@@ -268,7 +286,7 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
   const bool alias = (fe->C == FPW);  // FftPlan::ALIAS_P2
   const int stage_floats = round_up((FPW - 1) * cfg->hop_length + cfg->n_fft + 16, 4);
   const int z_bytes = round_up(fe->C * fe->MP * 8, 16);
-  const int p2_bytes = round_up((K + P.mel_tail + 2) * FPW * 4, 16);
+  const int p2_bytes = round_up((K + MEL_PAD_BINS) * FPW * 4, 16);
   int smem_limit = 227 * 1024, smem_sm = 228 * 1024, static_bytes = 2048;
   {
     int dev = 0;
