@@ -59,8 +59,9 @@ def build(force: bool = False, verbose: bool = False, out: str = OUT) -> str:
         jobs.append([nvcc] + NVCC_FLAGS + extra + [f"-DSFE_PLAN_TU={i}", "-c", "sfe_plans.cu", "-o", objs[1 + i]])
     dev = os.environ.get("SFE_DEV_PLANS")
     if dev:  # development shortcut: the other objects must already exist
-        keep = {int(x) for x in dev.split(",") if x.strip()}
-        jobs = [j for k, j in enumerate(jobs) if (k == 0 and "lib" in dev) or (k - 1) in keep or not os.path.exists(objs[k])]
+        toks = [x.strip() for x in dev.split(",") if x.strip()]
+        keep = {int(x) for x in toks if x.isdigit()}
+        jobs = [j for k, j in enumerate(jobs) if (k == 0 and "lib" in toks) or (k - 1) in keep or not os.path.exists(objs[k])]
     workers = int(os.environ.get("SFE_BUILD_JOBS", str(os.cpu_count() or 4)))
     with ThreadPoolExecutor(max_workers=max(1, workers)) as ex:
         list(ex.map(_run, jobs))

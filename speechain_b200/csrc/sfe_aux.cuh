@@ -85,8 +85,9 @@ __device__ __forceinline__ void moments_to_mean_std(double s1, double s2, long l
                                                     float& sd) {
   const double dn = static_cast<double>(n);
   const double m = s1 / dn;
-  // unbiased variance; n == 1 gives 0/0 = NaN like torch.std
-  double var = (s2 - s1 * m) / (dn - 1.0);
+  // unbiased variance; n == 1 gives NaN like torch.std — stated explicitly: the
+  // fixed-point sums leave a rounding residual in the numerator, and residual / 0 would be +-inf, not NaN
+  double var = (n == 1) ? __longlong_as_double(0x7ff8000000000000LL) : (s2 - s1 * m) / (dn - 1.0);
   if (var < 0.0) var = 0.0;
   float s = static_cast<float>(sqrt(var));
   if (s < clamp) s = clamp;  // NaN stays NaN, like torch.clamp

@@ -150,7 +150,11 @@ struct FftPlan {
   // the power spectrum may overwrite the FFT scratch only if no later FFT of the tile needs it
   static constexpr bool ALIAS_P2 = (S == 1);
   // one CTA per SM; warps per CTA at most (the register budget per thread follows: 85 / 128 / 255)
+#ifdef SFE_MAXW  // tuning experiments (tools/variant.py)
+  static constexpr int MAXW = SFE_MAXW;
+#else
   static constexpr int MAXW = (M_ <= 256) ? 24 : ((M_ <= 512) ? 16 : 8);
+#endif
   static constexpr int RL = (R3_ > 1) ? R3_ : R2_;               // radix of the last pass
   // the last pass leaves Z[l + G*r] in register r of lane l: the real-FFT unpack then pairs k with M-k
   // by one shuffle instead of a shared-memory round trip

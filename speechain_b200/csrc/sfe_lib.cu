@@ -287,13 +287,12 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
   const int stage_floats = round_up((FPW - 1) * cfg->hop_length + cfg->n_fft + 16, 4);
   const int z_bytes = round_up(fe->C * fe->MP * 8, 16);
   const int p2_bytes = round_up((K + MEL_PAD_BINS) * FPW * 4, 16);
-  int smem_limit = 227 * 1024, smem_sm = 228 * 1024, static_bytes = 2048;
+  int smem_limit = 227 * 1024, static_bytes = 2048;
   {
     int dev = 0;
     cudaDeviceProp pr;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&pr, dev) == cudaSuccess) {
       smem_limit = static_cast<int>(pr.sharedMemPerBlockOptin);
-      smem_sm = static_cast<int>(pr.sharedMemPerMultiprocessor);
     }
     // the opt-in limit covers static + dynamic shared memory: leave room for the kernel's static part
     cudaFuncAttributes fa;
