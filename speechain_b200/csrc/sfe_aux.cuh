@@ -216,10 +216,12 @@ __global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ 
   }
   // this utterance's time-mask intervals [lo, hi) -> shared memory (n_tmask <= 64)
   __shared__ int s_tlo[64], s_thi[64];
+  __shared__ int2 s_tiv[64];  // {first frame, length}: one unsigned compare per interval in the streaming loop
   for (int q = threadIdx.x; q < n_tmask; q += blockDim.x) {
     const int ps = m_tpos[b * n_tmask + q];
     s_tlo[q] = ps;
     s_thi[q] = ps + m_tlen[b * n_tmask + q];
+    s_tiv[q] = make_int2(ps, max(m_tlen[b * n_tmask + q], 0));
   }
   __syncthreads();
   const float fillv = p.fill_dev ? *p.fill_dev : p.fill;
@@ -245,10 +247,17 @@ __global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ 
       fv[e] = s_fm[d];
     }
     if (vec && !p.warp_on) {
-      // common case: four independent rows in flight per thread (the pass is latency bound otherwise)
-      auto finish = [&](long long t, float4 x) {
+      // common case: four independent rows in flight per thread (the pass is latency bound otherwise);
+      // 32-bit row indices, one compare per time-mask interval, 64-bit arithmetic only in the address
+      const int it1 = static_cast<int>(t1), nv = static_cast<int>(n_valid);
+      const float4* sp = reinterpret_cast<const float4*>(src) + c;
+      float4* dp = reinterpret_cast<float4*>(dst) + c;
+      auto finish = [&](int t, float4 x) {
         bool tmask = false;
-        for (int q = 0; q < n_tmask; ++q) tmask |= (t >= s_tlo[q]) && (t < s_thi[q]);
+        for (int q = 0; q < n_tmask; ++q) {
+          const int2 iv = s_tiv[q];
+          tmask |= static_cast<unsigned>(t - iv.x) < static_cast<unsigned>(iv.y);
+        }
         float* xv = reinterpret_cast<float*>(&x);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -256,23 +265,22 @@ __global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ 
           if (tmask || fv[e] != 0.f) v = fillv;
           xv[e] = v;
         }
-        __stcs(reinterpret_cast<float4*>(dst + t * D) + c, x);
+        __stcs(dp + static_cast<long long>(t) * W, x);
       };
       const float4 padv = make_float4(p.pad_value, p.pad_value, p.pad_value, p.pad_value);
       const bool synth = !p.src_has_pad;
-      long long t = t0 + r0;
-      for (; t + 3 * rows < t1; t += 4 * rows) {
+      int t = static_cast<int>(t0) + r0;
+      for (; t + 3 * rows < it1; t += 4 * rows) {
         float4 x[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const long long tt = t + u * rows;
-          x[u] = (synth && tt >= n_valid) ? padv : __ldcs(reinterpret_cast<const float4*>(src + tt * D) + c);
+          const int tt = t + u * rows;
+          x[u] = (synth && tt >= nv) ? padv : __ldcs(sp + static_cast<long long>(tt) * W);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) finish(t + u * rows, x[u]);
       }
-      for (; t < t1; t += rows)
-        finish(t, (synth && t >= n_valid) ? padv : __ldcs(reinterpret_cast<const float4*>(src + t * D) + c));
+      for (; t < it1; t += rows) finish(t, (synth && t >= nv) ? padv : __ldcs(sp + static_cast<long long>(t) * W));
       continue;
     }
     for (long long t = t0 + r0; t < t1; t += rows) {

@@ -642,10 +642,24 @@ static int normalize_impl(const float* src, float* dst, const int64_t* feat_len,
     P.warp_minlen = warp->minlen;
   }
   if (int rc = fill_masks(masks, B, &P.mk, &P.fill, &P.fill_dev)) return rc;
-  // ~32 KB of features per CTA
-  int fpc = 8192 / D;
-  if (fpc < 1) fpc = 1;
-  if (fpc > 128) fpc = 128;
+  // A CTA pays a fixed price (statistics of its utterance in fp64, per-column constants) before it streams:
+  // size the frame blocks for about SFE_NORM_CTAS_PER_SM (default 4) CTAs per SM, at least ~32 KB of features each.
+  int per_sm = 4;
+  if (const char* ev = getenv("SFE_NORM_CTAS_PER_SM")) {  // tuning knob
+    const int v = atoi(ev);
+    if (v >= 1 && v <= 64) per_sm = v;
+  }
+  int n_sm = 148;
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  long long blocks_per_utt = (static_cast<long long>(n_sm) * per_sm + B - 1) / B;
+  if (blocks_per_utt < 1) blocks_per_utt = 1;
+  long long fpc64 = (F + blocks_per_utt - 1) / blocks_per_utt;
+  const long long fmin = 8192 / D > 1 ? 8192 / D : 1;
+  if (fpc64 < fmin) fpc64 = fmin;
+  const int fpc = static_cast<int>(fpc64 > 0x3fffffff ? 0x3fffffff : fpc64);
   P.frames_per_cta = fpc;
   dim3 grid(static_cast<unsigned>((F + fpc - 1) / fpc), static_cast<unsigned>(B));
   normalize_kernel<<<grid, 256, 3 * D * sizeof(float), static_cast<cudaStream_t>(stream)>>>(P);
