@@ -96,23 +96,37 @@ __device__ __forceinline__ void moments_to_mean_std(double s1, double s2, long l
 }
 
 // mean/std (B, D) and packed [sum mean | sum std | B]                      feat_norm.py:115-133,239-266
+// A CTA owns Dc columns and cuts the utterances into S (<= blockDim / Dc) interleaved slices (thread = (slice,
+// column)); the slices' partial sums are combined in slice order, so the result does not depend on timing.
 __global__ void stats_finalize_kernel(const void* __restrict__ stats, int fixed, const long long* __restrict__ flen,
-                                      int B, int D, float clamp, float* __restrict__ mean, float* __restrict__ sd,
-                                      float* __restrict__ packed) {
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d >= D) return;
+                                      int B, int D, int Dc, int S, float clamp, float* __restrict__ mean,
+                                      float* __restrict__ sd, float* __restrict__ packed) {
+  extern __shared__ float fin_red[];  // [S][Dc][2]
+  const int sl = threadIdx.x / Dc, dl = threadIdx.x - sl * Dc;
+  const int d = blockIdx.x * Dc + dl;
   float sm = 0.f, ss = 0.f;
-  for (int b = 0; b < B; ++b) {  // rank-local sums in utterance order, like curr_means.sum(dim=0)
-    float m, s;
-    double s1, s2;
-    load_moments(stats, fixed, static_cast<long long>(b) * D + d, s1, s2);
-    moments_to_mean_std(s1, s2, flen[b], clamp, m, s);
-    if (mean) mean[static_cast<long long>(b) * D + d] = m;
-    if (sd) sd[static_cast<long long>(b) * D + d] = s;
-    sm += m;
-    ss += s;
+  if (sl < S && d < D) {
+    for (int b = sl; b < B; b += S) {
+      float m, s;
+      double s1, s2;
+      load_moments(stats, fixed, static_cast<long long>(b) * D + d, s1, s2);
+      moments_to_mean_std(s1, s2, flen[b], clamp, m, s);
+      if (mean) mean[static_cast<long long>(b) * D + d] = m;
+      if (sd) sd[static_cast<long long>(b) * D + d] = s;
+      sm += m;
+      ss += s;
+    }
   }
-  if (packed) {
+  if (sl < S) {
+    fin_red[(sl * Dc + dl) * 2] = sm;
+    fin_red[(sl * Dc + dl) * 2 + 1] = ss;
+  }
+  __syncthreads();
+  if (packed && sl == 0 && d < D) {
+    for (int j = 1; j < S; ++j) {
+      sm += fin_red[(j * Dc + dl) * 2];
+      ss += fin_red[(j * Dc + dl) * 2 + 1];
+    }
     packed[d] = sm;
     packed[D + d] = ss;
     if (d == 0) packed[2 * D] = static_cast<float>(B);

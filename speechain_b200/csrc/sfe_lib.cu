@@ -569,8 +569,14 @@ extern "C" int sfe_stats_finalize(const void* stats, int32_t stats_fixed, const 
                                   float clamp, float* mean, float* std, float* packed, void* stream) {
   if (!stats || !feat_len) return fail(SFE_ERR_BAD_ARG, "sfe_stats_finalize: NULL argument");
   if (B <= 0 || D <= 0) return fail(SFE_ERR_BAD_ARG, "sfe_stats_finalize: bad shape");
-  stats_finalize_kernel<<<(D + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      stats, stats_fixed, reinterpret_cast<const long long*>(feat_len), B, D, clamp, mean, std, packed);
+  // one CTA per 1024 columns; inside it the utterances are cut into interleaved slices (1024 / Dc of them)
+  const int Dc = D < 1024 ? D : 1024;
+  int S = 1024 / Dc;
+  if (S > B) S = B;
+  const int threads = ((S * Dc + 31) / 32) * 32;
+  stats_finalize_kernel<<<(D + Dc - 1) / Dc, threads, static_cast<size_t>(S) * Dc * 2 * sizeof(float),
+                          static_cast<cudaStream_t>(stream)>>>(
+      stats, stats_fixed, reinterpret_cast<const long long*>(feat_len), B, D, Dc, S, clamp, mean, std, packed);
   SFE_CUDA(cudaGetLastError());
   return SFE_OK;
 }
