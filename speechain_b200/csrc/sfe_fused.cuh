@@ -30,6 +30,9 @@
 #ifndef SFE_ABLATE
 #define SFE_ABLATE 0
 #endif
+#ifndef SFE_MEL_UNROLL  // tuning experiments (tools/variant.py)
+#define SFE_MEL_UNROLL 1
+#endif
 
 namespace sfe {
 
@@ -37,6 +40,7 @@ constexpr int NWARPS = 8;                 // warps per CTA of the small standalo
 constexpr int NTHREADS = NWARPS * 32;
 constexpr int FPW = 2;                    // frames per unit (per warp step)
 constexpr int MAX_MEL_ROUNDS = 16;        // phases of 32 filter units (n_mels <= 256)
+constexpr int kMelUnroll = SFE_MEL_UNROLL;
 constexpr int MEL_PAD_BINS = 4;           // zeroed bins behind the power spectrum (filter units read whole 4-tap blocks)
 constexpr int MASK_INLINE_MAX = 768;      // SFE_MASK_INLINE_MAX
 constexpr int UNIT_TABLE_MAX_B = 256;     // batches up to this size get a per-utterance cost table
@@ -810,7 +814,7 @@ __global__ void __launch_bounds__(PL::MAXW * 32, 1) fused_frontend_kernel(const 
             const float4* pp = reinterpret_cast<const float4*>(P2v + so.x);  // {bin k: frame 0, 1; bin k+1: frame 0, 1}
             const float4* wp = wl + wofs;
             float2 accA = make_float2(0.f, 0.f), accB = make_float2(0.f, 0.f);  // (frame 0, frame 1) pairs
-#pragma unroll 1
+#pragma unroll kMelUnroll
             for (int q = 0; q < n4; ++q) {
               const float4 wq = wp[q * 32];
               const float4 pa = pp[2 * q], pb = pp[2 * q + 1];
