@@ -153,11 +153,12 @@ struct FftPlan {
   static constexpr int MP = M_ + M_ / PADQ_ + 1;
   // the power spectrum may overwrite the FFT scratch only if no later FFT of the tile needs it
   static constexpr bool ALIAS_P2 = (S == 1);
-  // one CTA per SM; warps per CTA at most (the register budget per thread follows: 85 / 128 / 255)
+  // one CTA per SM; consumer warps per CTA at most, plus one producer warp: 24 / 16 / 8 warps in all (register
+  // files are per SM sub-partition, so a 25th warp would cost every thread 8 registers), 80 / 128 / 255 registers
 #ifdef SFE_MAXW  // tuning experiments (tools/variant.py)
   static constexpr int MAXW = SFE_MAXW;
 #else
-  static constexpr int MAXW = (M_ <= 256) ? 24 : ((M_ <= 512) ? 16 : 8);
+  static constexpr int MAXW = (M_ <= 256) ? 23 : ((M_ <= 512) ? 15 : 7);
 #endif
   static constexpr int RL = (R3_ > 1) ? R3_ : R2_;               // radix of the last pass
   // the last pass leaves Z[l + G*r] in register r of lane l: the real-FFT unpack then pairs k with M-k
@@ -348,7 +349,7 @@ __device__ __forceinline__ float fast_log(float x, float clampv, float lmul) {
 }
 
 template <class PL, bool PRE>
-__global__ void __launch_bounds__(PL::MAXW * 32, 1) fused_frontend_kernel(const __grid_constant__ FwdParams p) {
+__global__ void __launch_bounds__((PL::MAXW + 1) * 32, 1) fused_frontend_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int M = PL::M, G = PL::G, Q = PL::PADQ;
   // magnitude spectra (mag_spec, no shipped recipe): sqrt in one sweep after the unpack where the spectrum
@@ -356,14 +357,16 @@ __global__ void __launch_bounds__(PL::MAXW * 32, 1) fused_frontend_kernel(const 
   constexpr bool MAG_SWEEP = PL::ALIAS_P2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane / G, l = lane % G;
+  const int NW = (blockDim.x >> 5) - 1;     // consumer warps; the last warp of the CTA is the producer
+  const bool producer = (warp == NW);
 
   float* tab = reinterpret_cast<float*>(smem);
-  unsigned char* wbase = smem + p.sm_warp + warp * p.sm_warp_bytes;
+  unsigned char* wbase = smem + p.sm_warp + (producer ? 0 : warp) * p.sm_warp_bytes;
   cpx* Zw = reinterpret_cast<cpx*>(wbase) + g * PL::MP;
   float* P2 = reinterpret_cast<float*>(wbase + p.sm_p2_off);          // [k][FPW] interleaved
   float* stage = reinterpret_cast<float*>(wbase + p.sm_stage_off);    // this warp's samples
   long long* wacc = reinterpret_cast<long long*>(wbase + p.sm_acc_off);  // [D][2] fixed-point sums of the current utterance
-  const uint32_t bar = smem_u32(wbase + p.sm_bar_off);                // this warp's copy barrier
+  const uint32_t bar = smem_u32(wbase + p.sm_bar_off);                // this warp's "full" barrier ("empty" at +8)
   const uint32_t tbar = smem_u32(smem + p.sm_tbar);                   // tables
   __shared__ int s_cum[UNIT_TABLE_MAX_B + 1];  // cost coordinate at which every utterance starts
   __shared__ int s_next;                       // next chunk of this CTA's range
@@ -390,11 +393,13 @@ __global__ void __launch_bounds__(PL::MAXW * 32, 1) fused_frontend_kernel(const 
     mbar_expect_tx(tbar, bytes);
     bulk_g2s(smem_u32(tab), p.tables, bytes, tbar);
   }
-  if (lane == 0) {
-    mbar_init(bar, 1);
+  if (lane == 0 && !producer) {
+    mbar_init(bar, 1);       // "full": the unit's descriptor is written and its samples have landed
+    mbar_init(bar + 8, 1);   // "empty": the warp has consumed its staging buffer
     fence_mbar_init();
   }
-  for (int i = lane; i < 2 * D; i += 32) wacc[i] = 0;
+  if (!producer)
+    for (int i = lane; i < 2 * D; i += 32) wacc[i] = 0;
   if (blockIdx.x == 0 && p.feat_len)
     for (int b = tid; b < B; b += blockDim.x) p.feat_len[b] = frames_of(__ldg(p.len + b));
   if (tabled && warp == 0) {
@@ -437,136 +442,159 @@ __global__ void __launch_bounds__(PL::MAXW * 32, 1) fused_frontend_kernel(const 
   constexpr int EDGE_SHIFT = 4;  // gathered units leave room for the (unused) predecessor sample
 
   // ---- work distribution over the cost axis [0, ctot) ----
-  // One CTA per SM.  The axis is cut into one contiguous, equal-cost range per CTA (SMs are equally fast);
-  // inside a CTA the warps deal the range out among themselves one real unit (REAL_UNIT_COST) at a time
-  // from a shared-memory counter — a ~50-cycle atomic, no global scheduler traffic — so a warp that the
-  // hardware scheduler favours simply takes more units and the tail of an SM is one unit long.
+  // One CTA per SM.  The axis is cut into one contiguous, equal-cost range per CTA (SMs are equally fast).
+  // Inside a CTA the LAST WARP IS A PRODUCER: lane i serves consumer warp i.  Whenever warp i reports its
+  // staging buffer free, lane i takes the next real unit (REAL_UNIT_COST) of the CTA's range from a
+  // shared-memory counter, works out which utterance / frames it is, writes a 32-byte descriptor into the
+  // warp's slot and starts the bulk copy of the unit's samples onto the warp's "full" barrier.  The consumer
+  // warps carry none of that arithmetic (≈ 300 of 1300 instructions per unit) or state: they wait, read five
+  // words, and transform.  A consumer that the hardware scheduler favours simply asks more often, so the tail
+  // of an SM is one unit long.
   const int ctot = tabled ? s_cum[B] : B * upu;
   const int real_step = tabled ? REAL_UNIT_COST : 1;  // without the table every unit counts the same
   const int cta_lo = static_cast<int>(static_cast<long long>(ctot) * blockIdx.x / gridDim.x);
   const int cta_hi = static_cast<int>(static_cast<long long>(ctot) * (blockIdx.x + 1) / gridDim.x);
-  int c_hi = 0;  // end of the chunk this warp is working on
 
-  // The warp's position on the axis lives in a warp-private control block in shared memory, not in
-  // registers: it is needed only at unit boundaries, and the FFT in between has no registers to spare.
-  //   unit tu of utterance b (frames FPW*tu, FPW*tu+1) starts at cost coordinate c; the warp's chunk ends at c_hi
-  struct Ctl {
-    int b, tu, flen, nunit;   // nunit: units the utterance owns
-    int c, c_hi, live, bulk;  // bulk: a real interior unit, its samples arrive by bulk copy (else they are gathered)
-    int shift, inflight;      // staging index of the unit's first sample; its copy has been issued
-    unsigned int bytes, pad_;
-    long long len, ga;        // ga: first float of the bulk copy
+  enum { U_DONE = 0, U_PAD = 1, U_BULK = 2, U_EDGE = 3 };
+  struct Slot {               // what a consumer needs to know about its unit
+    int kind, b, tu, flen;    // frames FPW*tu, FPW*tu+1 of utterance b, which has flen frames
+    int shift, pad_;          // staging index of the unit's first sample (bulk units)
+    long long len;            // samples of the utterance (gathered units)
   };
-  static_assert(sizeof(Ctl) == 64, "control block layout");
-  Ctl* ctl = reinterpret_cast<Ctl*>(wbase + p.sm_bar_off + 16);
+  static_assert(sizeof(Slot) == 32, "slot layout");
 
-  // Moves the control block to the unit this warp works on next and starts that unit's bulk copy
-  // (`first`: nothing processed yet).  All lanes compute the same values; lane 0 stores them.
-  auto advance = [&](bool first) {
-    Ctl q;
-    q.b = -1; q.tu = 0; q.flen = 0; q.nunit = 0; q.c = 0; q.c_hi = 0; q.len = 0;
+  if (producer) {
+    // ======================= producer warp: lane i <-> consumer warp i =======================
+    if (lane >= NW) return;
+    unsigned char* cbase = smem + p.sm_warp + lane * p.sm_warp_bytes;
+    Slot* slot = reinterpret_cast<Slot*>(cbase + p.sm_bar_off + 16);
+    const uint32_t c_full = smem_u32(cbase + p.sm_bar_off), c_empty = c_full + 8;
+    const uint32_t c_stage = smem_u32(cbase + p.sm_stage_off);
+    // position on the axis: unit tu of utterance b starts at cost coordinate c; the lane's chunk ends at c_hi
+    int qb = -1, qtu = 0, qflen = 0, qnunit = 0, qc = 0, qc_hi = 0;
+    long long qlen = 0;
     auto load_utt = [&]() {
-      q.len = __ldg(p.len + q.b);
-      q.flen = clampF(frames_of(q.len));
-      q.nunit = (compact && tabled) ? (q.flen + FPW - 1) / FPW : upu;
+      qlen = __ldg(p.len + qb);
+      qflen = clampF(frames_of(qlen));
+      qnunit = (compact && tabled) ? (qflen + FPW - 1) / FPW : upu;
     };
     // step over utterances that own no unit (zero frames in compact mode) / past the end of one
     auto settle = [&]() {
-      while (q.tu >= q.nunit && q.b + 1 < B) {
-        ++q.b;
-        q.tu = 0;
+      while (qtu >= qnunit && qb + 1 < B) {
+        ++qb;
+        qtu = 0;
         load_utt();
-        if (tabled) q.c = s_cum[q.b];
+        if (tabled) qc = s_cum[qb];
       }
     };
-    bool have = false;  // q is a unit inside the warp's current chunk
-    if (!first) {
-      q.b = ctl->b; q.flen = ctl->flen; q.nunit = ctl->nunit; q.len = ctl->len;
-      q.tu = ctl->tu;
-      if (q.tu * FPW >= q.flen) {
-        // after a pad unit the chunk may hold more of them (a real unit always uses its chunk up)
-        q.c = ctl->c + 1;
-        q.c_hi = ctl->c_hi;
-        ++q.tu;
-        settle();
-        have = (q.tu < q.nunit && q.c < q.c_hi);
+    bool first = true, live = true;
+    uint32_t pe = 0u;  // parity of the consumer's "empty" barrier
+    while (live) {
+      bool ready = first;
+      if (!first) {
+        uint32_t ok;
+        asm volatile("{ .reg .pred q; mbarrier.test_wait.parity.shared::cta.b64 q, [%1], %2; selp.u32 %0, 1, 0, q; }"
+                     : "=r"(ok) : "r"(c_empty), "r"(pe) : "memory");
+        ready = (ok != 0u);
       }
-    }
-    q.live = 1;
-    while (!have) {
-      // next chunk of the CTA's range
-      int k = 0;
-      if (lane == 0)  // (plain atom.shared: atomicAdd() would wrap it in warp-aggregation code)
+      if (!ready) {
+        __nanosleep(40);
+        continue;
+      }
+      if (!first) pe ^= 1u;
+      // ---- the unit after the previous one of this consumer ----
+      bool have = false;  // (qb, qtu) is a unit inside the lane's current chunk
+      if (!first && qtu * FPW >= qflen) {
+        // after a pad unit the chunk may hold more of them (a real unit always uses its chunk up)
+        qc += 1;
+        ++qtu;
+        settle();
+        have = (qtu < qnunit && qc < qc_hi);
+      }
+      first = false;
+      while (!have) {
+        // next chunk of the CTA's range
+        unsigned int k;
         asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(k) : "r"(smem_u32(&s_next)) : "memory");
-      k = __shfl_sync(0xffffffffu, k, 0);
-      const long long lo64 = static_cast<long long>(cta_lo) + static_cast<long long>(k) * real_step;
-      if (lo64 >= cta_hi) { q.live = 0; break; }
-      const int c0 = static_cast<int>(lo64);
-      q.c_hi = min(c0 + real_step, cta_hi);
-      // first unit whose start coordinate is >= c0 (chunks move forward: usually still the same utterance)
-      if (tabled) {
-        int lo = q.b;
-        if (lo < 0 || s_cum[lo] > c0) lo = 0;
-        if (lo + 1 < B && s_cum[lo + 1] <= c0) {
-          int hi = B - 1;  // last utterance that starts at or before c0
-          ++lo;
-          while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (s_cum[mid] <= c0) lo = mid; else hi = mid - 1;
+        const long long lo64 = static_cast<long long>(cta_lo) + static_cast<long long>(k) * real_step;
+        if (lo64 >= cta_hi) { live = false; break; }
+        const int c0 = static_cast<int>(lo64);
+        qc_hi = min(c0 + real_step, cta_hi);
+        // first unit whose start coordinate is >= c0 (chunks move forward: usually still the same utterance)
+        if (tabled) {
+          int lo = qb;
+          if (lo < 0 || s_cum[lo] > c0) lo = 0;
+          if (lo + 1 < B && s_cum[lo + 1] <= c0) {
+            int hi = B - 1;  // last utterance that starts at or before c0
+            ++lo;
+            while (lo < hi) {
+              const int mid = (lo + hi + 1) >> 1;
+              if (s_cum[mid] <= c0) lo = mid; else hi = mid - 1;
+            }
+          }
+          if (lo != qb) {
+            qb = lo;
+            load_utt();
+          }
+          const int nreal = (qflen + FPW - 1) / FPW;
+          const int off = c0 - s_cum[qb];
+          const int real_cost = REAL_UNIT_COST * nreal;
+          if (off <= real_cost) {
+            qtu = (off + REAL_UNIT_COST - 1) / REAL_UNIT_COST;
+            qc = c0 - off + qtu * REAL_UNIT_COST;
+          } else {
+            qtu = nreal + (off - real_cost);
+            qc = c0;
+          }
+        } else {
+          int nb = c0 / upu;
+          if (nb >= B) nb = B - 1;
+          qtu = c0 - nb * upu;
+          qc = c0;
+          if (nb != qb) {
+            qb = nb;
+            load_utt();
           }
         }
-        if (lo != q.b) {
-          q.b = lo;
-          load_utt();
-        }
-        const int nreal = (q.flen + FPW - 1) / FPW;
-        const int off = c0 - s_cum[q.b];
-        const int real_cost = REAL_UNIT_COST * nreal;
-        if (off <= real_cost) {
-          q.tu = (off + REAL_UNIT_COST - 1) / REAL_UNIT_COST;
-          q.c = c0 - off + q.tu * REAL_UNIT_COST;
-        } else {
-          q.tu = nreal + (off - real_cost);
-          q.c = c0;
-        }
-      } else {
-        int nb = c0 / upu;
-        if (nb >= B) nb = B - 1;
-        q.tu = c0 - nb * upu;
-        q.c = c0;
-        if (nb != q.b) {
-          q.b = nb;
-          load_utt();
+        settle();
+        have = (qtu < qnunit && qc < qc_hi);
+      }
+      // ---- describe it, start its copy, publish ----
+      Slot sl;
+      sl.kind = U_DONE; sl.b = qb; sl.tu = qtu; sl.flen = qflen; sl.shift = 0; sl.pad_ = 0; sl.len = qlen;
+      bool bulk = false;
+      long long ga = 0;
+      uint32_t bytes = 0;
+      if (live) {
+        sl.kind = U_PAD;
+        if (qtu * FPW < qflen) {
+          const long long o_start = static_cast<long long>(qtu) * FPW * hop + p.off;
+          const long long o_end = o_start + static_cast<long long>(FPW - 1) * hop + win;
+          const long long row0 = static_cast<long long>(qb) * p.pitch;
+          const long long gi = row0 + o_start - pre1;
+          ga = gi & ~3LL;
+          const long long ge = (row0 + o_end + 3) & ~3LL;
+          bulk = base_aligned && (o_start - pre1 >= 0) && (o_end <= qlen) && (ge <= p.total_floats);
+          sl.shift = static_cast<int>(gi - ga) + pre1;
+          bytes = static_cast<uint32_t>((ge - ga) * 4);
+          sl.kind = bulk ? U_BULK : U_EDGE;
         }
       }
-      settle();
-      have = (q.tu < q.nunit && q.c < q.c_hi);
-    }
-    // where the unit's samples come from
-    q.bulk = 0; q.inflight = 0; q.shift = 0; q.bytes = 0; q.ga = 0; q.pad_ = 0;
-    if (q.live && q.tu * FPW < q.flen) {
-      const long long o_start = static_cast<long long>(q.tu) * FPW * hop + p.off;
-      const long long o_end = o_start + static_cast<long long>(FPW - 1) * hop + win;
-      const long long row0 = static_cast<long long>(q.b) * p.pitch;
-      const long long gi = row0 + o_start - pre1;
-      q.ga = gi & ~3LL;
-      const long long ge = (row0 + o_end + 3) & ~3LL;
-      q.bulk = (base_aligned && (o_start - pre1 >= 0) && (o_end <= q.len) && (ge <= p.total_floats)) ? 1 : 0;
-      q.shift = static_cast<int>(gi - q.ga) + pre1;
-      q.bytes = static_cast<uint32_t>((ge - q.ga) * 4);
-      q.inflight = q.bulk;
-    }
-    __syncwarp();  // every lane has read the old block
-    if (lane == 0) {
-      *ctl = q;
-      if (q.bulk) {  // the staging buffer is free (see the call sites): start the copy right away
+      *slot = sl;
+      if (bulk) {
+        // the consumer released the buffer through its "empty" barrier; order that before the async-proxy write
         fence_proxy_async();
-        mbar_expect_tx(bar, q.bytes);
-        bulk_g2s(smem_u32(stage), p.wav + q.ga, q.bytes, bar);
+        mbar_expect_tx(c_full, bytes);   // (arrive with release: the slot is visible to whoever sees the phase flip)
+        bulk_g2s(c_stage, p.wav + ga, bytes, c_full);
+      } else {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(c_full) : "memory");
       }
     }
-    __syncwarp();
-  };
+    return;
+  }
+
+  // ============================== consumer warps ==============================
+  const Slot* slot = reinterpret_cast<const Slot*>(wbase + p.sm_bar_off + 16);
   auto flush_sums = [&](int bb) {
     __syncwarp();
     for (int i = lane; i < 2 * D; i += 32) {
@@ -578,16 +606,24 @@ __global__ void __launch_bounds__(PL::MAXW * 32, 1) fused_frontend_kernel(const 
     }
     __syncwarp();
   };
+  auto release_stage = [&]() {  // every lane is past its last read of the staging buffer and of the slot
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar + 8) : "memory");
+  };
 
-  advance(true);
   uint32_t parity = 0u;
+  int prev_b = -1;
 
   while (true) {
-    // the unit being processed (the control block itself moves on in the middle of it)
-    if (!ctl->live) break;
-    const int b = ctl->b, flen = ctl->flen;
-    const int tA = ctl->tu * FPW;
-    const bool real = (tA < flen);
+    mbar_wait(bar, parity);   // descriptor written, samples landed
+    parity ^= 1u;
+    const int kind = slot->kind;
+    const int b = slot->b, flen = slot->flen;
+    const int tA = slot->tu * FPW;
+    if (p.stats && prev_b >= 0 && (kind == U_DONE || b != prev_b)) flush_sums(prev_b);
+    if (kind == U_DONE) break;
+    prev_b = b;
+    const bool real = (kind != U_PAD);
 
     if (!real) {
       // ---------------- pad unit: nothing to transform ----------------
@@ -613,18 +649,15 @@ __global__ void __launch_bounds__(PL::MAXW * 32, 1) fused_frontend_kernel(const 
         for (int i = lane; i < nfr * K; i += 32) dst[i] = p.pad_lin;
       }
       if (p.energy && lane < nfr) p.energy[static_cast<long long>(b) * F + tA + lane] = 0.f;
-      advance(false);
+      release_stage();
     } else {
       // ---------------- samples of this unit ----------------
-      const bool staged_raw = (ctl->bulk != 0);
-      const int shift = staged_raw ? ctl->shift : EDGE_SHIFT;
-      if (staged_raw) {
-        mbar_wait(bar, parity);   // (the copy was started when the control block moved here)
-        parity ^= 1u;
-      } else {
+      const bool staged_raw = (kind == U_BULK);
+      const int shift = staged_raw ? slot->shift : EDGE_SHIFT;
+      if (!staged_raw) {
         // edge unit: explicit gather with batch-level reflection, zero beyond the length and
         // pre-emphasis applied here (staging then holds the final samples)
-        const long long len = ctl->len;
+        const long long len = slot->len;
         const long long o_start = static_cast<long long>(tA) * hop + p.off;
         const float* row = p.wav + static_cast<long long>(b) * p.pitch;
         const int n = (FPW - 1) * hop + win;
@@ -652,8 +685,9 @@ __global__ void __launch_bounds__(PL::MAXW * 32, 1) fused_frontend_kernel(const 
         __syncwarp();
       }
 
-      // the unit after this one is found, and its copy started, as soon as the staging buffer is free
-      auto prefetch_next = [&]() { advance(false); };
+      // the staging buffer is handed back to the producer as soon as the first FFT pass has consumed it:
+      // the next unit's descriptor and copy are prepared under the rest of this unit
+      auto prefetch_next = [&]() { release_stage(); };
 
       // ---------------- FFT + |X|^2 of FPW frames ----------------
       float esum[PL::S];
@@ -886,8 +920,6 @@ __global__ void __launch_bounds__(PL::MAXW * 32, 1) fused_frontend_kernel(const 
       __syncwarp();  // P2 (and the scratch it may alias) is free for the next unit
     }
 
-    // ---------------- next unit ----------------
-    if (p.stats && (!ctl->live || ctl->b != b)) flush_sums(b);
   }
 }
 

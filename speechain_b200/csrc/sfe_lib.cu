@@ -318,7 +318,7 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
     P.sm_acc_off = round_up(wb, 16);
     wb = P.sm_acc_off + (D > 0 ? D : 1) * 16;
     P.sm_bar_off = round_up(wb, 16);
-    P.sm_warp_bytes = P.sm_bar_off + 16 + 64;  // mbarrier, control block
+    P.sm_warp_bytes = P.sm_bar_off + 16 + 32;  // two mbarriers, unit descriptor
   }
   // one CTA per SM with as many warps as shared memory and the plan's register budget allow
   pl->warps_per_cta = (smem_limit - P.sm_warp) / P.sm_warp_bytes;
@@ -374,7 +374,7 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
   int occ = 0;
   if (e == cudaSuccess)
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void*>(fe->fn[cfg->has_preemphasis ? 1 : 0]),
-                                                      pl->warps_per_cta * 32, pl->smem_bytes);
+                                                      (pl->warps_per_cta + 1) * 32, pl->smem_bytes);
   if (e != cudaSuccess) {
     std::string msg = std::string("sfe_plan_create: ") + cudaGetErrorString(e);
     cudaFree(pl->d_tables);
@@ -509,7 +509,7 @@ static int frontend_forward_impl(const sfe_plan* pl, const float* wav, int64_t w
   // one CTA per SM; every CTA takes an equal-cost contiguous range of the batch's units
   long long grid = static_cast<long long>(pl->n_sm) * pl->ctas_per_sm;
   if (grid > nu) grid = nu;
-  pl->fft->fn[pl->cfg.has_preemphasis ? 1 : 0]<<<static_cast<unsigned>(grid), pl->warps_per_cta * 32, pl->smem_bytes, st>>>(P);
+  pl->fft->fn[pl->cfg.has_preemphasis ? 1 : 0]<<<static_cast<unsigned>(grid), (pl->warps_per_cta + 1) * 32, pl->smem_bytes, st>>>(P);
   SFE_CUDA(cudaGetLastError());
   return SFE_OK;
 }

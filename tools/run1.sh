@@ -1,1 +1,2 @@
-REPS=2 timeout 400 bash tools/abn.sh "c2 c1" speechain_b200/csrc/libsfe.so tools/ab/libsfe_w22.so tools/ab/libsfe_mu2.so tools/ab/libsfe_mu3.so
+timeout 300 python -m pytest tests -m gpu -q -x 2>&1 | tail -4
+REPS=1 timeout 300 bash tools/abn.sh "c2 c1 c3" tools/ab/libsfe_prev.so speechain_b200/csrc/libsfe.so
