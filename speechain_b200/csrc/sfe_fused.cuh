@@ -458,7 +458,7 @@ __global__ void __launch_bounds__((PL::MAXW + 1) * 32, 1) fused_frontend_kernel(
   enum { U_DONE = 0, U_PAD = 1, U_BULK = 2, U_EDGE = 3 };
   struct Slot {               // what a consumer needs to know about its unit
     int kind, b, tu, flen;    // frames FPW*tu, FPW*tu+1 of utterance b, which has flen frames
-    int shift, pad_;          // staging index of the unit's first sample (bulk units)
+    int shift, pad_;          // staging index of the unit's first sample (bulk units); pad units in a row (pad kind)
     long long len;            // samples of the utterance (gathered units)
   };
   static_assert(sizeof(Slot) == 32, "slot layout");
@@ -578,6 +578,13 @@ __global__ void __launch_bounds__((PL::MAXW + 1) * 32, 1) fused_frontend_kernel(
           sl.shift = static_cast<int>(gi - ga) + pre1;
           bytes = static_cast<uint32_t>((ge - ga) * 4);
           sl.kind = bulk ? U_BULK : U_EDGE;
+        } else {
+          // a run of pad units of this utterance inside the chunk goes out as ONE descriptor (their rows are
+          // contiguous): a pad unit is too cheap to pay a producer round trip each
+          const int n = min(qc_hi - qc, qnunit - qtu);
+          sl.pad_ = n;
+          qtu += n - 1;
+          qc += n - 1;
         }
       }
       *slot = sl;
@@ -627,7 +634,7 @@ __global__ void __launch_bounds__((PL::MAXW + 1) * 32, 1) fused_frontend_kernel(
 
     if (!real) {
       // ---------------- pad unit: nothing to transform ----------------
-      const int nfr = min(FPW, F - tA);
+      const int nfr = min(FPW * slot->pad_, F - tA);  // rows of the whole run of pad units
       if (p.mel && !p.skip_pad) {
         float* dst = p.mel + (static_cast<long long>(b) * F + tA) * D;
         const float fillv = p.fill_dev ? *p.fill_dev : p.fill;
@@ -648,7 +655,8 @@ __global__ void __launch_bounds__((PL::MAXW + 1) * 32, 1) fused_frontend_kernel(
         float* dst = p.lin + (static_cast<long long>(b) * F + tA) * K;
         for (int i = lane; i < nfr * K; i += 32) dst[i] = p.pad_lin;
       }
-      if (p.energy && lane < nfr) p.energy[static_cast<long long>(b) * F + tA + lane] = 0.f;
+      if (p.energy)
+        for (int i = lane; i < nfr; i += 32) p.energy[static_cast<long long>(b) * F + tA + i] = 0.f;
       release_stage();
     } else {
       // ---------------- samples of this unit ----------------
