@@ -1,19 +1,23 @@
 // Fused waveform -> (log-)mel / linear spectrogram kernel for sm_100a.
 //
-// Every WARP runs its own pipeline; there is no CTA-wide barrier after the one-time setup.  The work is cut
-// into *units* of FPW = 2 consecutive frames of one utterance.  The units of the batch (utterance major;
-// units that hold only frames past an utterance's length are either skipped or cost 1/8 of a real one) are
-// split into equal-cost contiguous ranges, one per resident warp — no scheduler state, no atomics.  A warp
+// One CTA per SM: one producer warp and up to 23 consumer warps; there is no CTA-wide barrier after the
+// one-time setup.  The work is cut into *units* of FPW = 2 consecutive frames of one utterance, laid out
+// utterance-major on a cost axis (units that hold only frames past an utterance's length are either skipped
+// or cost 1/8 of a real one); every CTA owns a contiguous equal-cost range of it.
 //
-//   stages the hop + win samples its unit touches into a warp-private shared-memory buffer with ONE 1-D bulk
-//   async copy (cp.async.bulk -> UBLKCP, completion on a warp-private mbarrier); the copy of unit i+1 is
-//   issued as soon as the first FFT pass of unit i has consumed the buffer, so it flies under the rest of
-//   unit i.  Neighbouring units overlap by win - hop samples: those re-reads hit L2, HBM is read once.
-//   -> window (+ pre-emphasis on the fly) -> real FFT as an n_fft/2-point complex Stockham FFT (radix
-//   16/8/5/4/3/2 butterflies in registers, passes exchanged through a warp-private padded shared buffer)
-//   -> real-FFT unpack + |X|^2 -> banded (sparse) mel filter -> clamp/log -> [global (x-mean)/std]
-//   -> [SpecAugment masks] -> coalesced stores, plus exact fixed-point per-utterance sum / sum-of-squares
-//   accumulation for the normaliser in warp-private shared memory (flushed when the utterance changes).
+//   producer   lane i serves consumer warp i: when the warp hands its staging buffer back ("empty" mbarrier)
+//              the lane takes the next unit of the CTA's range from a shared-memory counter, writes a 32-byte
+//              descriptor into the warp's slot and starts ONE 1-D bulk async copy (cp.async.bulk -> UBLKCP)
+//              of the hop + win samples the unit touches onto the warp's "full" mbarrier.  The buffer comes
+//              back as soon as the first FFT pass of unit i has consumed it, so the copy of unit i+1 flies
+//              under the rest of unit i.  Neighbouring units overlap by win - hop samples: those re-reads
+//              hit L2, HBM is read once.
+//   consumer   window (+ pre-emphasis on the fly) -> real FFT as an n_fft/2-point complex Stockham FFT (radix
+//              16/8/5/4/3/2 butterflies in registers, passes exchanged through a warp-private padded shared
+//              buffer) -> real-FFT unpack + |X|^2 -> banded (sparse) mel filter -> clamp/log -> [global
+//              (x-mean)/std] -> [SpecAugment masks] -> coalesced stores, plus exact fixed-point per-utterance
+//              sum / sum-of-squares accumulation for the normaliser in warp-private shared memory (flushed
+//              when the utterance changes).
 //
 // Reference arithmetic replaced: speechain/module/frontend/speech2linear.py:165-245,
 // linear2mel.py:177-187 (see include/sfe.h).
