@@ -439,8 +439,9 @@ def main():
         "host": {"enqueue_ms_per_step_max_over_ranks": host_ms_max / steps, "device_ms_per_step_min_over_ranks": ms_min / steps,
                  "cpus": os.cpu_count(), "affinity": len(os.sched_getaffinity(0))},
         "e2e": {"value": total_audio * e2e_steps / (e2e_ms * 1e-3), "unit": "audio-s/s",
-                "h2d_bytes_per_step": 4 * S + 8 * B, "d2h_bytes_per_step": 8 * B, "steps": e2e_steps,
-                "note": "pinned host (B,T,1) waveforms -> ops.upload_waveforms (valid samples only) -> public API "
+                "h2d_bytes_per_step": ops.upload_bytes(wl_host) + 8 * B, "d2h_bytes_per_step": 8 * B, "steps": e2e_steps,
+                "note": "pinned host (B,T,1) waveforms -> ops.upload_waveforms (valid samples; rows of similar length "
+                        "as one pitched copy) -> public API "
                         "AcousticFrontend.forward; copy of step i+1 overlapped with step i; D2H = feature lengths "
                         "(the features stay on the GPU for the model)"},
         "gpu_launches": steps * ({"utterance": 2, "global": 4}.get((w["normalize"] or {}).get("norm_type"), 1)),

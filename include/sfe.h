@@ -193,11 +193,15 @@ int sfe_normalize(const float* src, float* dst, const int64_t* feat_len, int32_t
                   const sfe_masks* masks, void* stream);
 
 /* Ragged host->device staging of a padded waveform batch (the step before the path:
- * Model.batch_to_cuda, model/abs.py:329-352, copies the zero padding too).  Copies only the first
- * len_host[b] samples of every row from (pinned) host memory; device samples beyond a row's length
- * are left untouched — the frontend kernel never reads them.  One cudaMemcpyAsync per row. */
+ * Model.batch_to_cuda, model/abs.py:329-352, copies the zero padding too).  Copies the first
+ * len_host[b] samples of every row from (pinned) host memory; neighbouring rows of similar length
+ * (batches are sorted by length) travel as one pitched copy as wide as the longest of them while the
+ * padding dragged along stays below 1/8 of the group's bytes.  Device samples beyond a row's length
+ * may or may not be written — the frontend kernel never reads them. */
 int sfe_upload_waveforms(const float* wav_host, int64_t host_pitch, const int64_t* len_host, int32_t B,
                          float* wav_dev, int64_t dev_pitch, void* stream);
+/* Bytes sfe_upload_waveforms moves for these lengths (valid samples + the padding inside row groups). */
+int64_t sfe_upload_bytes(const int64_t* len_host, int32_t B);
 
 /* DeltaFeature.forward (delta_feat.py:57-81): (B, F, D) -> (B, F, D*(order+1)). */
 int sfe_delta(const float* feat, int32_t B, int64_t F, int32_t D, int32_t order, int32_t N,

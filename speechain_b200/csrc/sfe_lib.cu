@@ -705,16 +705,63 @@ extern "C" int sfe_chain_forward(const sfe_plan* pl, const float* wav, int64_t w
   return SFE_OK;
 }
 
+// Row groups of the ragged upload: [b, e) travels as one pitched copy of width w (see include/sfe.h).
+static bool upload_grouping() {
+  static const bool group = [] {
+    const char* ev = getenv("SFE_UPLOAD_GROUP");  // SFE_UPLOAD_GROUP=0: one copy per row
+    return !(ev && ev[0] == '0');
+  }();
+  return group;
+}
+static int upload_next_group(const int64_t* len_host, int B, int b, int64_t* width) {
+  int64_t w = len_host[b], sum = len_host[b];
+  int e = b + 1;
+  while (upload_grouping() && e < B && e - b < 64) {
+    const int64_t w2 = w > len_host[e] ? w : len_host[e], s2 = sum + len_host[e];
+    const int64_t area = w2 * (e - b + 1);
+    if (area - s2 > area / 8) break;
+    w = w2;
+    sum = s2;
+    ++e;
+  }
+  *width = w;
+  return e;
+}
+
+extern "C" int64_t sfe_upload_bytes(const int64_t* len_host, int32_t B) {
+  if (!len_host || B <= 0) return 0;
+  int64_t total = 0;
+  for (int b = 0; b < B;) {
+    int64_t w;
+    const int e = upload_next_group(len_host, B, b, &w);
+    total += w * (e - b) * static_cast<int64_t>(sizeof(float));
+    b = e;
+  }
+  return total;
+}
+
 extern "C" int sfe_upload_waveforms(const float* wav_host, int64_t host_pitch, const int64_t* len_host, int32_t B,
                                     float* wav_dev, int64_t dev_pitch, void* stream) {
   if (!wav_host || !len_host || !wav_dev || B <= 0) return fail(SFE_ERR_BAD_ARG, "sfe_upload_waveforms: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  for (int b = 0; b < B; ++b) {
-    const int64_t n = len_host[b];
-    if (n < 0 || n > host_pitch || n > dev_pitch) return fail(SFE_ERR_BAD_ARG, "sfe_upload_waveforms: length exceeds the row pitch");
-    if (n == 0) continue;
-    SFE_CUDA(cudaMemcpyAsync(wav_dev + b * dev_pitch, wav_host + b * host_pitch, static_cast<size_t>(n) * sizeof(float),
-                             cudaMemcpyHostToDevice, st));
+  for (int b = 0; b < B; ++b)
+    if (len_host[b] < 0 || len_host[b] > host_pitch || len_host[b] > dev_pitch)
+      return fail(SFE_ERR_BAD_ARG, "sfe_upload_waveforms: length exceeds the row pitch");
+  // a DMA descriptor per row costs more than the few padding samples a pitched copy of a row group drags along
+  for (int b = 0; b < B;) {
+    int64_t w;
+    const int e = upload_next_group(len_host, B, b, &w);
+    if (w > 0) {
+      if (e - b == 1)
+        SFE_CUDA(cudaMemcpyAsync(wav_dev + b * dev_pitch, wav_host + b * host_pitch, static_cast<size_t>(w) * sizeof(float),
+                                 cudaMemcpyHostToDevice, st));
+      else
+        SFE_CUDA(cudaMemcpy2DAsync(wav_dev + b * dev_pitch, static_cast<size_t>(dev_pitch) * sizeof(float),
+                                   wav_host + b * host_pitch, static_cast<size_t>(host_pitch) * sizeof(float),
+                                   static_cast<size_t>(w) * sizeof(float), static_cast<size_t>(e - b),
+                                   cudaMemcpyHostToDevice, st));
+    }
+    b = e;
   }
   return SFE_OK;
 }

@@ -365,7 +365,8 @@ def mean_all(x: torch.Tensor) -> torch.Tensor:
 
 def upload_waveforms(wav_host: torch.Tensor, len_host: torch.Tensor, out: Optional[torch.Tensor] = None,
                      device=None) -> torch.Tensor:
-    """Ragged H2D copy of a collated batch: only the valid prefix of every row crosses PCIe.
+    """Ragged H2D copy of a collated batch: only the valid prefix of every row crosses PCIe (rows of similar
+    length travel as one pitched copy, dragging along at most 1/8 of padding).
 
     wav_host (B, T, 1) or (B, T) fp32 CPU (pinned for an asynchronous copy), len_host (B,) int64 CPU.
     Returns the device tensor of the same shape; samples beyond each length are NOT initialised
@@ -381,6 +382,12 @@ def upload_waveforms(wav_host: torch.Tensor, len_host: torch.Tensor, out: Option
     with _on_device(out.device):
         _lib.check(_lib.load().sfe_upload_waveforms(wav_host.data_ptr(), T, len_host.data_ptr(), B, out.data_ptr(), T, _stream()))
     return out
+
+
+def upload_bytes(len_host: torch.Tensor) -> int:
+    """Bytes ``upload_waveforms`` moves for these lengths (valid samples + the padding inside its row groups)."""
+    len_host = len_host.long().contiguous()
+    return int(_lib.load().sfe_upload_bytes(len_host.data_ptr(), len_host.numel()))
 
 
 def mel2linear(mel: torch.Tensor, feat_len: torch.Tensor, pinv_t: torch.Tensor, *, log_mode: int, log_base: float,

@@ -149,3 +149,19 @@ def test_product_code_never_touches_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M) or "ref_port_torch" in src:
                     bad.append(os.path.join(dp, fn))
     assert not bad, bad
+
+
+def test_upload_row_groups_bound_the_padding():
+    """sfe_upload_bytes mirrors the grouping of sfe_upload_waveforms (no GPU needed): equal rows cost exactly their
+    samples, ragged rows at most 8/7 of them (a group's padding stays below 1/8 of its bytes), isolated rows nothing
+    extra."""
+    import torch
+
+    from speechain_b200.host import ops
+    assert ops.upload_bytes(torch.tensor([100, 100, 100])) == 4 * 300
+    assert ops.upload_bytes(torch.tensor([1000, 10])) == 4 * 1010          # too different: two copies
+    assert ops.upload_bytes(torch.tensor([0, 0])) == 0
+    g = torch.Generator().manual_seed(3)
+    lens = torch.tensor(sorted(torch.randint(32000, 320001, (64,), generator=g).tolist(), reverse=True))
+    valid = 4 * int(lens.sum())
+    assert valid <= ops.upload_bytes(lens) <= valid * 8 // 7 + 4
