@@ -196,7 +196,7 @@ int sfe_normalize(const float* src, float* dst, const int64_t* feat_len, int32_t
  * Model.batch_to_cuda, model/abs.py:329-352, copies the zero padding too).  Copies the first
  * len_host[b] samples of every row from (pinned) host memory; neighbouring rows of similar length
  * (batches are sorted by length) travel as one pitched copy as wide as the longest of them while the
- * padding dragged along stays below 1/8 of the group's bytes.  Device samples beyond a row's length
+ * padding dragged along stays below 1/24 of the group's bytes.  Device samples beyond a row's length
  * may or may not be written — the frontend kernel never reads them. */
 int sfe_upload_waveforms(const float* wav_host, int64_t host_pitch, const int64_t* len_host, int32_t B,
                          float* wav_dev, int64_t dev_pitch, void* stream);

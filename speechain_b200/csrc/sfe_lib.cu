@@ -714,12 +714,17 @@ static bool upload_grouping() {
   return group;
 }
 static int upload_next_group(const int64_t* len_host, int B, int b, int64_t* width) {
+  static const int den = [] {  // a group's padding stays below 1/den of its bytes (tuning knob; measured on C2: 1/3 0.57 M, 1/5 0.69 M, 1/8 0.73 M, 1/12 0.754 M, 1/24 0.755 M audio-s/s, one copy per row 0.64 M)
+    const char* ev = getenv("SFE_UPLOAD_WASTE_DEN");
+    const int v = ev ? atoi(ev) : 24;
+    return v >= 2 && v <= 1024 ? v : 24;
+  }();
   int64_t w = len_host[b], sum = len_host[b];
   int e = b + 1;
   while (upload_grouping() && e < B && e - b < 64) {
     const int64_t w2 = w > len_host[e] ? w : len_host[e], s2 = sum + len_host[e];
     const int64_t area = w2 * (e - b + 1);
-    if (area - s2 > area / 8) break;
+    if (area - s2 > area / den) break;
     w = w2;
     sum = s2;
     ++e;

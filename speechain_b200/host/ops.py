@@ -366,7 +366,7 @@ def mean_all(x: torch.Tensor) -> torch.Tensor:
 def upload_waveforms(wav_host: torch.Tensor, len_host: torch.Tensor, out: Optional[torch.Tensor] = None,
                      device=None) -> torch.Tensor:
     """Ragged H2D copy of a collated batch: only the valid prefix of every row crosses PCIe (rows of similar
-    length travel as one pitched copy, dragging along at most 1/8 of padding).
+    length travel as one pitched copy, dragging along at most 1/24 of padding).
 
     wav_host (B, T, 1) or (B, T) fp32 CPU (pinned for an asynchronous copy), len_host (B,) int64 CPU.
     Returns the device tensor of the same shape; samples beyond each length are NOT initialised

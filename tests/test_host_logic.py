@@ -153,7 +153,7 @@ def test_product_code_never_touches_the_oracle():
 
 def test_upload_row_groups_bound_the_padding():
     """sfe_upload_bytes mirrors the grouping of sfe_upload_waveforms (no GPU needed): equal rows cost exactly their
-    samples, ragged rows at most 8/7 of them (a group's padding stays below 1/8 of its bytes), isolated rows nothing
+    samples, ragged rows at most 24/23 of them (a group's padding stays below 1/24 of its bytes), isolated rows nothing
     extra."""
     import torch
 
@@ -164,4 +164,4 @@ def test_upload_row_groups_bound_the_padding():
     g = torch.Generator().manual_seed(3)
     lens = torch.tensor(sorted(torch.randint(32000, 320001, (64,), generator=g).tolist(), reverse=True))
     valid = 4 * int(lens.sum())
-    assert valid <= ops.upload_bytes(lens) <= valid * 8 // 7 + 4
+    assert valid <= ops.upload_bytes(lens) <= valid * 24 // 23 + 4

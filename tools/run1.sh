@@ -1,2 +1,7 @@
-timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "ragged_upload or native" 2>&1 | tail -2
-for g in 0 1 0 1; do SFE_UPLOAD_GROUP=$g python bench.py --workload c2 --steps 100 --warmup 10 --no-cpu 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('group $g e2e', round(d['e2e']['value']), 'h2d', d['e2e']['h2d_bytes_per_step'])"; done
+mkdir -p gpurun_out/final
+timeout 300 python -m pytest tests -m gpu -q 2>&1 | tail -2
+for wl in c2 c1 c3 c4 c5; do
+  timeout 200 python bench.py --workload $wl > gpurun_out/final/bench_$wl.json 2> gpurun_out/final/bench_$wl.err
+done
+timeout 200 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/final/bench_ref.json 2>&1
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
