@@ -69,9 +69,10 @@ class SpecAugment(Module):
                     "The number of maximum frequency masking bins cannot be larger than the feature dimension! "
                     f"self.freq_mask_width[1]={self.freq_mask_width[1]} and feat_dim={feat_dim}.")
             flen = torch.randint(self.freq_mask_width[0], self.freq_mask_width[1] + 1,
-                                 size=(batch_size, self.freq_mask_num), **kw)
-            fpos = torch.randint(0, max(1, feat_dim - flen.max().item()), size=(batch_size, self.freq_mask_num), **kw)
-            fpos, flen = fpos.numpy(), flen.numpy()
+                                 size=(batch_size, self.freq_mask_num), **kw).numpy()
+            # (the maximum through numpy: same value as flen.max().item(), a third of the host time)
+            fpos = torch.randint(0, max(1, feat_dim - int(flen.max())), size=(batch_size, self.freq_mask_num), **kw)
+            fpos = fpos.numpy()
         if self.time_mask:
             lo, hi = self.time_mask_width
             if isinstance(lo, float):
@@ -79,9 +80,9 @@ class SpecAugment(Module):
             if isinstance(hi, float):
                 hi = int(hi * time_minlen)
             hi = min(hi, time_minlen)
-            tlen = torch.randint(lo, hi + 1, size=(batch_size, self.time_mask_num), **kw)
-            tpos = torch.randint(0, max(1, time_minlen - tlen.max().item()), size=(batch_size, self.time_mask_num), **kw)
-            tpos, tlen = tpos.numpy(), tlen.numpy()
+            tlen = torch.randint(lo, hi + 1, size=(batch_size, self.time_mask_num), **kw).numpy()
+            tpos = torch.randint(0, max(1, time_minlen - int(tlen.max())), size=(batch_size, self.time_mask_num), **kw)
+            tpos = tpos.numpy()
         return warp, fpos, flen, tpos, tlen
 
     def draw_device(self, batch_size, feat_dim, feat_len_host, device, generator=None):
