@@ -101,7 +101,34 @@ class DeviceMasks:
             flat = torch.from_numpy(np.concatenate([a.ravel() for a in self._host]))
             self.buf = flat.pin_memory().to(device, non_blocking=True)
 
+    @classmethod
+    def persistent(cls, batch_size: int, n_freq: int, n_time: int):
+        """Host-resident descriptors whose int32 arrays (and ctypes struct) live as long as the object: the
+        SpecAugment draws are written straight into them every step (``views``: torch tensors sharing their
+        memory), so a step builds no arrays and no struct.  Only for batches small enough to travel inside the
+        kernel parameter block — the library copies them at launch time, before the next draw can touch them."""
+        self = cls.__new__(cls)
+        self.n_freq, self.n_time = int(n_freq), int(n_time)
+        self.fill, self.fill_dev, self.on_host, self.buf = 0.0, None, True, None
+        self._host, self.views = [], []
+        for n in (n_freq, n_freq, n_time, n_time):
+            if n:
+                a = np.zeros((batch_size, n), dtype=np.int32)
+                self._host.append(a)
+                self.views.append(torch.from_numpy(a))
+            else:
+                self.views.append(None)
+        assert sum(a.size for a in self._host) <= _lib.MASK_INLINE_MAX
+        self._struct = None
+        self._struct = self.struct()
+        return self
+
     def struct(self) -> _lib.SfeMasks:
+        m = getattr(self, "_struct", None)
+        if m is not None:  # persistent descriptors: the pointers never change
+            m.fill = self.fill
+            m.fill_dev = self.fill_dev.data_ptr() if self.fill_dev is not None else None
+            return m
         m = _lib.SfeMasks()
         if self.on_host:
             ptrs = [a.ctypes.data for a in self._host]

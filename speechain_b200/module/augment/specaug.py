@@ -86,12 +86,50 @@ class SpecAugment(Module):
         return warp, fpos, flen, tpos, tlen
 
     def draw_device(self, batch_size, feat_dim, feat_len_host, device, generator=None):
-        """Draw and upload: returns (warp, DeviceMasks or None)."""
+        """Draw and hand to the device: returns (warp, DeviceMasks or None).
+
+        Small batches (the descriptors fit the kernel parameter block) take a lean path: the same ``torch.randint``
+        calls as ``draw`` — same order, bounds and shapes, hence the same stream — write int32 straight into
+        persistent host arrays (``out=``), whose ctypes descriptor is built once.  The returned object is valid
+        until the next draw of this module."""
         minlen = int(feat_len_host.min())
-        warp, fpos, flen, tpos, tlen = self.draw(batch_size, feat_dim, minlen, generator)
-        masks = None
-        if fpos is not None or tpos is not None:
-            masks = DeviceMasks(device, fpos, flen, tpos, tlen, fill=0.0)
+        nf = self.freq_mask_num if self.freq_mask else 0
+        nt = self.time_mask_num if self.time_mask else 0
+        if generator is not None or not 0 < 2 * batch_size * (nf + nt) <= ops._lib.MASK_INLINE_MAX:
+            warp, fpos, flen, tpos, tlen = self.draw(batch_size, feat_dim, minlen, generator)
+            masks = None
+            if fpos is not None or tpos is not None:
+                masks = DeviceMasks(device, fpos, flen, tpos, tlen, fill=0.0)
+            return warp, masks
+        cache = self.__dict__.setdefault("_mask_cache", {})
+        masks = cache.get(batch_size)
+        if masks is None:
+            masks = cache[batch_size] = DeviceMasks.persistent(batch_size, nf, nt)
+        masks.fill, masks.fill_dev = 0.0, None
+        warp = None
+        if self.time_warp and minlen > 2 * self.time_warp_window + 1:
+            w = self.time_warp_window
+            center = torch.randint(low=w + 1, high=minlen - w, size=(1,))[0].item()
+            pos = torch.randint(low=center - w, high=center + w, size=(1,))[0].item()
+            warp = (center, pos, minlen)
+        t_fpos, t_flen, t_tpos, t_tlen = masks.views
+        if nf:
+            if self.feat_dim is None:
+                # latent bug of specaug.py:135-141, kept as the same error: feat_dim is never set lazily
+                assert self.feat_dim == feat_dim and self.freq_mask_width[1] < feat_dim, (
+                    "The number of maximum frequency masking bins cannot be larger than the feature dimension! "
+                    f"self.freq_mask_width[1]={self.freq_mask_width[1]} and feat_dim={feat_dim}.")
+            torch.randint(self.freq_mask_width[0], self.freq_mask_width[1] + 1, (batch_size, nf), out=t_flen)
+            torch.randint(0, max(1, feat_dim - int(masks._host[1].max())), (batch_size, nf), out=t_fpos)
+        if nt:
+            lo, hi = self.time_mask_width
+            if isinstance(lo, float):
+                lo = int(lo * minlen)
+            if isinstance(hi, float):
+                hi = int(hi * minlen)
+            hi = min(hi, minlen)
+            torch.randint(lo, hi + 1, (batch_size, nt), out=t_tlen)
+            torch.randint(0, max(1, minlen - int(masks._host[-1].max())), (batch_size, nt), out=t_tpos)
         return warp, masks
 
     def forward(self, feat: torch.Tensor, feat_len: torch.Tensor):

@@ -165,3 +165,36 @@ def test_upload_row_groups_bound_the_padding():
     lens = torch.tensor(sorted(torch.randint(32000, 320001, (64,), generator=g).tolist(), reverse=True))
     valid = 4 * int(lens.sum())
     assert valid <= ops.upload_bytes(lens) <= valid * 24 // 23 + 4
+
+
+def test_lean_draw_path_equals_reference_draw_sequence():
+    """draw_device's persistent-buffer path (int32 ``out=`` draws) consumes the CPU generator exactly like ``draw``
+    (the reference's call sequence): same warp, same intervals, step after step, for several configurations."""
+    import numpy as np
+    import torch
+
+    from speechain_b200.module.augment.specaug import SpecAugment
+    for conf in (dict(time_warp=False, freq_mask_width=30, freq_mask_num=2, time_mask_width=0.05, time_mask_num=2),
+                 dict(time_warp=True, freq_mask_width=15, freq_mask_num=4, time_mask_width=20, time_mask_num=4),
+                 dict(time_warp=True, freq_mask=False, time_mask_width=[2, 0.1], time_mask_num=3),
+                 dict(time_warp=False, time_mask=False, freq_mask_width=[3, 10], freq_mask_num=1)):
+        a, b = SpecAugment(input_size=80, **conf), SpecAugment(input_size=80, **conf)
+        rng = np.random.default_rng(1)
+        torch.manual_seed(11)
+        ref = []
+        lens = [rng.integers(40, 900, size=16) for _ in range(4)]
+        for fl in lens:
+            ref.append(a.draw(16, 80, int(fl.min())))
+        torch.manual_seed(11)
+        for fl, (warp, fpos, flen, tpos, tlen) in zip(lens, ref):
+            w2, m = b.draw_device(16, 80, fl, "cpu")
+            assert w2 == warp and m.on_host
+            got = {"fpos": m.views[0], "flen": m.views[1], "tpos": m.views[2], "tlen": m.views[3]}
+            for name, want in (("fpos", fpos), ("flen", flen), ("tpos", tpos), ("tlen", tlen)):
+                if want is None:
+                    assert got[name] is None
+                else:
+                    assert np.array_equal(got[name].numpy(), want), name
+            st = m.struct()
+            assert st.n_freq == (0 if fpos is None else fpos.shape[1]) and st.n_time == (0 if tpos is None else tpos.shape[1])
+            assert st.on_host == 1 and st.fill == 0.0
