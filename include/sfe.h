@@ -101,6 +101,18 @@ void sfe_plan_destroy(sfe_plan* plan);
 int64_t sfe_plan_num_frames(const sfe_plan* plan, int64_t T_max);
 /* dynamic shared memory per CTA and CTAs per SM of the fused kernel (for reports) */
 int  sfe_plan_query(const sfe_plan* plan, int32_t* smem_bytes, int32_t* ctas_per_sm, int32_t* n_sm);
+/* Host only (no CUDA call): which compiled straight-line Mel program of the tile kernel (sfe_melprog.h) has
+ * exactly the band structure of the filterbank `mel_weight_host` (n_mels, n_bins) — linear2mel.py:135-155 builds
+ * the matrix, :177 multiplies by it — and the weights in the layout that program reads.
+ *   meta[10] = {bank id (0: none, the gather kernel runs), n_bins, n_mels, groups per stream, first bin of
+ *               stream B, d_split, b_off, c_split, row floats, tail emits}
+ *   table    = groups * 16 floats: per 4-bin group {A bin 0 (even filter, odd filter), A bin 1 | A bin 2, A bin 3 |
+ *              B bin 0, B bin 1 | B bin 2, B bin 3}
+ * Returns the number of table floats (written if table_cap is large enough), 0 if no program matches, < 0 on a
+ * bad argument.  Exists so that program + weights can be checked against the filterbank without a GPU
+ * (tests/test_mel_schedule.py executes the generated program text). */
+int  sfe_mel_schedule(const float* mel_weight_host, int32_t n_mels, int32_t n_bins, int32_t* meta, float* table,
+                      int32_t table_cap);
 
 /* Fused waveform -> (log-)mel / linear spectrogram / energy (+ per-utterance sums).
  * Replaces Speech2LinearSpec.forward + LinearSpec2MelSpec.forward (= Speech2MelSpec.forward),

@@ -53,6 +53,7 @@ SYMBOLS = {
     "sfe_plan_destroy": (None, [_vp]),
     "sfe_plan_num_frames": (_i64, [_vp, _i64]),
     "sfe_plan_query": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
+    "sfe_mel_schedule": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _i32]),
     "sfe_frontend_forward": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                        C.POINTER(SfeMasks), _i32, _vp]),
     "sfe_chain_forward": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _f32, _i32, _i32,
@@ -93,7 +94,7 @@ def load():
         if not os.path.exists(LIB_PATH):
             raise ImportError(
                 f"{LIB_PATH} is missing: the CUDA library is not built.  Run "
-                f"`python -c 'import __graft_entry__ as g; g.build()'` (or `make -C speechain_b200/csrc`). "
+                f"`python -c 'import __graft_entry__ as g; g.build()'` (or `python -m speechain_b200.csrc.build`). "
                 f"There is no CPU or PyTorch fallback for this path.")
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in SYMBOLS.items():

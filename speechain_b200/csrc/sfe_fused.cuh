@@ -105,6 +105,11 @@ struct FwdParams {
   // per-CTA: [tables | table mbarrier | warp 0 | warp 1 | ...]; per warp: [FFT scratch (P2 may alias it) | P2 |
   // staging | sums | mbarrier]
   int sm_tbar, sm_warp, sm_warp_bytes, sm_p2_off, sm_stage_off, sm_acc_off, sm_bar_off;
+  // ---- tile kernel (sfe_tile.cuh): shared-memory carve-up (byte offsets) and the Mel emit schedule ----
+  // [tables (window, twiddles) | emit schedule | control block | stage x2 | power-spectrum tiles x2 | warp scratch]
+  int t2_ctrl, t2_stage, t2_stage_floats, t2_p2, t2_pp, t2_rowf, t2_warp, t2_warp_bytes;
+  int t2_o_sched_g, t2_sched_floats;  // float offset of the schedule in the device blob; its length
+  int ms_ng, ms_two, ms_b_ld, ms_d_split, ms_b_off, ms_c_split, ms_tail_a, ms_tail_b;  // sfe_melsched.h
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -178,7 +183,8 @@ __device__ __forceinline__ int padidx(int i) { return i + i / PADQ; }
 // One Stockham pass of radix R with P = product of the previous radices.  FIRST passes read the
 // windowed samples; the others read the warp-private Z buffer.  In place: all inputs of all
 // rounds are held in registers before anything is written.
-template <class PL, int R, int P, bool FIRST, bool VEC, bool PRE>
+// SYNC1: the samples of a FIRST pass live in the scratch the pass writes (edge units of the tile kernel).
+template <class PL, int R, int P, bool FIRST, bool VEC, bool PRE, bool SYNC1 = false>
 __device__ __forceinline__ void stockham_pass(cpx* __restrict__ Z, const cpx* __restrict__ tw, int l,
                                               const float* __restrict__ fr, const float* __restrict__ wtab,
                                               int win, float pre) {
@@ -262,7 +268,7 @@ __device__ __forceinline__ void stockham_pass(cpx* __restrict__ Z, const cpx* __
       }
     }
   }
-  if (!FIRST) __syncwarp();
+  if (!FIRST || SYNC1) __syncwarp();
 #pragma unroll
   for (int rd = 0; rd < NR; ++rd) {
     const int j = l + rd * G;

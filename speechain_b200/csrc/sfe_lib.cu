@@ -8,13 +8,17 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/sfe.h"
 #include "sfe_aux.cuh"
 #include "sfe_fused.cuh"
 #include "sfe_gl.cuh"
+#include "sfe_melsched.h"
 #include "sfe_registry.h"
 
 using namespace sfe;
@@ -55,6 +59,9 @@ struct sfe_plan {
   int smem_bytes;
   int ctas_per_sm;
   int warps_per_cta;  // warps never synchronise with each other: chosen for the most resident warps per SM
+  // tile kernel (sfe_tile.cuh): usable for this plan / its dynamic shared memory
+  int t2_ok = 0;
+  int t2_smem = 0;
   // standalone mel kernel
   int l2m_smem;
   int l2m_sm_warp, l2m_warp_bytes;
@@ -80,6 +87,38 @@ extern "C" int sfe_supported_nfft(int32_t* out, int cap) {
 
 static int round_up(int x, int a) { return (x + a - 1) / a * a; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the FUNCTION, not to a plan: several plans share a
+// kernel instance (same n_fft, different n_mels / hop; the no-mel plan recover() builds next to the training
+// plan), so the attribute is only ever raised — a later, smaller plan must not shrink it under an earlier one.
+static cudaError_t raise_dyn_smem(const void* fn, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, int> cur;  // (device, function) -> bytes granted so far
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(mu);
+  int& have = cur[std::make_pair(dev, fn)];
+  if (bytes <= have) return cudaSuccess;
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) have = bytes;
+  return e;
+}
+
+// SM count of the current device, looked up once per device (hot host path: no driver query per call)
+static int cached_sm_count() {
+  static std::mutex mu;
+  static std::map<int, int> cnt;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cnt.find(dev);
+  if (it != cnt.end()) return it->second;
+  int n = 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+  cnt[dev] = n;
+  return n;
+}
+
 extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
   if (!cfg || !out) return fail(SFE_ERR_BAD_ARG, "sfe_plan_create: NULL argument");
   *out = nullptr;
@@ -89,7 +128,7 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
   if (cfg->hop_length < 1) return fail(SFE_ERR_BAD_CONFIG, "hop_length must be >= 1");
   if (!cfg->window_host) return fail(SFE_ERR_BAD_CONFIG, "window_host is NULL");
   if (cfg->n_mels < 0 || cfg->n_mels > 32 * MAX_MEL_ROUNDS)
-    return fail(SFE_ERR_BAD_CONFIG, "n_mels must be in [0, 256]");
+    return fail(SFE_ERR_BAD_CONFIG, "n_mels must be in [0, " + std::to_string(32 * MAX_MEL_ROUNDS) + "]");
   if (cfg->n_mels > 0 && !cfg->mel_weight_host) return fail(SFE_ERR_BAD_CONFIG, "mel_weight_host is NULL");
   // the kernels take logarithms with the flush-to-zero SFU form, exact only above the smallest normal float
   if ((cfg->n_mels > 0 && cfg->mel_logging && !(cfg->mel_clamp >= FLT_MIN)) ||
@@ -280,6 +319,42 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
   align4();
   P.tab_floats = static_cast<int>(tab.size());
 
+  // ---- tile kernel: weights in its Mel program's layout (behind the blob the gather kernel copies) + carve-up ----
+  if (fe->t2[0] && D > 0) {
+    const int TS = fe->t2_ts;
+    const MelBankInfo bi = match_bank(cfg->mel_weight_host, D, K);
+    if (bi.bank != 0 && bi.bank == fe->t2_bank) {  // the filterbank has the band structure compiled for this plan
+      // a row holds the spectrum plus the zero-weight bins the program rounds up to; pitch = odd multiple of 16 bytes
+      // (one lane per row reads 128 bits at a time: conflict-free)
+      int pp = round_up(bi.ROWF, 4);
+      if (((pp / 4) & 1) == 0) pp += 4;
+      const std::vector<float> wt = program_weights(cfg->mel_weight_host, bi);
+      P.t2_o_sched_g = static_cast<int>(tab.size());
+      P.t2_sched_floats = static_cast<int>(wt.size());
+      tab.insert(tab.end(), wt.begin(), wt.end());
+      align4();
+      P.t2_pp = pp;
+      P.t2_rowf = bi.ROWF;
+      const int hop = cfg->hop_length;
+      int o = round_up((P.o_mtab + P.t2_sched_floats) * 4, 16);
+      P.t2_ctrl = o;
+      o += round_up(T2_CTRL_BYTES(TS), 16);
+      P.t2_stage = o;
+      P.t2_stage_floats = (TS - 1) * FPW * hop + round_up((FPW - 1) * hop + win + 8, 4);
+      o += 2 * P.t2_stage_floats * 4;
+      o = round_up(o, 16);
+      P.t2_p2 = o;
+      o += fe->t2_npb * (2 * TS * pp) * 4;
+      P.t2_warp = o;
+      // FFT scratch; gathered pairs also stage their samples here (a whole pair when both frames are in flight,
+      // one frame at a time otherwise)
+      const int gather_floats = (fe->C == FPW ? (FPW - 1) * hop + win : win) + 8;
+      P.t2_warp_bytes = round_up(std::max(fe->C * fe->MP * 8, gather_floats * 4), 16);
+      pl->t2_smem = P.t2_warp + fe->t2_nf * P.t2_warp_bytes;  // (only the FFT warps have a scratch)
+      pl->t2_ok = 1;
+    }
+  }
+
   // ---- shared-memory carve-up: [tables | table mbarrier | one private region per warp] ----
   // Warps never synchronise with each other, so the number of warps per CTA is free: take the one that
   // puts the most warps on an SM (big FFT plans need > 20 KB per warp).
@@ -366,11 +441,19 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
   if (e == cudaSuccess) e = cudaMemset(pl->d_acc, 0, sizeof(double));
   for (int v = 0; v < 2; ++v)
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fe->fn[v]), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               pl->smem_bytes);
+      e = raise_dyn_smem(reinterpret_cast<const void*>(fe->fn[v]), pl->smem_bytes);
+  if (e == cudaSuccess && pl->t2_ok) {
+    cudaFuncAttributes fa;
+    int t2_static = 4096;
+    if (cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(fe->t2[0])) == cudaSuccess)
+      t2_static = static_cast<int>(fa.sharedSizeBytes);
+    if (pl->t2_smem + t2_static > static_cast<int>(prop.sharedMemPerBlockOptin)) pl->t2_ok = 0;
+  }
+  for (int v = 0; v < 3; ++v)
+    if (e == cudaSuccess && pl->t2_ok)
+      e = raise_dyn_smem(reinterpret_cast<const void*>(fe->t2[v]), pl->t2_smem);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(reinterpret_cast<const void*>(&linear2mel_kernel),
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, pl->l2m_smem);
+    e = raise_dyn_smem(reinterpret_cast<const void*>(&linear2mel_kernel), pl->l2m_smem);
   int occ = 0;
   if (e == cudaSuccess)
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void*>(fe->fn[cfg->has_preemphasis ? 1 : 0]),
@@ -410,6 +493,19 @@ extern "C" int sfe_plan_query(const sfe_plan* pl, int32_t* smem_bytes, int32_t* 
   if (ctas_per_sm) *ctas_per_sm = pl->ctas_per_sm;
   if (n_sm) *n_sm = pl->n_sm;
   return SFE_OK;
+}
+
+extern "C" int sfe_mel_schedule(const float* mel_weight_host, int32_t n_mels, int32_t n_bins, int32_t* meta,
+                                float* table, int32_t table_cap) {
+  if (!mel_weight_host || !meta || n_mels <= 0 || n_bins <= 0) return -fail(SFE_ERR_BAD_ARG, "sfe_mel_schedule: bad argument");
+  const MelBankInfo bi = match_bank(mel_weight_host, n_mels, n_bins);
+  const int vals[10] = {bi.bank, bi.K, bi.D, bi.NG, bi.B_LD, bi.D_SPLIT, bi.B_OFF, bi.C_SPLIT, bi.ROWF, bi.TAIL};
+  for (int i = 0; i < 10; ++i) meta[i] = vals[i];
+  if (!bi.bank) return 0;
+  const std::vector<float> wt = program_weights(mel_weight_host, bi);
+  const int n = static_cast<int>(wt.size());
+  if (table && table_cap >= n) memcpy(table, wt.data(), sizeof(float) * n);
+  return n;
 }
 
 // validate + translate the public mask descriptor (device arrays, or host arrays copied into the
@@ -509,7 +605,25 @@ static int frontend_forward_impl(const sfe_plan* pl, const float* wav, int64_t w
   // one CTA per SM; every CTA takes an equal-cost contiguous range of the batch's units
   long long grid = static_cast<long long>(pl->n_sm) * pl->ctas_per_sm;
   if (grid > nu) grid = nu;
-  pl->fft->fn[pl->cfg.has_preemphasis ? 1 : 0]<<<static_cast<unsigned>(grid), (pl->warps_per_cta + 1) * 32, pl->smem_bytes, st>>>(P);
+  // The tile kernel (sfe_tile.cuh) serves every call with a Mel output whose filterbank could be scheduled;
+  // the gather kernel keeps the rest (linear-only plans, n_fft 2048, unaligned outputs, energy + pre-emphasis).
+  static const int force = [] {  // SFE_KERNEL=gather|tile: A/B runs
+    const char* ev = getenv("SFE_KERNEL");
+    return !ev ? 0 : (ev[0] == 'g' ? 1 : (ev[0] == 't' ? 2 : 0));
+  }();
+  const bool tile = pl->t2_ok && mel && force != 1 && !(reinterpret_cast<uintptr_t>(mel) & 15) &&
+                    !(energy && pl->cfg.has_preemphasis) &&
+                    (!norm_mean || !(reinterpret_cast<uintptr_t>(norm_mean) & 15)) &&
+                    (!norm_std || !(reinterpret_cast<uintptr_t>(norm_std) & 15));
+  if (force == 2 && !tile) return fail(SFE_ERR_BAD_ARG, "SFE_KERNEL=tile: this call cannot run on the tile kernel");
+  if (tile) {
+    long long g2 = pl->n_sm;
+    if (g2 > nu) g2 = nu;
+    const fused_fn fn = energy ? pl->fft->t2[2] : pl->fft->t2[pl->cfg.has_preemphasis ? 1 : 0];
+    fn<<<static_cast<unsigned>(g2), pl->fft->t2_nw * 32, pl->t2_smem, st>>>(P);
+  } else {
+    pl->fft->fn[pl->cfg.has_preemphasis ? 1 : 0]<<<static_cast<unsigned>(grid), (pl->warps_per_cta + 1) * 32, pl->smem_bytes, st>>>(P);
+  }
   SFE_CUDA(cudaGetLastError());
   return SFE_OK;
 }
@@ -650,16 +764,15 @@ static int normalize_impl(const float* src, float* dst, const int64_t* feat_len,
   if (int rc = fill_masks(masks, B, &P.mk, &P.fill, &P.fill_dev)) return rc;
   // A CTA pays a fixed price (statistics of its utterance in fp64, per-column constants) before it streams:
   // size the frame blocks for about SFE_NORM_CTAS_PER_SM (default 4) CTAs per SM, at least ~32 KB of features each.
-  int per_sm = 4;
-  if (const char* ev = getenv("SFE_NORM_CTAS_PER_SM")) {  // tuning knob
-    const int v = atoi(ev);
-    if (v >= 1 && v <= 64) per_sm = v;
-  }
-  int n_sm = 148;
-  {
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  }
+  static const int per_sm = [] {  // tuning knob, read once
+    int v = 4;
+    if (const char* ev = getenv("SFE_NORM_CTAS_PER_SM")) {
+      const int x = atoi(ev);
+      if (x >= 1 && x <= 64) v = x;
+    }
+    return v;
+  }();
+  const int n_sm = cached_sm_count();
   long long blocks_per_utt = (static_cast<long long>(n_sm) * per_sm + B - 1) / B;
   if (blocks_per_utt < 1) blocks_per_utt = 1;
   long long fpc64 = (F + blocks_per_utt - 1) / blocks_per_utt;
@@ -779,7 +892,7 @@ extern "C" int sfe_delta(const float* feat, int32_t B, int64_t F, int32_t D, int
   for (int i = 1; i <= N; ++i) denom += i * i;
   const long long total = static_cast<long long>(B) * F * D;
   long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > cached_sm_count() * 16LL) blocks = cached_sm_count() * 16LL;
   delta_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       feat, B, F, D, order, N, static_cast<float>(2 * denom), out);
   SFE_CUDA(cudaGetLastError());
@@ -800,8 +913,12 @@ extern "C" int sfe_mean_all(const float* x, int64_t n, float* out, void* stream)
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   long long blocks = (n + 256 * 8 - 1) / (256 * 8);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > cached_sm_count() * 8LL) blocks = cached_sm_count() * 8LL;
+  // the word is cleared on THIS call's stream: an aborted earlier call (or another stream driven by the same
+  // host thread) cannot leave it dirty
+  SFE_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), st));
   sum_all_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, n, acc);
+  SFE_CUDA(cudaGetLastError());
   mean_finish_kernel<<<1, 1, 0, st>>>(acc, n, out);
   SFE_CUDA(cudaGetLastError());
   return SFE_OK;
@@ -812,13 +929,11 @@ extern "C" int sfe_mel2linear(const float* mel, const int64_t* feat_len, int32_t
                               float* lin, void* stream) {
   if (!mel || !feat_len || !pinv_t || !lin || B < 0 || F < 0 || D <= 0 || K <= 0 || log_mode < 0 || log_mode > 2)
     return fail(SFE_ERR_BAD_ARG, "sfe_mel2linear: bad argument");
-  if (D > 32 * MAX_MEL_ROUNDS) return fail(SFE_ERR_BAD_ARG, "sfe_mel2linear: n_mels must be <= 512");
+  if (D > 32 * MAX_MEL_ROUNDS) return fail(SFE_ERR_BAD_ARG, "sfe_mel2linear: n_mels must be <= " + std::to_string(32 * MAX_MEL_ROUNDS));
   const long long n_rows = static_cast<long long>(B) * F;
   if (n_rows == 0) return SFE_OK;
   const int smem = D * M2L_ROWS * static_cast<int>(sizeof(float));
-  if (smem > 48 * 1024)
-    SFE_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(&mel2linear_kernel),
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  if (smem > 48 * 1024) SFE_CUDA(raise_dyn_smem(reinterpret_cast<const void*>(&mel2linear_kernel), smem));
   const long long grid = (n_rows + M2L_ROWS - 1) / M2L_ROWS;
   if (grid > 0x7fffffffLL) return fail(SFE_ERR_BAD_ARG, "sfe_mel2linear: too many rows");
   mel2linear_kernel<<<static_cast<unsigned>(grid), M2L_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
@@ -910,8 +1025,8 @@ extern "C" int sfe_griffinlim(sfe_plan* pl, const float* spec_in, const int64_t*
   P.sm_stage_off = round_up(fe->C * fe->MP * 8, 16);
   P.sm_warp_bytes = P.sm_stage_off + round_up(fe->C * P.stage_floats * 4, 16);
   const int smem = P.sm_warp + GL_WARPS * P.sm_warp_bytes;
-  SFE_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fe->gl_stft), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  SFE_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fe->gl_istft), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  SFE_CUDA(raise_dyn_smem(reinterpret_cast<const void*>(fe->gl_stft), smem));
+  SFE_CUDA(raise_dyn_smem(reinterpret_cast<const void*>(fe->gl_istft), smem));
   const long long groups = (P.n_frames + fe->C - 1) / fe->C;
   long long gridf = (groups + GL_WARPS - 1) / GL_WARPS;
   if (gridf > pl->n_sm * 8LL) gridf = pl->n_sm * 8LL;

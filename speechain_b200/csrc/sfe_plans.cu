@@ -23,7 +23,18 @@ SFE_PLAN_LIST(SFE_DEF_PLAN)
 template <class PL>
 static FftEntry make_entry() {
   FftEntry e{2 * PL::M, PL::WIN, PL::M, PL::G, PL::R1, PL::R2, PL::R3, PL::MP, PL::C, PL::MAXW,
-             {&fused_frontend_kernel<PL, false>, &fused_frontend_kernel<PL, true>}, nullptr, nullptr};
+             {&fused_frontend_kernel<PL, false>, &fused_frontend_kernel<PL, true>}, nullptr, nullptr,
+             {nullptr, nullptr, nullptr}, 0, 0, 0, 0, 0};
+  if constexpr (TileCfg<PL>::SUPPORTED) {
+    e.t2[0] = &tile_frontend_kernel<PL, false, false>;
+    e.t2[1] = &tile_frontend_kernel<PL, true, false>;
+    e.t2[2] = &tile_frontend_kernel<PL, false, true>;
+    e.t2_ts = TileCfg<PL>::TS;
+    e.t2_nw = TileCfg<PL>::NW;
+    e.t2_bank = TileCfg<PL>::BANK;
+    e.t2_nf = TileCfg<PL>::NF;
+    e.t2_npb = TileCfg<PL>::NPB;
+  }
   if constexpr (PL::WIN == 0) {
     e.gl_stft = &gl_stft_kernel<PL>;
     e.gl_istft = &gl_istft_kernel<PL>;

@@ -4,6 +4,7 @@
 #pragma once
 #include "sfe_fused.cuh"
 #include "sfe_gl.cuh"
+#include "sfe_tile.cuh"
 
 namespace sfe {
 
@@ -15,6 +16,9 @@ struct FftEntry {
   int M, G, R1, R2, R3, MP, C, MAXW;
   fused_fn fn[2];  // [0] no pre-emphasis, [1] pre-emphasis applied while loading
   gl_fn gl_stft, gl_istft;  // Griffin-Lim transforms (generic-window entries only)
+  // tile kernel (sfe_tile.cuh; nullptr where the plan has none): [0] plain, [1] pre-emphasis, [2] energy output
+  fused_fn t2[3];
+  int t2_ts, t2_nw, t2_bank, t2_nf, t2_npb;  // pairs per tile, warps per CTA, compiled Mel program (sfe_melprog.h), FFT warps, power-spectrum buffers
 };
 
 // (M, G, R1, R2, R3, PADQ, WIN) of every compiled plan, in registry order

@@ -55,22 +55,23 @@ class HostLengths:
     """Remembers the host copy (numpy int64) of a device length tensor so that the next module in
     the chain (normalise, SpecAugment) does not pay a device->host sync to learn min/max lengths.
 
-    Entries are keyed by tensor identity + version; a tensor that was modified in place or is
-    simply unknown falls back to one ``.cpu()`` copy."""
+    The host copy rides ON the tensor object (attribute ``_sfe_host_len``, like ``_sfe_stats``) together with
+    the tensor's version counter and data pointer: it dies with the tensor, so a fresh length tensor that
+    happens to reuse a freed tensor's ``id()`` and allocator block (what the data loader produces every step,
+    model/abs.py:329-352) can never see the previous batch's lengths.  A tensor that was modified in place,
+    re-pointed (``set_``) or is simply unknown falls back to one ``.cpu()`` copy."""
 
-    _cache: Dict[int, tuple] = {}
+    _ATTR = "_sfe_host_len"
 
     @classmethod
     def remember(cls, dev: torch.Tensor, host) -> None:
-        if len(cls._cache) > 64:
-            cls._cache.clear()
-        cls._cache[id(dev)] = (dev._version, dev.data_ptr(), host)
+        setattr(dev, cls._ATTR, (dev._version, dev.data_ptr(), host))
 
     @classmethod
     def get(cls, t: torch.Tensor) -> np.ndarray:
         if not t.is_cuda:
             return t.numpy() if t.dtype == torch.int64 else t.long().numpy()
-        hit = cls._cache.get(id(t))
+        hit = getattr(t, cls._ATTR, None)
         if hit is not None and hit[0] == t._version and hit[1] == t.data_ptr():
             return hit[2]
         host = t.cpu().long().numpy()

@@ -198,3 +198,35 @@ def test_lean_draw_path_equals_reference_draw_sequence():
             st = m.struct()
             assert st.n_freq == (0 if fpos is None else fpos.shape[1]) and st.n_time == (0 if tpos is None else tpos.shape[1])
             assert st.on_host == 1 and st.fill == 0.0
+
+
+def test_host_length_cache_dies_with_its_tensor():
+    """A length tensor built fresh every step (model/abs.py:329-352) may reuse the id(), the allocator block and
+    the version counter of the previous step's tensor: the cached host lengths must not survive that."""
+    from speechain_b200.host.ops import HostLengths
+
+    class FakeCuda:  # the attributes HostLengths looks at, without a device
+        is_cuda, _version = True, 0
+
+        def __init__(self, values):
+            self.values = values
+
+        def data_ptr(self):
+            return 0x7F0000000000  # the caching allocator hands the same block back
+
+        def cpu(self):
+            return torch.tensor(self.values)
+
+    a = FakeCuda([5, 4, 3])
+    HostLengths.remember(a, np.array([5, 4, 3]))
+    assert HostLengths.get(a).tolist() == [5, 4, 3]
+    del a
+    b = FakeCuda([9, 8, 7])  # may well sit at the same id(); same data_ptr and version
+    assert HostLengths.get(b).tolist() == [9, 8, 7]
+    # an in-place edit or a re-pointed tensor invalidates the copy
+    b._version = 1
+    b.values = [1, 1, 1]
+    assert HostLengths.get(b).tolist() == [1, 1, 1]
+    # real tensors: the copy rides on the object
+    t = torch.tensor([3, 2, 1])
+    assert HostLengths.get(t).tolist() == [3, 2, 1]
