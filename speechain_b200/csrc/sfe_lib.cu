@@ -326,8 +326,7 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
     if (bi.bank != 0 && bi.bank == fe->t2_bank) {  // the filterbank has the band structure compiled for this plan
       // a row holds the spectrum plus the zero-weight bins the program rounds up to; pitch = odd multiple of 16 bytes
       // (one lane per row reads 128 bits at a time: conflict-free)
-      int pp = round_up(bi.ROWF, 4);
-      if (((pp / 4) & 1) == 0) pp += 4;
+      const int pp = t2_row_pitch(bi.ROWF);
       const std::vector<float> wt = program_weights(cfg->mel_weight_host, bi);
       P.t2_o_sched_g = static_cast<int>(tab.size());
       P.t2_sched_floats = static_cast<int>(wt.size());
@@ -336,21 +335,21 @@ extern "C" int sfe_plan_create(const sfe_config* cfg, sfe_plan** out) {
       P.t2_pp = pp;
       P.t2_rowf = bi.ROWF;
       const int hop = cfg->hop_length;
+      // [tables | Mel weights | control block | NPB power-spectrum tiles | per FFT warp: FFT scratch, "samples
+      //  landed" barrier, staging buffer]
       int o = round_up((P.o_mtab + P.t2_sched_floats) * 4, 16);
       P.t2_ctrl = o;
       o += round_up(T2_CTRL_BYTES(TS), 16);
-      P.t2_stage = o;
-      P.t2_stage_floats = (TS - 1) * FPW * hop + round_up((FPW - 1) * hop + win + 8, 4);
-      o += 2 * P.t2_stage_floats * 4;
-      o = round_up(o, 16);
       P.t2_p2 = o;
       o += fe->t2_npb * (2 * TS * pp) * 4;
       P.t2_warp = o;
-      // FFT scratch; gathered pairs also stage their samples here (a whole pair when both frames are in flight,
-      // one frame at a time otherwise)
+      // gathered pairs stage their samples in the FFT scratch (a whole pair when both frames are in flight, one
+      // frame at a time otherwise)
       const int gather_floats = (fe->C == FPW ? (FPW - 1) * hop + win : win) + 8;
-      P.t2_warp_bytes = round_up(std::max(fe->C * fe->MP * 8, gather_floats * 4), 16);
-      pl->t2_smem = P.t2_warp + fe->t2_nf * P.t2_warp_bytes;  // (only the FFT warps have a scratch)
+      P.t2_stage = round_up(std::max(fe->C * fe->MP * 8, gather_floats * 4), 16);  // offset of the barrier in a warp's region
+      P.t2_stage_floats = round_up((FPW - 1) * hop + win + 8, 4);
+      P.t2_warp_bytes = P.t2_stage + 16 + P.t2_stage_floats * 4;
+      pl->t2_smem = P.t2_warp + fe->t2_nf * P.t2_warp_bytes;
       pl->t2_ok = 1;
     }
   }
@@ -611,7 +610,7 @@ static int frontend_forward_impl(const sfe_plan* pl, const float* wav, int64_t w
     const char* ev = getenv("SFE_KERNEL");
     return !ev ? 0 : (ev[0] == 'g' ? 1 : (ev[0] == 't' ? 2 : 0));
   }();
-  const bool tile = pl->t2_ok && mel && force != 1 && !(reinterpret_cast<uintptr_t>(mel) & 15) &&
+  const bool tile = pl->t2_ok && mel && force != 1 && T_max < 0x7fffffffLL && !(reinterpret_cast<uintptr_t>(mel) & 15) &&
                     !(energy && pl->cfg.has_preemphasis) &&
                     (!norm_mean || !(reinterpret_cast<uintptr_t>(norm_mean) & 15)) &&
                     (!norm_std || !(reinterpret_cast<uintptr_t>(norm_std) & 15));

@@ -45,3 +45,27 @@ static FftEntry make_entry() {
 FftEntry SFE_CAT(sfe_plan_entry_, SFE_PLAN_TU)() { return make_entry<PlanOf<SFE_PLAN_TU>::type>(); }
 
 }  // namespace sfe
+
+#if defined(SFE_T2_TRACE)
+// development only: copy the trace of the tile kernel out (tools/trace_tile.py)
+extern "C" int sfe_debug_trace(unsigned long long* t, unsigned int* tag, int cap) {
+  unsigned int n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, sfe::g_t2_trace_n, sizeof(n));
+  if (n > (1u << 15)) n = 1u << 15;
+  if (static_cast<int>(n) > cap) n = cap;
+  cudaMemcpyFromSymbol(t, sfe::g_t2_trace_t, sizeof(unsigned long long) * n);
+  cudaMemcpyFromSymbol(tag, sfe::g_t2_trace_tag, sizeof(unsigned int) * n);
+  const unsigned int zero = 0;
+  cudaMemcpyToSymbol(sfe::g_t2_trace_n, &zero, sizeof(zero));
+  return static_cast<int>(n);
+}
+#endif
+
+#if defined(SFE_T2_PROF)
+extern "C" int sfe_debug_prof(long long* out) {  // development only (tools/prof_tile.py)
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, sfe::g_t2_prof, sizeof(long long) * 32 * 16);
+  return 0;
+}
+#endif

@@ -1,35 +1,72 @@
 // Tile variant of the fused waveform -> (log-)mel kernel for sm_100a: the kernel of the shipped recipes.
 //
 // Same arithmetic as sfe_fused.cuh up to the power spectrum (window, pre-emphasis, Stockham FFT, real-FFT
-// unpack).  What changes is WHO does the Mel stage and HOW the work flows: one CTA per SM, warp-specialised,
-// every hand-over an mbarrier, no CTA-wide barrier after the set-up:
+// unpack).  What changes is WHO does the Mel stage: one CTA per SM, warp-specialised, every hand-over an
+// mbarrier, no CTA-wide barrier after the set-up:
 //
-//   tiles        A CTA walks its contiguous, equal-cost range of 2-frame units ("pairs") in TILES of TS pairs.
-//   producer     (1 warp) describes tile j — one lane per pair: utterance, frames, kind — and starts the bulk
-//                async copies (cp.async.bulk -> UBLKCP) of its samples into stage buffer j & 1 as soon as the
-//                FFT warps have read tile j - 2 out of it: 2*hop samples per pair plus the overlap tail of the
-//                last one, so HBM is read once with no overlap re-reads inside a tile.  Pairs that touch the
-//                batch-level reflection, the end of their utterance, or another utterance than the tile's
-//                first are gathered by their FFT warp instead, exactly like in sfe_fused.cuh.
-//   FFT warps    (16) claim pairs from a shared counter; pair s of tile j: window (+ pre-emphasis) -> FFT ->
-//                unpack -> |X|^2 into ROWS 2s, 2s+1 of power-spectrum buffer j % NPB.
-//   Mel warps    (NPB, one per power-spectrum buffer) take a complete tile and run the Mel stage for all 2*TS
-//                frames at once with ONE LANE PER FRAME: the lane walks the bins of its row in order with one
-//                packed FMA per bin into an (even filter, odd filter) accumulator pair and stores a filter when
-//                its last bin is in — straight-line code generated for the recipe's filterbank
-//                (sfe_melprog.h): no flag test, no branch, no address arithmetic; the weights are one
-//                broadcast 128-bit load per two bins; no lane idles on a narrow filter.  The gather-style Mel
-//                stage of sfe_fused.cuh spent 290 of its 960 instructions per pair here, ~90 % of them address
-//                arithmetic and predicates; this one ~50.  Then the read-out: two rows per step, 16 lanes per
-//                row, logarithm, per-utterance sums, optional (x-mean)/std and SpecAugment masks, 128-bit
-//                coalesced stores.
+//   FFT warps    (NF) claim the CTA's 2-frame units ("pairs") one by one from a shared counter.  A warp stages the
+//                samples of its NEXT pair itself — ONE 1-D bulk async copy (cp.async.bulk -> UBLKCP) into its
+//                private staging buffer, issued right after the first FFT pass of the current pair has
+//                consumed the buffer, so that it lands under the rest of the pair; pairs that touch the
+//                batch-level reflection or the end of their utterance are gathered by the warp instead.
+//                Window (+ pre-emphasis) -> FFT -> unpack -> |X|^2 goes into ROWS 2s, 2s+1 of a CTA-wide TILE of
+//                TS pairs (pair q of the CTA: tile q / TS, slot s = q % TS, buffer tile % NPB).
+//                (A shared ring of stage buffers filled by a producer warp was measured first: the round trip
+//                buffer drained -> producer woken -> copy issued -> samples landed -> FFT warps woken took
+//                longer than the FFT of the buffered pairs, 33 us for C1 with the Mel stage switched off.)
+//   Mel warps    (NPB, one per tile buffer) take a complete tile and run the Mel stage for all 2*TS frames at
+//                once with ONE LANE PER FRAME: the lane walks the bins of its row in order with one packed FMA
+//                per bin into an (even filter, odd filter) accumulator pair and stores a filter when its last
+//                bin is in — straight-line code generated for the recipe's filterbank (sfe_melprog.h): no flag
+//                test, no branch, no address arithmetic; the weights are one broadcast 128-bit load per two
+//                bins; no lane idles on a narrow filter.  The gather-style Mel stage of sfe_fused.cuh spent 290
+//                of its 960 instructions per pair here, ~90 % of them address arithmetic and predicates; this
+//                one ~50.  Then the read-out: two rows per step, 16 lanes per row, logarithm, per-utterance
+//                sums, optional (x-mean)/std and SpecAugment masks, 128-bit coalesced stores.
 //
 // Reference arithmetic replaced: speechain/module/frontend/speech2linear.py:165-245, linear2mel.py:177-187.
 #pragma once
 #include "sfe_fused.cuh"
 #include "sfe_melprog.h"
 
+// Timing experiments only (tools/variant.py), never defined in the shipped build: 1 Mel warps hand their tiles back
+// untouched, 2 additionally the FFT warps skip their transform, 3 FFT warps skip the transform but the Mel stage runs.
+#ifndef SFE_T2_ABLATE
+#define SFE_T2_ABLATE 0
+#endif
+
 namespace sfe {
+
+// Development only (tools/trace_tile.py): -DSFE_T2_TRACE records (tag, warp, index, globaltimer) events of CTA 0.
+#ifdef SFE_T2_TRACE
+__device__ unsigned long long g_t2_trace_t[1 << 15];
+__device__ unsigned int g_t2_trace_tag[1 << 15];
+__device__ unsigned int g_t2_trace_n;
+__device__ __forceinline__ void t2_trace(int tag, int idx) {
+  if (blockIdx.x != 0 || (threadIdx.x & 31) != 0) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  const unsigned int i = atomicAdd(&g_t2_trace_n, 1u);
+  if (i < (1u << 15)) {
+    g_t2_trace_t[i] = t;
+    g_t2_trace_tag[i] = (static_cast<unsigned>(tag) << 24) | ((threadIdx.x >> 5) << 16) | (static_cast<unsigned>(idx) & 0xffffu);
+  }
+}
+#define SFE_TR(tag, idx) t2_trace(tag, idx)
+#else
+#define SFE_TR(tag, idx)
+#endif
+// -DSFE_T2_PROF: per-warp cycle totals of the phases of CTA 0 (registers only while running)
+#ifdef SFE_T2_PROF
+__device__ long long g_t2_prof[32 * 16];
+#define SFE_PF_DECL long long pf_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long pf_t = clock64();
+#define SFE_PF(k) { const long long t_ = clock64(); pf_acc[k] += t_ - pf_t; pf_t = t_; }
+#define SFE_PF_DUMP(w) if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) { for (int k_ = 0; k_ < 12; ++k_) g_t2_prof[(w) * 16 + k_] = pf_acc[k_]; }
+#else
+#define SFE_PF_DECL
+#define SFE_PF(k)
+#define SFE_PF_DUMP(w)
+#endif
 
 template <int BANK> struct MelBank { typedef void type; };
 template <> struct MelBank<1> { typedef melprog::Bank1 type; };
@@ -45,15 +82,21 @@ struct TileCfg {
                             : (PL::M == 512 && PL::WIN == 1024) ? 3 : 0;
   static constexpr bool SUPPORTED = (BANK != 0);
   static constexpr int TS = (PL::M <= 256) ? 16 : 8;   // pairs per tile: 2*TS rows, one lane per row in the Mel stage
+#ifdef SFE_T2_NPB  // tuning experiments (tools/variant.py)
+  static constexpr int NPB = SFE_T2_NPB;
+#else
   static constexpr int NPB = (PL::M <= 256) ? 3 : 2;   // power-spectrum buffers = Mel warps
+#endif
 #ifdef SFE_T2_NF  // tuning experiments (tools/variant.py)
   static constexpr int NF = SFE_T2_NF;
 #else
-  static constexpr int NF = 16;                        // FFT warps
+  static constexpr int NF = (PL::M <= 256) ? 17 : 14;  // FFT warps (n_fft 1024: 9.5 KB of scratch + staging per warp)
 #endif
-  static constexpr int NW = NF + 1 + NPB;              // + producer + Mel warps: <= 5 warps per SM sub-partition, 96 registers
+  static constexpr int NW = NF + NPB;                  // + Mel warps: 20 = 5 warps per SM sub-partition at <= 96 registers
 };
-constexpr int T2_ROWQ = 8;  // tiles whose row descriptors are kept (the producer runs ahead of the Mel warps)
+// Row pitch of a power-spectrum tile: the spectrum plus the zero-weight bins its Mel program rounds up to, an ODD
+// multiple of 16 bytes (one lane per row reads 128 bits at a time: conflict-free).
+__host__ __device__ constexpr int t2_row_pitch(int rowf) { return (((rowf + 3) / 4) & 1) ? (rowf + 3) / 4 * 4 : (rowf + 3) / 4 * 4 + 4; }
 
 // Waiting warps must not eat the issue slots of the warps they wait for: sleep between polls.
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
@@ -75,17 +118,31 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-struct T2Slot {  // a pair as its FFT warp sees it
-  int kind, b, tu, flen;  // frames 2*tu, 2*tu+1 of utterance b, which has flen frames
-  int soff, pad_;         // bulk pairs: index of the pair's first sample in the stage buffer
-  long long len;          // samples of the utterance (gathered pairs)
-};
-struct T2Row {  // a pair as the Mel stage sees it
+struct T2Row {  // a pair as the Mel stage sees it: frames tA, tA+1 of utterance b, which has flen frames
   int b, tA, flen, kind;
 };
-static_assert(sizeof(T2Slot) == 32 && sizeof(T2Row) == 16, "descriptor layout");
-// control block: barriers and counters (128 bytes), slots[2][TS], rows[T2_ROWQ][TS]
-constexpr int T2_CTRL_BYTES(int TS) { return 128 + 2 * TS * 32 + T2_ROWQ * TS * 16; }
+static_assert(sizeof(T2Row) == 16, "descriptor layout");
+// control block: barriers and counters (96 bytes), rows[3][TS]
+constexpr int T2_CTRL_BYTES(int TS) { return 96 + 3 * TS * 16; }
+
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase flips (or ~1 us passes) — it
+// neither eats the issue slots of the warps it waits for nor adds a polling interval to the hand-over
+#ifndef SFE_T2_WAIT  // tuning experiments: 0 plain try_wait loop, 1 sleep between polls, 2 hardware suspend hint
+#define SFE_T2_WAIT 2
+#endif
+__device__ __forceinline__ void mbar_wait_hint(uint32_t bar, uint32_t parity) {
+  if (SFE_T2_WAIT == 0) { mbar_wait(bar, parity); return; }
+  if (SFE_T2_WAIT == 1) { mbar_wait_backoff(bar, parity); return; }
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 1000;\n"
+      "@!p bra WAIT_%=;\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
 
 template <class PL, bool PRE, bool ENERGY>
 __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(const __grid_constant__ FwdParams p) {
@@ -99,25 +156,22 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
   float* tab = reinterpret_cast<float*>(smem);
   unsigned char* ctrl = smem + p.t2_ctrl;
   const uint32_t tbar = smem_u32(ctrl);          // tables landed
-  const uint32_t full0 = smem_u32(ctrl + 8);     // [2]   stage buffer holds its tile (descriptors + samples)   producer -> FFT
-  const uint32_t sfree0 = smem_u32(ctrl + 24);   // [2]   every pair of the tile has read its samples            FFT -> producer
-  const uint32_t pfull0 = smem_u32(ctrl + 40);   // [NPB] every pair of the tile has stored its rows             FFT -> Mel
-  const uint32_t pfree0 = smem_u32(ctrl + 64);   // [NPB] the Mel stage has consumed the buffer                  Mel -> FFT
-  int* s_misc = reinterpret_cast<int*>(ctrl + 88);  // [0] next pair of the CTA, [1] first pair, [2] number of pairs
-  // A barrier's phase bit cannot tell tile j from the tile two rounds later on the same buffer, and claims are only
-  // a counter — FFT warps may race ahead of a slow one: they also check WHICH tile a buffer holds / may take.
-  volatile int* stile = reinterpret_cast<volatile int*>(ctrl + 104);  // [2]   tile whose samples stage buffer sb holds
-  volatile int* pgen = stile + 2;                                      // [NPB] tile that may write buffer pb next
-  T2Slot* slots = reinterpret_cast<T2Slot*>(ctrl + 128);                // [2][TS]
-  T2Row* rows = reinterpret_cast<T2Row*>(ctrl + 128 + 2 * TS * 32);     // [T2_ROWQ][TS]
-  float* stage0 = reinterpret_cast<float*>(smem + p.t2_stage);
+  const uint32_t pfull0 = smem_u32(ctrl + 8);    // [NPB] every pair of the tile has stored its rows    FFT -> Mel
+  const uint32_t pfree0 = smem_u32(ctrl + 32);   // [NPB] the Mel stage has consumed the buffer         Mel -> FFT
+  int* s_misc = reinterpret_cast<int*>(ctrl + 56);  // [0] next pair of the CTA, [1] first pair, [2] number of pairs
+  // A barrier's phase bit cannot tell a tile from the one two rounds later on the same buffer, and claims are only
+  // a counter — FFT warps may race ahead of a slow one: they also check WHICH tile may write a buffer.
+  volatile int* pgen = reinterpret_cast<volatile int*>(ctrl + 72);   // [NPB] tile that may write buffer pb next
+  T2Row* rows = reinterpret_cast<T2Row*>(ctrl + 96);                  // [NPB][TS]
   float* p2_0 = reinterpret_cast<float*>(smem + p.t2_p2);
   __shared__ int s_cum[UNIT_TABLE_MAX_B + 1];  // cost coordinate at which every utterance starts
   __shared__ int s_pc[UNIT_TABLE_MAX_B + 1];   // pair index at which every utterance starts
+  __shared__ int s_len[UNIT_TABLE_MAX_B];      // samples of every utterance (the host keeps longer inputs on the gather kernel)
+  __shared__ int s_flen[UNIT_TABLE_MAX_B];     // frames of every utterance
 
   const int hop = p.hop, win = p.win, K = p.K, F = p.F, B = p.B;
   const int upu = p.units_per_utt;
-  const int PP = p.t2_pp;
+  constexpr int PP = t2_row_pitch(MelBank<TileCfg<PL>::BANK>::type::ROWF);
   const bool compact = p.skip_pad && !p.lin && !p.energy;  // pairs past an utterance's last frame are not enumerated
   const bool tabled = (B <= UNIT_TABLE_MAX_B);
   auto frames_of = [&](long long len) -> long long {
@@ -131,12 +185,7 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
   // ---- one-time set-up ----
   if (tid == 0) {
     s_misc[0] = 0;
-    stile[0] = stile[1] = -1;
     mbar_init(tbar, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(full0 + 8 * i, 1);
-      mbar_init(sfree0 + 8 * i, TS);
-    }
     for (int i = 0; i < NPB; ++i) {
       pgen[i] = i;
       mbar_init(pfull0 + 8 * i, TS);
@@ -153,6 +202,10 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
     const int r = i / (p.t2_rowf - K), c = i - r * (p.t2_rowf - K);
     p2_0[r * PP + K + c] = 0.f;
   }
+  if (warp < NF && lane == 0) {  // every FFT warp's "samples landed" barrier
+    mbar_init(smem_u32(smem + p.t2_warp + warp * p.t2_warp_bytes + p.t2_stage), 1);
+    fence_mbar_init();
+  }
   if (blockIdx.x == 0 && p.feat_len)
     for (int b = tid; b < B; b += blockDim.x) p.feat_len[b] = frames_of(__ldg(p.len + b));
   if (warp == 0) {
@@ -164,7 +217,11 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
         const int b = b0 + lane;
         int c = 0, n = 0;
         if (b < B) {
-          const int nr = (clampF(frames_of(__ldg(p.len + b))) + FPW - 1) / FPW;
+          const long long len = __ldg(p.len + b);
+          s_len[b] = static_cast<int>(len);
+          const int fl = clampF(frames_of(len));
+          s_flen[b] = fl;
+          const int nr = (fl + FPW - 1) / FPW;
           n = compact ? nr : upu;
           c = REAL_UNIT_COST * nr + (n - nr);
         }
@@ -207,6 +264,10 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
       }
       s_misc[1] = plo;
       s_misc[2] = phi - plo;
+      int b0 = 0;  // utterance of the CTA's first pair: where every FFT warp starts looking
+      if (tabled)
+        while (b0 + 1 < B && s_pc[b0 + 1] <= plo) ++b0;
+      s_misc[3] = b0;
     }
   }
   __syncthreads();  // barrier inits, the tables of the work split and this CTA's range are visible
@@ -214,94 +275,11 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
   const int P_lo = s_misc[1], npairs = s_misc[2];
   const int ntiles = (npairs + TS - 1) / TS;
 
-  if (warp == NF) {
-    // =========================================== producer warp ===========================================
-    const int stage_floats = p.t2_stage_floats;
-    const bool bulk_ok = ((reinterpret_cast<uintptr_t>(p.wav) & 15) == 0) && ((hop & 1) == 0);
-    for (int j = 0; j < ntiles; ++j) {
-      const int sb = j & 1;
-      if (j >= 2) mbar_wait_backoff(sfree0 + 8 * sb, static_cast<uint32_t>(((j >> 1) - 1) & 1));
-      // describe tile j, one lane per pair
-      const int nsl = min(TS, npairs - j * TS);
-      T2Slot sl;
-      sl.kind = U_DONE; sl.b = 0; sl.tu = 0; sl.flen = 0; sl.soff = 0; sl.pad_ = 0; sl.len = 0;
-      bool elig = false;
-      long long ga = 0;
-      int need = 0, shiftfull = 0;
-      if (lane < nsl) {
-        const int P = P_lo + j * TS + lane;
-        if (tabled) {
-          int lo = 0, hi = B - 1;  // smallest b whose pairs end beyond P
-          while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (s_pc[mid + 1] > P) hi = mid; else lo = mid + 1;
-          }
-          sl.b = lo;
-          sl.tu = P - s_pc[lo];
-        } else {
-          sl.b = P / upu;
-          sl.tu = P - sl.b * upu;
-        }
-        sl.len = __ldg(p.len + sl.b);
-        sl.flen = clampF(frames_of(sl.len));
-        sl.kind = U_PAD;
-        if (sl.tu * FPW < sl.flen) {
-          sl.kind = U_EDGE;
-          const long long o_start = static_cast<long long>(sl.tu) * FPW * hop + p.off;
-          const long long o_end = o_start + static_cast<long long>(FPW - 1) * hop + win;
-          const long long gi = static_cast<long long>(sl.b) * p.pitch + o_start - pre1;
-          ga = gi & ~3LL;
-          shiftfull = static_cast<int>(gi - ga) + pre1;
-          need = (shiftfull + (FPW - 1) * hop + win + 3) & ~3;  // floats from ga that cover the pair
-          elig = bulk_ok && (o_start - pre1 >= 0) && (o_end <= sl.len) && (ga + need <= p.total_floats);
-        }
-      }
-      // bulk pairs: ONE contiguous run of pairs of ONE utterance per tile (their samples are contiguous in HBM
-      // and in the stage buffer: pair s at s * 2 hop); everything else is gathered by its FFT warp
-      unsigned m = __ballot_sync(FULLM, elig);
-      uint32_t bytes = 0;
-      if (m) {
-        const int f = __ffs(m) - 1;
-        const int bstar = __shfl_sync(FULLM, sl.b, f);
-        elig = elig && (sl.b == bstar);
-        m = __ballot_sync(FULLM, elig);
-        const unsigned run = m & ~(m + (1u << f));
-        elig = (run >> lane) & 1u;
-        if (elig) {
-          const int last = 31 - __clz(run);
-          sl.kind = U_BULK;
-          sl.soff = lane * FPW * hop + shiftfull;
-          bytes = static_cast<uint32_t>((lane == last ? need : FPW * hop) * 4);
-        }
-      }
-      uint32_t total = bytes;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(FULLM, total, o);
-      if (lane < nsl) {
-        slots[sb * TS + lane] = sl;
-        T2Row rd;
-        rd.b = sl.b; rd.tA = sl.tu * FPW; rd.flen = sl.flen; rd.kind = sl.kind;
-        rows[(j & (T2_ROWQ - 1)) * TS + lane] = rd;
-      }
-      __syncwarp();
-      if (lane == 0) {
-        stile[sb] = j;
-        mbar_expect_tx(full0 + 8 * sb, total);  // arrive (release): the descriptors are visible to whoever sees the phase flip
-      }
-      __syncwarp();
-      if (elig) {
-        fence_proxy_async();  // the buffer's previous readers are done (sfree): order that before the async-proxy writes
-        bulk_g2s(smem_u32(stage0 + sb * stage_floats + lane * FPW * hop), p.wav + ga, bytes, full0 + 8 * sb);
-      }
-    }
-    return;
-  }
-
   mbar_wait(tbar, 0u);  // tables have landed
 
-  if (warp > NF) {
-    // ============================== Mel warps: warp NF + 1 + pb owns buffer pb ==============================
-    const int pb = warp - NF - 1;
+  if (warp >= NF) {
+    // ================================ Mel warps: warp NF + pb owns buffer pb ================================
+    const int pb = warp - NF;
     float* p2buf = p2_0 + pb * p2_floats;
     const float4* wprog = reinterpret_cast<const float4*>(tab + p.o_mtab);  // Mel weights in the program's layout
     const int n_fmask = p.mk.n_fmask, n_tmask = p.mk.n_tmask;
@@ -309,13 +287,17 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
     const int* m_flen = p.mk.inl_on ? p.mk.inl + B * n_fmask : p.mk.flen;
     const int* m_tpos = p.mk.inl_on ? p.mk.inl + 2 * B * n_fmask : p.mk.tpos;
     const int* m_tlen = p.mk.inl_on ? p.mk.inl + 2 * B * n_fmask + B * n_tmask : p.mk.tlen;
+    SFE_PF_DECL
     for (int j = pb; j < ntiles; j += NPB) {
-      mbar_wait_backoff(pfull0 + 8 * pb, static_cast<uint32_t>((j / NPB) & 1));
+      SFE_PF(4)
+      mbar_wait_hint(pfull0 + 8 * pb, static_cast<uint32_t>((j / NPB) & 1));
+      SFE_PF(0)
+      SFE_TR(10, j);
       const int nsl = min(TS, npairs - j * TS);
-      const T2Row* trow = rows + (j & (T2_ROWQ - 1)) * TS;
+      const T2Row* trow = rows + pb * TS;
       typedef typename MelBank<TileCfg<PL>::BANK>::type BK;
       static_assert(BK::D == 80, "the read-out below is laid out for 80 Mel bins");
-      const int nrows = 2 * nsl;
+      const int nrows = (SFE_T2_ABLATE == 1 || SFE_T2_ABLATE == 2) ? 0 : 2 * nsl;
       bool va = false, ex = false, tm = false;  // the row is a real frame / is written / is time-masked
       int myb = 0, myt = 0;
       if (lane < nrows) {
@@ -350,6 +332,7 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
         __syncwarp();
       }
 
+      SFE_PF(1)
       // ---- banded Mel: the recipe filterbank's straight-line program (sfe_melprog.h) ----
       // One packed FMA per bin into (even filter, odd filter); a finished filter's raw sum is stored over a bin
       // the lane has already consumed (constant address, no flag test, no branch); two independent streams
@@ -388,6 +371,8 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
       }
       __syncwarp();
 
+      SFE_TR(11, j);
+      SFE_PF(2)
       // ---- read-out: two rows per step, 16 lanes per row; lane q owns Mel bins 4q..4q+3 and 64+q ----
       if (p.mel) {
         const int h = lane >> 4, q = lane & 15;
@@ -430,9 +415,44 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
 #pragma unroll
           for (int e = 0; e < 5; ++e) s1[e] = s2[e] = 0.f;
         };
+        // The usual tile: 2*TS consecutive real frames of ONE utterance, nothing but the logarithm (and the sums)
+        // between the row and HBM — straight-line, every offset an immediate, the loads of all steps in flight.
+        const int b0 = __shfl_sync(FULLM, myb, 0), t0 = __shfl_sync(FULLM, myt, 0);
+        const bool plain = !fancy && nsl == TS && dolog &&
+                           __all_sync(FULLM, lane >= 2 * TS || (va && ex && myb == b0 && myt == t0 + lane));
+        if (plain) {
+          float* dst0 = p.mel + (static_cast<long long>(b0) * F + t0) * BK::D + h * BK::D;
+          const float* src0 = p2buf + h * PP;
+          if (stats_on) {
+#pragma unroll
+            for (int it = 0; it < TS; ++it) {
+              const float4 x4 = *reinterpret_cast<const float4*>(src0 + 2 * it * PP + so4);
+              float x[5] = {x4.x, x4.y, x4.z, x4.w, src0[2 * it * PP + so1]};
+#pragma unroll
+              for (int e = 0; e < 5; ++e) {
+                x[e] = fast_log(x[e], clampv, lmul);
+                s1[e] += x[e];
+                s2[e] = fmaf(x[e], x[e], s2[e]);
+              }
+              *reinterpret_cast<float4*>(dst0 + 2 * it * BK::D + 4 * q) = make_float4(x[0], x[1], x[2], x[3]);
+              dst0[2 * it * BK::D + 64 + q] = x[4];
+            }
+            flush(b0);
+          } else {
+#pragma unroll
+            for (int it = 0; it < TS; ++it) {
+              const float4 x4 = *reinterpret_cast<const float4*>(src0 + 2 * it * PP + so4);
+              float x[5] = {x4.x, x4.y, x4.z, x4.w, src0[2 * it * PP + so1]};
+#pragma unroll
+              for (int e = 0; e < 5; ++e) x[e] = fast_log(x[e], clampv, lmul);
+              *reinterpret_cast<float4*>(dst0 + 2 * it * BK::D + 4 * q) = make_float4(x[0], x[1], x[2], x[3]);
+              dst0[2 * it * BK::D + 64 + q] = x[4];
+            }
+          }
+        }
         int curb = -1;
         unsigned fm = 0u;
-        for (int it = 0; it < nsl; ++it) {
+        for (int it = 0; it < (plain ? 0 : nsl); ++it) {
           const T2Row rd = trow[it];
           if (rd.b != curb) {
             if (curb >= 0 && stats_on) flush(curb);
@@ -484,12 +504,15 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
 
       // hand the buffer back: tile j + NPB may write its rows
       __syncwarp();
+      SFE_TR(12, j);
+      SFE_PF(3)
       if (lane == 0) {
         pgen[pb] = j + NPB;
         __threadfence_block();
         mbar_arrive(pfree0 + 8 * pb);
       }
     }
+    SFE_PF_DUMP(warp)
     return;
   }
 
@@ -497,62 +520,121 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
   unsigned char* wbase = smem + p.t2_warp + warp * p.t2_warp_bytes;
   cpx* Zw = reinterpret_cast<cpx*>(wbase) + g * PL::MP;
   float* escratch = reinterpret_cast<float*>(wbase);  // gathered pairs stage their samples in the FFT scratch
+  float* stage = reinterpret_cast<float*>(wbase + p.t2_stage + 16);  // this warp's bulk-copied samples
+  const uint32_t sbar = smem_u32(wbase + p.t2_stage);                // ... have landed
   const float* wtab = tab + p.o_win;
   const cpx* tw2 = reinterpret_cast<const cpx*>(tab + p.o_tw2);
   const cpx* tw3 = reinterpret_cast<const cpx*>(tab + p.o_tw3);
   const cpx* wpost = reinterpret_cast<const cpx*>(tab + p.o_wpost);
-  const int stage_floats = p.t2_stage_floats;
-  const int qend = ntiles * TS;  // (the last tile's missing pairs still count for its barriers)
+  const int qend = ntiles * TS;  // (the last tile's missing pairs still count for its barrier)
+  const bool bulk_ok = ((reinterpret_cast<uintptr_t>(p.wav) & 15) == 0);
 
-  while (true) {
+  // A pair as its warp sees it.  Everything here is warp-uniform: every lane computes the same values (no
+  // broadcast), lengths and frame counts come from the shared-memory tables, the utterance is found by stepping
+  // from the previous pair's (claims move forward).
+  struct Pair {
+    int q, kind, b, tA, flen, shift;
+    long long len;
+  };
+  int b_hint = s_misc[3];
+  auto claim = [&]() -> Pair {
+    Pair c;
     int q = 0;
     if (lane == 0) q = atomicAdd(&s_misc[0], 1);
-    q = __shfl_sync(FULLM, q, 0);
+    c.q = __shfl_sync(FULLM, q, 0);
+    c.kind = U_DONE; c.b = 0; c.tA = 0; c.flen = 0; c.shift = 0; c.len = 0;
+    if (c.q >= npairs) return c;  // nothing to stage (past the end, or padding of the CTA's last tile)
+    const int P = P_lo + c.q;
+    int tu;
+    if (tabled) {
+      int bb = b_hint;
+      while (bb + 1 < B && s_pc[bb + 1] <= P) ++bb;  // (also steps over utterances without pairs)
+      b_hint = bb;
+      c.b = bb;
+      tu = P - s_pc[bb];
+      c.len = s_len[bb];
+      c.flen = s_flen[bb];
+    } else {
+      c.b = P / upu;
+      tu = P - c.b * upu;
+      c.len = __ldg(p.len + c.b);
+      c.flen = clampF(frames_of(c.len));
+    }
+    c.tA = tu * FPW;
+    c.kind = U_PAD;
+    if (c.tA < c.flen) {
+      c.kind = U_EDGE;
+      const long long o_start = static_cast<long long>(c.tA) * hop + p.off;
+      const long long o_end = o_start + static_cast<long long>(FPW - 1) * hop + win;
+      const long long gi = static_cast<long long>(c.b) * p.pitch + o_start - pre1;
+      const long long ga = gi & ~3LL;
+      const int shiftfull = static_cast<int>(gi - ga) + pre1;
+      const int need = (shiftfull + (FPW - 1) * hop + win + 3) & ~3;  // floats from ga that cover the pair
+      if (bulk_ok && (o_start - pre1 >= 0) && (o_end <= c.len) && (ga + need <= p.total_floats)) {
+        c.kind = U_BULK;
+        c.shift = shiftfull;
+        if (lane == 0) {
+          // (the warp is past its last read of the buffer — __syncwarp before the call; order that before the
+          //  async-proxy write)
+          fence_proxy_async();
+          mbar_expect_tx(sbar, static_cast<uint32_t>(need) * 4u);
+          bulk_g2s(smem_u32(stage), p.wav + ga, static_cast<uint32_t>(need) * 4u, sbar);
+        }
+      }
+    }
+    return c;
+  };
+
+  uint32_t sparity = 0u;  // phase of sbar the next bulk pair completes
+  Pair nx = claim();
+  SFE_PF_DECL
+  while (true) {
+    const Pair cu = nx;
+    const int q = cu.q;
+    SFE_TR(20, q);
     if (q >= qend) break;
-    const int j = q / TS, s = q - j * TS, sb = j & 1, pb = j % NPB;
+    const int j = q / TS, s = q - j * TS, pb = j % NPB;  // tile, slot and buffer of the Mel stage
+    const int kind = cu.kind, b = cu.b, flen = cu.flen, tA = cu.tA;
+    float* p2buf = p2_0 + pb * p2_floats;
     // rows of buffer pb may be overwritten once the Mel stage of tile j - NPB has consumed them
     auto p2_wait = [&]() {
       while (true) {
-        mbar_wait_backoff(pfree0 + 8 * pb, static_cast<uint32_t>(((j / NPB) & 1) ^ 1));
+        mbar_wait_hint(pfree0 + 8 * pb, static_cast<uint32_t>(((j / NPB) & 1) ^ 1));
         if (pgen[pb] == j) break;
-        __nanosleep(200);  // the phase that completed belongs to an earlier tile of this buffer
+        __nanosleep(100);  // the phase that completed belongs to an earlier tile of this buffer
       }
     };
     auto publish = [&]() {
       __syncwarp();
-      if (lane == 0) mbar_arrive(pfull0 + 8 * pb);
+      if (lane == 0) {
+        T2Row rd;
+        rd.b = b; rd.tA = tA; rd.flen = flen; rd.kind = kind;
+        rows[pb * TS + s] = rd;
+        mbar_arrive(pfull0 + 8 * pb);  // (release: rows and descriptor are visible to the Mel warp)
+      }
     };
-    if (q >= npairs) {  // padding of the CTA's last tile
-      p2_wait();
-      publish();
-      continue;
-    }
-    while (true) {
-      mbar_wait_backoff(full0 + 8 * sb, static_cast<uint32_t>((j >> 1) & 1));
-      if (stile[sb] == j) break;
-      __nanosleep(200);
-    }
-    const T2Slot sl = slots[sb * TS + s];
-    const int kind = sl.kind, b = sl.b, flen = sl.flen, tA = sl.tu * FPW;
-    float* p2buf = p2_0 + pb * p2_floats;
-    // every lane is past its last read of the stage buffer and of the slot
-    auto stage_release = [&]() {
+    if (kind == U_DONE || kind == U_PAD || SFE_T2_ABLATE >= 2) {  // (U_DONE: padding of the CTA's last tile)
+      if (kind == U_BULK) { mbar_wait_hint(sbar, sparity); sparity ^= 1u; }
       __syncwarp();
-      if (lane == 0) mbar_arrive(sfree0 + 8 * sb);
-    };
-
-    if (kind == U_PAD) {
-      stage_release();
+      nx = claim();
       p2_wait();
       publish();
+      SFE_PF(7)
       continue;
     }
     // ---------------- samples of this pair ----------------
     const bool bulk = (kind == U_BULK);
-    const float* sbase = bulk ? (stage0 + sb * stage_floats) : escratch;
+    const float* sbase = bulk ? stage : escratch;
+    SFE_PF(6)
+    if (bulk) {
+      mbar_wait_hint(sbar, sparity);
+      sparity ^= 1u;
+    }
+    SFE_PF(0)
+    SFE_TR(21, q);
     auto gather = [&](int t0, int n) {
       // explicit gather with batch-level reflection, zero beyond the length and pre-emphasis applied here
-      const long long len = sl.len;
+      const long long len = cu.len;
       const long long o_start = static_cast<long long>(t0) * hop + p.off;
       const float* row = p.wav + static_cast<long long>(b) * p.pitch;
       for (int i0 = lane; i0 < n; i0 += 32 * 4) {
@@ -589,12 +671,19 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
         if (sub > 0) __syncwarp();  // the previous frame's transform is out of the scratch
         gather(t, win);
       }
-      const int fo = bulk ? (fslot * hop + sl.soff) : ((PL::S == 1 ? fslot * hop : 0) + EDGE_SHIFT);
+      const int fo = bulk ? (fslot * hop + cu.shift) : ((PL::S == 1 ? fslot * hop : 0) + EDGE_SHIFT);
       const float* fr = sbase + fo;
       const float pre = (PRE && bulk) ? p.pre : 0.f;  // gathered pairs were pre-emphasised by the gather
       if ((fo & 1) == 0) stockham_pass<PL, PL::R1, 1, true, true, PRE, true>(Zw, nullptr, l, fr, wtab, win, pre);
       else stockham_pass<PL, PL::R1, 1, true, false, PRE, true>(Zw, nullptr, l, fr, wtab, win, pre);
-      if (sub == PL::S - 1) stage_release();
+      if (sub == PL::S - 1) {
+        // the staging buffer is free (the pass ends with a __syncwarp): claim the next pair and start its copy,
+        // which lands under the rest of this one
+        SFE_PF(1)
+        nx = claim();
+        SFE_PF(2)
+        SFE_TR(22, q);
+      }
       fft_rest<PL>(Zw, tw2, tw3, l);
 
       // real-FFT unpack: X[k] = E + W^k O, X[M-k] = conj(E - W^k O); the 1/2 lives in the window.
@@ -623,7 +712,7 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
           }
         }
       }
-      if (sub == 0) p2_wait();
+      if (sub == 0) { SFE_TR(23, q); SFE_PF(3) p2_wait(); SFE_PF(4) SFE_TR(24, q); }
       float* row = p2buf + (2 * s + fslot) * PP;
       float es = 0.f;
 #pragma unroll
@@ -664,8 +753,11 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
         if (l == 0 && t < F) p.energy[static_cast<long long>(b) * F + t] = (t < flen) ? sqrtf(fmaxf(es, 1e-10f)) : 0.f;
       }
     }
+    SFE_PF(5)
     publish();
+    SFE_TR(25, q);
   }
+  SFE_PF_DUMP(warp)
 }
 
 }  // namespace sfe

@@ -1,0 +1,5 @@
+#!/bin/bash
+O=gpurun_out/r2s7; mkdir -p $O
+timeout -s KILL 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -2 > $O/pytest.log; cat $O/pytest.log
+export SFE_KERNEL=tile
+REPS=1 bash tools/abn.sh "c1" speechain_b200/csrc/libsfe.so tools/ab/libsfe_w0.so tools/ab/libsfe_w1.so tools/ab/libsfe_a2w2.so tools/ab/libsfe_a2w0.so tools/ab/libsfe_a2w1.so 2>&1 | tee $O/abn.log
