@@ -61,11 +61,14 @@ __device__ __forceinline__ void t2_trace(int tag, int idx) {
 __device__ long long g_t2_prof[32 * 16];
 #define SFE_PF_DECL long long pf_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long pf_t = clock64();
 #define SFE_PF(k) { const long long t_ = clock64(); pf_acc[k] += t_ - pf_t; pf_t = t_; }
-#define SFE_PF_DUMP(w) if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) { for (int k_ = 0; k_ < 12; ++k_) g_t2_prof[(w) * 16 + k_] = pf_acc[k_]; }
+#define SFE_PF_DUMP(w) if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) { for (int k_ = 0; k_ < 8; ++k_) g_t2_prof[(w) * 16 + k_] = pf_acc[k_]; \
+  unsigned long long te_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(te_)); g_t2_prof[(w) * 16 + 8] = pf_g0; g_t2_prof[(w) * 16 + 9] = pf_g1; g_t2_prof[(w) * 16 + 10] = pf_g2; g_t2_prof[(w) * 16 + 11] = te_; }
+#define SFE_PF_G(v) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); v = t_; }
 #else
 #define SFE_PF_DECL
 #define SFE_PF(k)
 #define SFE_PF_DUMP(w)
+#define SFE_PF_G(v)
 #endif
 
 template <int BANK> struct MelBank { typedef void type; };
@@ -92,6 +95,9 @@ struct TileCfg {
 #else
   static constexpr int NF = (PL::M <= 256) ? 17 : 14;  // FFT warps (n_fft 1024: 9.5 KB of scratch + staging per warp)
 #endif
+  // Two frames in flight per warp (G = 16) store their rows at the same time: rows 16 banks apart (4 rows with the
+  // pitch below) make that store conflict-free, so pair s owns rows 8 (s / 4) + s % 4 and that + 4
+  static constexpr bool PERM = (PL::C == 2);
   static constexpr int NW = NF + NPB;                  // + Mel warps: 20 = 5 warps per SM sub-partition at <= 96 registers
 };
 // Row pitch of a power-spectrum tile: the spectrum plus the zero-weight bins its Mel program rounds up to, an ODD
@@ -118,6 +124,9 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+template <bool PERM> __device__ __forceinline__ int t2_row(int s, int f) {  // tile row of frame f of pair s
+  return PERM ? (8 * (s >> 2) + (s & 3) + 4 * f) : (2 * s + f);
+}
 struct T2Row {  // a pair as the Mel stage sees it: frames tA, tA+1 of utterance b, which has flen frames
   int b, tA, flen, kind;
 };
@@ -149,19 +158,21 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int M = PL::M, G = PL::G, Q = PL::PADQ, TS = TileCfg<PL>::TS, NPB = TileCfg<PL>::NPB, NF = TileCfg<PL>::NF;
   constexpr unsigned FULLM = 0xffffffffu;
+  constexpr bool PERM = TileCfg<PL>::PERM;
   enum { U_DONE = 0, U_PAD = 1, U_BULK = 2, U_EDGE = 3 };
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane / G, l = lane % G;
 
+  long long pf_g0 = 0, pf_g1 = 0, pf_g2 = 0;  // (profile builds: kernel entry, set-up done, tables landed)
+  SFE_PF_G(pf_g0)
   float* tab = reinterpret_cast<float*>(smem);
   unsigned char* ctrl = smem + p.t2_ctrl;
   const uint32_t tbar = smem_u32(ctrl);          // tables landed
   const uint32_t pfull0 = smem_u32(ctrl + 8);    // [NPB] every pair of the tile has stored its rows    FFT -> Mel
-  const uint32_t pfree0 = smem_u32(ctrl + 32);   // [NPB] the Mel stage has consumed the buffer         Mel -> FFT
   int* s_misc = reinterpret_cast<int*>(ctrl + 56);  // [0] next pair of the CTA, [1] first pair, [2] number of pairs
-  // A barrier's phase bit cannot tell a tile from the one two rounds later on the same buffer, and claims are only
-  // a counter — FFT warps may race ahead of a slow one: they also check WHICH tile may write a buffer.
-  volatile int* pgen = reinterpret_cast<volatile int*>(ctrl + 72);   // [NPB] tile that may write buffer pb next
+  // [NPB] the tile that may write buffer pb next (Mel -> FFT): a counter rather than a barrier, because claims are
+  // only a counter too — an FFT warp may race two rounds ahead of a slow one, which a phase bit cannot tell apart
+  volatile int* pgen = reinterpret_cast<volatile int*>(ctrl + 72);
   T2Row* rows = reinterpret_cast<T2Row*>(ctrl + 96);                  // [NPB][TS]
   float* p2_0 = reinterpret_cast<float*>(smem + p.t2_p2);
   __shared__ int s_cum[UNIT_TABLE_MAX_B + 1];  // cost coordinate at which every utterance starts
@@ -189,7 +200,6 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
     for (int i = 0; i < NPB; ++i) {
       pgen[i] = i;
       mbar_init(pfull0 + 8 * i, TS);
-      mbar_init(pfree0 + 8 * i, 1);
     }
     fence_mbar_init();
     const uint32_t b1 = static_cast<uint32_t>(p.o_mtab) * 4u, b2 = static_cast<uint32_t>(p.t2_sched_floats) * 4u;
@@ -271,11 +281,13 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
     }
   }
   __syncthreads();  // barrier inits, the tables of the work split and this CTA's range are visible
+  SFE_PF_G(pf_g1)
 
   const int P_lo = s_misc[1], npairs = s_misc[2];
   const int ntiles = (npairs + TS - 1) / TS;
 
   mbar_wait(tbar, 0u);  // tables have landed
+  SFE_PF_G(pf_g2)
 
   if (warp >= NF) {
     // ================================ Mel warps: warp NF + pb owns buffer pb ================================
@@ -297,15 +309,17 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
       const T2Row* trow = rows + pb * TS;
       typedef typename MelBank<TileCfg<PL>::BANK>::type BK;
       static_assert(BK::D == 80, "the read-out below is laid out for 80 Mel bins");
-      const int nrows = (SFE_T2_ABLATE == 1 || SFE_T2_ABLATE == 2) ? 0 : 2 * nsl;
+      // lane = row: the pair and frame behind it
+      const int srow = PERM ? (4 * (lane >> 3) + (lane & 3)) : (lane >> 1), grow = PERM ? ((lane >> 2) & 1) : (lane & 1);
+      const bool rowact = (lane < 2 * TS) && (srow < nsl) && !(SFE_T2_ABLATE == 1 || SFE_T2_ABLATE == 2);
       bool va = false, ex = false, tm = false;  // the row is a real frame / is written / is time-masked
       int myb = 0, myt = 0;
-      if (lane < nrows) {
-        const T2Row rd = trow[lane >> 1];
+      if (rowact) {
+        const T2Row rd = trow[srow];
         myb = rd.b;
-        myt = rd.tA + (lane & 1);
-        va = (rd.kind != U_PAD) && (myt < rd.flen);
-        ex = (myt < F) && !(p.skip_pad && !va);
+        myt = rd.tA + grow;
+        va = (rd.kind != U_PAD) && (rd.kind != U_DONE) && (myt < rd.flen);
+        ex = (rd.kind != U_DONE) && (myt < F) && !(p.skip_pad && !va);
         for (int qq = 0; qq < n_tmask; ++qq) {
           const int ps = m_tpos[myb * n_tmask + qq], ln = m_tlen[myb * n_tmask + qq];
           tm |= (myt >= ps) && (myt < ps + ln);
@@ -316,9 +330,10 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
 
       // ---- linear spectrogram output (before the Mel stage overwrites the rows) ----
       if (p.lin) {
-        for (int r = 0; r < nrows; ++r) {
+        for (int r = 0; r < 2 * TS; ++r) {
           const int rb = __shfl_sync(FULLM, myb, r), rt = __shfl_sync(FULLM, myt, r);
-          if (rt < F) {
+          const bool ract = __shfl_sync(FULLM, static_cast<int>(rowact && (trow[srow].kind != U_DONE)), r) != 0;
+          if (ract && rt < F) {
             float* dst = p.lin + (static_cast<long long>(rb) * F + rt) * K;
             const bool v = (va_bits >> r) & 1u;
             const float* src = p2buf + r * PP;
@@ -339,7 +354,7 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
       // (bins below / above B_LD) for instruction-level parallelism, joined at the end.  The logarithm is
       // taken by the read-out.  (A data-driven version of this loop — flag tests and branches around the
       // emits — cost 5 900 instructions and ~30 us of one warp per tile, the whole CTA waiting for it.)
-      if (lane < nrows) {
+      if (rowact) {
         float* rowp = p2buf + lane * PP;
         const float4* pA = reinterpret_cast<const float4*>(rowp);
         const float4* pB = reinterpret_cast<const float4*>(rowp + BK::B_LD);
@@ -352,13 +367,24 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
 #define SFE_X(v_, i) ((i) == 0 ? v_.x : (i) == 1 ? v_.y : (i) == 2 ? v_.z : v_.w)
 #define SFE_FA(buf, i) aA = f2fma(SFE_W(wA0[buf], wA1[buf], i), make_float2(SFE_X(xA[buf], i), SFE_X(xA[buf], i)), aA);
 #define SFE_FB(buf, i) aB = f2fma(SFE_W(wB0[buf], wB1[buf], i), make_float2(SFE_X(xB[buf], i), SFE_X(xB[buf], i)), aB);
-#define SFE_EA(slot, pos) if (slot) { rowp[pos] = aA.y; aA.y = 0.f; } else { rowp[pos] = aA.x; aA.x = 0.f; }
-#define SFE_EB(slot, pos) if (slot) { rowp[pos] = aB.y; aB.y = 0.f; } else { rowp[pos] = aB.x; aB.x = 0.f; }
+#define SFE_EA(slot, k) if (slot) { oa[k] = aA.y; aA.y = 0.f; } else { oa[k] = aA.x; aA.x = 0.f; }
+#define SFE_EB(slot, k) if (slot) { ob[k] = aB.y; aB.y = 0.f; } else { ob[k] = aB.x; aB.x = 0.f; }
+#define SFE_SA(pos) *reinterpret_cast<float4*>(rowp + (pos)) = make_float4(oa[0], oa[1], oa[2], oa[3]);
+#define SFE_SB(pos) *reinterpret_cast<float4*>(rowp + (pos)) = make_float4(ob[0], ob[1], ob[2], ob[3]);
+#define SFE_EA1(slot, pos) if (slot) { rowp[pos] = aA.y; aA.y = 0.f; } else { rowp[pos] = aA.x; aA.x = 0.f; }
+#define SFE_EB1(slot, pos) if (slot) { rowp[pos] = aB.y; aB.y = 0.f; } else { rowp[pos] = aB.x; aB.x = 0.f; }
+#define SFE_PA(k, pos) rowp[pos] = oa[k];
 #define SFE_JOIN(slot, pos) rowp[pos] += (slot) ? aA.y : aA.x; rowp[(pos) + 1] += (slot) ? aA.x : aA.y;
 #define SFE_MOVE(from, to) rowp[to] = rowp[from];
-        if constexpr (TileCfg<PL>::BANK == 1) { SFE_MELPROG_1(SFE_LD, SFE_FA, SFE_FB, SFE_EA, SFE_EB, SFE_JOIN, SFE_MOVE) }
-        else if constexpr (TileCfg<PL>::BANK == 2) { SFE_MELPROG_2(SFE_LD, SFE_FA, SFE_FB, SFE_EA, SFE_EB, SFE_JOIN, SFE_MOVE) }
-        else { SFE_MELPROG_3(SFE_LD, SFE_FA, SFE_FB, SFE_EA, SFE_EB, SFE_JOIN, SFE_MOVE) }
+        float oa[4] = {0.f, 0.f, 0.f, 0.f}, ob[4] = {0.f, 0.f, 0.f, 0.f};  // finished filters waiting for a 128-bit store
+        if constexpr (TileCfg<PL>::BANK == 1) { SFE_MELPROG_1(SFE_LD, SFE_FA, SFE_FB, SFE_EA, SFE_EB, SFE_SA, SFE_SB, SFE_EA1, SFE_EB1, SFE_PA, SFE_JOIN, SFE_MOVE) }
+        else if constexpr (TileCfg<PL>::BANK == 2) { SFE_MELPROG_2(SFE_LD, SFE_FA, SFE_FB, SFE_EA, SFE_EB, SFE_SA, SFE_SB, SFE_EA1, SFE_EB1, SFE_PA, SFE_JOIN, SFE_MOVE) }
+        else { SFE_MELPROG_3(SFE_LD, SFE_FA, SFE_FB, SFE_EA, SFE_EB, SFE_SA, SFE_SB, SFE_EA1, SFE_EB1, SFE_PA, SFE_JOIN, SFE_MOVE) }
+#undef SFE_SA
+#undef SFE_SB
+#undef SFE_EA1
+#undef SFE_EB1
+#undef SFE_PA
 #undef SFE_LD
 #undef SFE_W
 #undef SFE_X
@@ -419,15 +445,15 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
         // between the row and HBM — straight-line, every offset an immediate, the loads of all steps in flight.
         const int b0 = __shfl_sync(FULLM, myb, 0), t0 = __shfl_sync(FULLM, myt, 0);
         const bool plain = !fancy && nsl == TS && dolog &&
-                           __all_sync(FULLM, lane >= 2 * TS || (va && ex && myb == b0 && myt == t0 + lane));
+                           __all_sync(FULLM, lane >= 2 * TS || (va && ex && myb == b0 && myt == t0 + 2 * srow + grow));
         if (plain) {
           float* dst0 = p.mel + (static_cast<long long>(b0) * F + t0) * BK::D + h * BK::D;
-          const float* src0 = p2buf + h * PP;
+          const float* src0 = p2buf + (t2_row<PERM>(0, 1) * h) * PP;
           if (stats_on) {
 #pragma unroll
             for (int it = 0; it < TS; ++it) {
-              const float4 x4 = *reinterpret_cast<const float4*>(src0 + 2 * it * PP + so4);
-              float x[5] = {x4.x, x4.y, x4.z, x4.w, src0[2 * it * PP + so1]};
+              const float4 x4 = *reinterpret_cast<const float4*>(src0 + t2_row<PERM>(it, 0) * PP + so4);
+              float x[5] = {x4.x, x4.y, x4.z, x4.w, src0[t2_row<PERM>(it, 0) * PP + so1]};
 #pragma unroll
               for (int e = 0; e < 5; ++e) {
                 x[e] = fast_log(x[e], clampv, lmul);
@@ -441,8 +467,8 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
           } else {
 #pragma unroll
             for (int it = 0; it < TS; ++it) {
-              const float4 x4 = *reinterpret_cast<const float4*>(src0 + 2 * it * PP + so4);
-              float x[5] = {x4.x, x4.y, x4.z, x4.w, src0[2 * it * PP + so1]};
+              const float4 x4 = *reinterpret_cast<const float4*>(src0 + t2_row<PERM>(it, 0) * PP + so4);
+              float x[5] = {x4.x, x4.y, x4.z, x4.w, src0[t2_row<PERM>(it, 0) * PP + so1]};
 #pragma unroll
               for (int e = 0; e < 5; ++e) x[e] = fast_log(x[e], clampv, lmul);
               *reinterpret_cast<float4*>(dst0 + 2 * it * BK::D + 4 * q) = make_float4(x[0], x[1], x[2], x[3]);
@@ -467,7 +493,7 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
               }
             }
           }
-          const int r = 2 * it + h;
+          const int r = t2_row<PERM>(it, h);
           const bool v = (va_bits >> r) & 1u, w = (ex_bits >> r) & 1u;
           if (!w) continue;
           float x[5] = {padv, padv, padv, padv, padv};
@@ -507,9 +533,8 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
       SFE_TR(12, j);
       SFE_PF(3)
       if (lane == 0) {
+        __threadfence_block();  // release: every lane's reads of the tile (__syncwarp above) are done
         pgen[pb] = j + NPB;
-        __threadfence_block();
-        mbar_arrive(pfree0 + 8 * pb);
       }
     }
     SFE_PF_DUMP(warp)
@@ -530,13 +555,15 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
   const bool bulk_ok = ((reinterpret_cast<uintptr_t>(p.wav) & 15) == 0);
 
   // A pair as its warp sees it.  Everything here is warp-uniform: every lane computes the same values (no
-  // broadcast), lengths and frame counts come from the shared-memory tables, the utterance is found by stepping
-  // from the previous pair's (claims move forward).
+  // broadcast).  Claims of a warp move forward, and mostly stay inside one utterance: its pair range, length,
+  // frame count and row base are cached in registers, so a claim is ~30 instructions (the general search with
+  // table loads and 64-bit arithmetic cost as much as an FFT pass per pair).
   struct Pair {
     int q, kind, b, tA, flen, shift;
     long long len;
   };
-  int b_hint = s_misc[3];
+  int c_b = s_misc[3], c_p0 = 0, c_p1 = -1, c_len = 0, c_flen = 0;  // cached utterance: pairs [c_p0, c_p1)
+  long long c_row = 0;                                             // ... and the float index of its first sample
   auto claim = [&]() -> Pair {
     Pair c;
     int q = 0;
@@ -545,32 +572,36 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
     c.kind = U_DONE; c.b = 0; c.tA = 0; c.flen = 0; c.shift = 0; c.len = 0;
     if (c.q >= npairs) return c;  // nothing to stage (past the end, or padding of the CTA's last tile)
     const int P = P_lo + c.q;
-    int tu;
-    if (tabled) {
-      int bb = b_hint;
-      while (bb + 1 < B && s_pc[bb + 1] <= P) ++bb;  // (also steps over utterances without pairs)
-      b_hint = bb;
-      c.b = bb;
-      tu = P - s_pc[bb];
-      c.len = s_len[bb];
-      c.flen = s_flen[bb];
-    } else {
-      c.b = P / upu;
-      tu = P - c.b * upu;
-      c.len = __ldg(p.len + c.b);
-      c.flen = clampF(frames_of(c.len));
+    if (P >= c_p1) {  // another utterance
+      if (tabled) {
+        while (c_b + 1 < B && s_pc[c_b + 1] <= P) ++c_b;  // (also steps over utterances without pairs)
+        c_p0 = s_pc[c_b];
+        c_p1 = s_pc[c_b + 1];
+        c_len = s_len[c_b];
+        c_flen = s_flen[c_b];
+      } else {
+        c_b = P / upu;
+        c_p0 = c_b * upu;
+        c_p1 = c_p0 + upu;
+        c_len = static_cast<int>(__ldg(p.len + c_b));
+        c_flen = clampF(frames_of(c_len));
+      }
+      c_row = static_cast<long long>(c_b) * p.pitch;
     }
-    c.tA = tu * FPW;
+    c.b = c_b;
+    c.len = c_len;
+    c.flen = c_flen;
+    c.tA = (P - c_p0) * FPW;
     c.kind = U_PAD;
-    if (c.tA < c.flen) {
+    if (c.tA < c_flen) {
       c.kind = U_EDGE;
-      const long long o_start = static_cast<long long>(c.tA) * hop + p.off;
-      const long long o_end = o_start + static_cast<long long>(FPW - 1) * hop + win;
-      const long long gi = static_cast<long long>(c.b) * p.pitch + o_start - pre1;
+      const int o_start = c.tA * hop + p.off;               // (the host keeps inputs of 2^31 samples off this kernel)
+      const int o_end = o_start + (FPW - 1) * hop + win;
+      const long long gi = c_row + (o_start - pre1);
       const long long ga = gi & ~3LL;
       const int shiftfull = static_cast<int>(gi - ga) + pre1;
       const int need = (shiftfull + (FPW - 1) * hop + win + 3) & ~3;  // floats from ga that cover the pair
-      if (bulk_ok && (o_start - pre1 >= 0) && (o_end <= c.len) && (ga + need <= p.total_floats)) {
+      if (bulk_ok && (o_start - pre1 >= 0) && (o_end <= c_len) && (ga + need <= p.total_floats)) {
         c.kind = U_BULK;
         c.shift = shiftfull;
         if (lane == 0) {
@@ -598,11 +629,8 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
     float* p2buf = p2_0 + pb * p2_floats;
     // rows of buffer pb may be overwritten once the Mel stage of tile j - NPB has consumed them
     auto p2_wait = [&]() {
-      while (true) {
-        mbar_wait_hint(pfree0 + 8 * pb, static_cast<uint32_t>(((j / NPB) & 1) ^ 1));
-        if (pgen[pb] == j) break;
-        __nanosleep(100);  // the phase that completed belongs to an earlier tile of this buffer
-      }
+      while (pgen[pb] != j) __nanosleep(64);  // (almost always already true: one shared-memory load)
+      __threadfence_block();                  // acquire: the Mel warp's reads of the rows are behind us
     };
     auto publish = [&]() {
       __syncwarp();
@@ -713,7 +741,7 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
         }
       }
       if (sub == 0) { SFE_TR(23, q); SFE_PF(3) p2_wait(); SFE_PF(4) SFE_TR(24, q); }
-      float* row = p2buf + (2 * s + fslot) * PP;
+      float* row = p2buf + t2_row<PERM>(s, fslot) * PP;
       float es = 0.f;
 #pragma unroll
       for (int i = 0; i < NI; ++i) {

@@ -61,25 +61,39 @@ def build(name, W):
     rowf = 8 * ng
     assert d_split <= kB - 3 and D - d_split >= 2 and b_off + D <= rowf
     ops = []  # the program
-    posA, posB = 0, b_off + d_split
     curA, curB = 0, d_split
 
+    pend = {"A": [], "B": []}  # outputs of a stream waiting to leave as one 128-bit store: (filter d, slot)
+
+    def flush_scalar(stream):
+        for d, slot in pend[stream]:
+            ops.append(f"E{stream}1({slot}, {d if stream == 'A' else b_off + d})")
+        pend[stream].clear()
+
     def emit(stream, g):
-        nonlocal posA, posB, curA, curB
-        # loads of group g + 1 are issued before group g's bins: an emit must land below the first bin NOT yet loaded
+        """Filter `cur` of the stream is complete.  Four consecutive outputs starting at a multiple of four leave as
+        ONE 128-bit store (a row-strided 32-bit store is a 4-way bank conflict; the 128-bit one is conflict-free);
+        the few outputs outside such a group are stored one by one."""
+        nonlocal curA, curB
+        # loads of group g + 1 are issued before group g's bins: a store must land below the first bin NOT yet loaded
         limit = (4 * (g + 2)) if stream == "A" else (kB + 4 * (g + 2))
+        d = curA if stream == "A" else curB
+        pos = d if stream == "A" else b_off + d
+        assert pos < limit and (stream == "A" or pos >= kB)
+        if d % 4 == 0:
+            flush_scalar(stream)
+        if d % 4 == len(pend[stream]):      # continues (or starts) an aligned group
+            pend[stream].append((d, d & 1))
+            ops.append(f"E{stream}({d & 1}, {d % 4})")
+            if d % 4 == 3:
+                ops.append(f"S{stream}({pos - 3})")
+                pend[stream].clear()
+        else:                               # the stream started inside a group: plain store
+            ops.append(f"E{stream}1({d & 1}, {pos})")
         if stream == "A":
-            assert posA < limit and posA == curA
-            ops.append(f"EA({curA & 1}, {posA})")
-            posA += 1
             curA += 1
         else:
-            assert posB < limit and posB >= kB and posB == b_off + curB
-            raw = curB - d_split < 2  # the two filters that straddle the cut wait for stream A's share
-            ops.append(f"EB({curB & 1}, {posB})")
-            posB += 1
             curB += 1
-            return raw
 
     ops.append("LD(0, 0)")
     for g in range(ng):
@@ -100,9 +114,13 @@ def build(name, W):
     for _ in range(tail_a):
         emit("A", ng)
     assert curA == d_split
+    flush_pending_a = list(pend["A"])
+    pend["A"].clear()
+    for k, (d, slot) in enumerate(flush_pending_a):  # (already taken out of the accumulator: registers -> row)
+        ops.append(f"PA({k}, {d})")
     for _ in range(tail):
         emit("B", ng)
-    assert curB == D
+    assert curB == D and not pend["B"], "80 filters end on a group boundary"
     # A's accumulator still holds its share of filters d_split (slot d_split & 1) and d_split + 1
     ops.append(f"JOIN({d_split & 1}, {b_off + d_split})")
     for d in range(4 * c_split, d_split):
@@ -116,9 +134,11 @@ def main():
     out.append("// GENERATED by tools/gen_mel_program.py — do not edit.  Straight-line Mel programs of the tile kernel\n"
                "// (sfe_tile.cuh) for the filterbanks of the shipped recipes; see the generator for the why and the how.\n"
                "// Macros: LD(g, buf) load group g's bins and weights into register set buf; FA/FB(buf, i) packed FMA of\n"
-               "// bin i of the group (stream A / B); EA/EB(slot, pos) store accumulator slot (0 even filter, 1 odd) to\n"
-               "// row[pos] and clear it; JOIN(slot, pos) add stream A's leftovers to row[pos], row[pos+1];\n"
-               "// MOVE(from, to) row[to] = row[from].\n#pragma once\n\nnamespace sfe {\nnamespace melprog {\n")
+               "// bin i of the group (stream A / B); EA/EB(slot, k) move accumulator slot (0 even filter, 1 odd) to\n"
+               "// output register k of the stream and clear it; SA/SB(pos) store the stream's four output registers to\n"
+               "// row[pos..pos+3]; EA1/EB1(slot, pos) store the slot to row[pos] directly and clear it; PA(k, pos) store\n"
+               "// output register k of stream A to row[pos]; JOIN(slot, pos) add stream A's leftovers to row[pos],\n"
+               "// row[pos+1]; MOVE(from, to) row[to] = row[from].\n#pragma once\n\nnamespace sfe {\nnamespace melprog {\n")
     for name, bank, args in BANKS:
         W = mel_filterbank(*args).numpy()
         meta, pre, curs, ops = build(name, W)
@@ -136,7 +156,7 @@ def main():
                 cur = "  "
             cur += op + " "
         lines.append(cur.rstrip() + "\n")
-        out.append(f"#define SFE_MELPROG_{bank}(LD, FA, FB, EA, EB, JOIN, MOVE) \\\n" + "".join(lines) + "\n")
+        out.append(f"#define SFE_MELPROG_{bank}(LD, FA, FB, EA, EB, SA, SB, EA1, EB1, PA, JOIN, MOVE) \\\n" + "".join(lines) + "\n")
     out.append("}  // namespace melprog\n}  // namespace sfe\n")
     path = os.path.join(ROOT, "speechain_b200", "csrc", "sfe_melprog.h")
     with open(path, "w") as f:

@@ -24,4 +24,6 @@ print("FFT warps: cycles in [0 data wait, 1 pass1, 2 claim, 3 lastpass+unpack, 4
 print("Mel warps: cycles in [0 tile wait, 1 flags, 2 program, 3 read-out, 4 hand-back]")
 for wi in range(32):
     if out[wi].any():
-        print(f"w{wi:02d} total {out[wi].sum():8d} ", " ".join(f"{x:7d}" for x in out[wi][:8]))
+        g = out[wi][8:12]
+        print(f"w{wi:02d} total {out[wi][:8].sum():8d} ", " ".join(f"{x:7d}" for x in out[wi][:8]),
+              f" | ns: setup {g[1] - g[0]:6d} tables {g[2] - g[1]:6d} loop {g[3] - g[2]:6d} all {g[3] - g[0]:6d}")
