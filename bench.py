@@ -176,9 +176,22 @@ def cpu_pass(w, wav, wl, weight, port):
     return feat
 
 
-def time_cpu(w, steps, warmup, n_utt=None):
-    """Time the CPU port on the first `n_utt` utterances of the workload's batch (all by default)."""
+def cpu_impl():
+    """The CPU arm: the reference's OWN modules when `oracle/build_ref.py` has staged them under oracle/_ref
+    (kind "reference"), else the bit-identical port of their op sequence (kind "port")."""
+    try:
+        from oracle import ref_modules  # imports oracle/_ref/speechain/module/...
+        if ref_modules.available():
+            return ref_modules, "reference"
+    except Exception:  # noqa: BLE001
+        pass
     from oracle import ref_port_torch as port
+    return port, "port"
+
+
+def time_cpu(w, steps, warmup, n_utt=None):
+    """Time the CPU arm on the first `n_utt` utterances of the workload's batch (all by default)."""
+    port, _ = cpu_impl()
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     lens = workload_lengths(w)
@@ -234,9 +247,10 @@ def run_reference(args, w, rank, world):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1),
         "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["desc"], "note": "reference op sequence on torch CPU (oracle/ref_port_torch.py); "
-                   "/root/reference itself does not travel to the GPU box"},
-        "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": threads, "kind": "port",
+        "config": {"workload": w["desc"], "note": ("the reference's own modules (oracle/_ref, staged by oracle/build_ref.py) on "
+                   "torch CPU" if cpu_impl()[1] == "reference" else "reference op sequence on torch CPU "
+                   "(oracle/ref_port_torch.py); oracle/_ref is not staged on this box")},
+        "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": threads, "kind": cpu_impl()[1],
                          "sample": f"{len(ts)} passes over {n_utt} of the batch's {B} utterances ({audio_s:.0f} audio-s "
                                    f"each), {cpu_model()}"},
         "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -247,6 +261,97 @@ def run_reference(args, w, rank, world):
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
+def measure_also(dev, world, rank, dist, peak, steps):
+    """Two more configurations inside the same line: C1 (the one the 60 % target is quoted on: the fused kernel
+    alone) and C4 (global normalisation in training mode: the path's only collective, the packed statistics
+    all-reduce) — timed like the headline: CUDA events, ring of batches > 3x L2, max over ranks."""
+    from speechain_b200.host import ops
+    from speechain_b200.module.acoustic_frontend import AcousticFrontend
+    out = {}
+
+    def build(w):
+        lens = workload_lengths(w, world, rank)
+        chain = AcousticFrontend(frontend=dict(conf=w["frontend"]), normalize=w["normalize"], specaug=w["specaug"],
+                                 distributed=world > 1).to(dev)
+        chain.train()
+        fe = chain.frontend
+        B, T = len(lens), max(lens)
+        hop, D = fe.speech2linear.hop_length, fe.output_size
+        F = 1 + T // hop
+        ring = max(2, int(np.ceil(3 * L2_BYTES / (4 * B * T + 4 * B * F * D))) + 1)
+        batches = [make_batch(w, lens, w["seed"] + 100 * i + rank, dev) for i in range(ring)]
+        wl_dev = torch.tensor(lens, dtype=torch.int64, device=dev)
+        ops.HostLengths.remember(wl_dev, np.asarray(lens, dtype=np.int64))
+        return chain, fe, lens, batches, wl_dev, ring, F, D
+
+    def timed(fn, n):
+        for i in range(3):
+            fn(i)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / n
+
+    # ---- C1: fused kernel alone (single-pass configuration: kernel == step) ----
+    w = WORKLOADS["c1"]
+    chain, fe, lens, batches, wl_dev, ring, F, D = build(w)
+    ms = timed(lambda i: fe.run(batches[i % ring], wl_dev), max(50, min(steps, 300)))
+    kb = 4 * sum(lens) + 4 * len(lens) * F * D
+    out["c1"] = {"workload": w["desc"], "us_per_launch": ms * 1e3, "audio_s_per_s": world * sum(lens) / w["sr"] / (ms * 1e-3),
+                 "roofline": {"bound": "hbm", "achieved": kb / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                              "frac": kb / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": kb}}
+    del chain, fe, batches
+
+    # ---- C4: frontend + global normalisation (training, epoch=None): statistics all-reduce every step ----
+    w = WORKLOADS["c4"]
+    chain, fe, lens, batches, wl_dev, ring, F, D = build(w)
+    n4 = max(10, min(steps, 40))
+    ms = timed(lambda i: chain(batches[i % ring], wl_dev, epoch=None), n4)
+    c4 = {"workload": w["desc"], "ms_per_step": ms, "value": world * sum(lens) / w["sr"] / (ms * 1e-3), "unit": "audio-s/s",
+          "steps": n4, "step_algorithmic_bytes": 4 * sum(lens) + 3 * 4 * len(lens) * F * D}
+    c4["step_gbs"] = c4["step_algorithmic_bytes"] / (ms * 1e-3) / 1e9
+    if dist is not None:
+        # the collective alone, on the buffer the step exchanges
+        packed = torch.zeros(2 * D + 1, dtype=torch.float32, device=dev)
+        ar_ms = timed(lambda i: dist.all_reduce(packed), 50)
+        c4["allreduce_us"] = ar_ms * 1e3
+        # every rank must hold the same global statistics, bit for bit, and they must be what a single process
+        # computes from the ranks' packed [sum of means | sum of stds | N] buffers
+        torch.manual_seed(7)
+        out_fe = fe.run(batches[0], wl_dev, want_stats=True, skip_pad=True)
+        _, _, mine = ops.stats_finalize(out_fe["stats"], out_fe["feat_len"], chain.normalize.clamp, want_packed=True)
+        chain(batches[0], wl_dev, epoch=None)
+        gm, gs = chain.normalize.global_mean.clone(), chain.normalize.global_std.clone()
+        allp = [torch.empty_like(mine) for _ in range(world)]
+        allm = [torch.empty_like(gm) for _ in range(world)]
+        alls = [torch.empty_like(gs) for _ in range(world)]
+        dist.all_gather(allp, mine)
+        dist.all_gather(allm, gm)
+        dist.all_gather(alls, gs)
+        same = all(torch.equal(allm[0], m) for m in allm) and all(torch.equal(alls[0], x) for x in alls)
+        tot = torch.stack(allp).double().sum(0)
+        ref_m, ref_s = (tot[:D] / tot[2 * D]).float(), (tot[D:2 * D] / tot[2 * D]).float()
+        c4["ranks_agree_bitwise"] = bool(same)
+        c4["max_abs_diff_vs_single_process_recompute"] = float(max((gm - ref_m).abs().max().item(),
+                                                                   (gs - ref_s).abs().max().item()))
+        c4["ranks"] = world
+    else:
+        c4["allreduce_us"] = None
+        c4["ranks_agree_bitwise"] = None
+        c4["ranks"] = 1
+    out["c4"] = c4
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -255,6 +360,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-also", action="store_true", help="skip the extra C1 / C4 measurements")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -406,6 +512,11 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
+    also = None
+    if not args.no_also and args.workload == "c2":
+        del batches, host, dbuf
+        torch.cuda.empty_cache()
+        also = measure_also(dev, world, rank, dist, load_peaks()[0], steps)
     clocks = sampler.stop()
 
     if rank != 0:
@@ -434,12 +545,16 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["desc"], "utterances_per_gpu": B, "audio_s_per_step_per_gpu": audio_s,
                    "padded_len": T, "frames": F, "sharding": "utterance stride [W-1-r::W], no data-path collective",
-                   "cache": f"ring of {ring} distinct batches ({ring * (in_bytes_padded + out_bytes) / 1e6:.0f} MB) > 3x L2"},
+                   "cache": f"ring of {ring} distinct batches ({ring * (in_bytes_padded + out_bytes) / 1e6:.0f} MB) > 3x L2",
+                   "value_note": "`value` feeds device-resident lengths whose host copy is already known (one "
+                                 "HostLengths entry); a CUDA length tensor fresh from batch_to_cuda costs one .cpu() sync per "
+                                 "step on top — `e2e` passes host lengths like a collated batch and pays everything"},
         "clocks": clocks,
         "host": {"enqueue_ms_per_step_max_over_ranks": host_ms_max / steps, "device_ms_per_step_min_over_ranks": ms_min / steps,
                  "cpus": os.cpu_count(), "affinity": len(os.sched_getaffinity(0))},
         "e2e": {"value": total_audio * e2e_steps / (e2e_ms * 1e-3), "unit": "audio-s/s",
                 "h2d_bytes_per_step": ops.upload_bytes(wl_host) + 8 * B, "d2h_bytes_per_step": 8 * B, "steps": e2e_steps,
+                "h2d_gbs_per_gpu": (ops.upload_bytes(wl_host) + 8 * B) * e2e_steps / (e2e_ms * 1e-3) / 1e9,
                 "note": "pinned host (B,T,1) waveforms -> ops.upload_waveforms (valid samples; rows of similar length "
                         "as one pitched copy) -> public API "
                         "AcousticFrontend.forward; copy of step i+1 overlapped with step i; D2H = feature lengths "
@@ -451,6 +566,9 @@ def main():
                      "step_algorithmic_bytes": step_bytes,
                      "step_gbs": step_bytes / (ms_total / steps * 1e-3) / 1e9},
     }
+    if also is not None:
+        line["also"] = also
+    line["roofline"]["kernel"] = os.environ.get("SFE_KERNEL", "default: tile kernel for the recipe plans, else gather")
     traffic_file = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
     if os.path.exists(traffic_file):
         with open(traffic_file) as f:
@@ -460,7 +578,7 @@ def main():
         _, probe, _ = time_cpu(w, 1, 1)
         n_pass = int(min(60, max(3, round(10.0 / max(probe[0], 1e-3)))))
         a_s, ts, threads = time_cpu(w, n_pass, 0)
-        line["cpu_baseline"] = {"value": a_s * len(ts) / sum(ts), "unit": "audio-s/s", "cores": threads, "kind": "port",
+        line["cpu_baseline"] = {"value": a_s * len(ts) / sum(ts), "unit": "audio-s/s", "cores": threads, "kind": cpu_impl()[1],
                                 "sample": f"{len(ts)} full passes over one batch ({a_s:.0f} audio-s each) after 2 "
                                           f"warm-ups, {sum(ts):.1f} s of CPU work, {cpu_model()}"}
     print(json.dumps(line), flush=True)

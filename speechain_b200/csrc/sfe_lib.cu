@@ -610,7 +610,7 @@ static int frontend_forward_impl(const sfe_plan* pl, const float* wav, int64_t w
     const char* ev = getenv("SFE_KERNEL");
     return !ev ? 0 : (ev[0] == 'g' ? 1 : (ev[0] == 't' ? 2 : 0));
   }();
-  const bool tile = pl->t2_ok && mel && force != 1 && T_max < 0x7ff00000LL && !(reinterpret_cast<uintptr_t>(mel) & 15) &&
+  const bool tile = pl->t2_ok && mel && !lin && force != 1 && T_max < 0x7ff00000LL && !(reinterpret_cast<uintptr_t>(mel) & 15) &&
                     !(energy && pl->cfg.has_preemphasis) &&
                     (!norm_mean || !(reinterpret_cast<uintptr_t>(norm_mean) & 15)) &&
                     (!norm_std || !(reinterpret_cast<uintptr_t>(norm_std) & 15));

@@ -74,15 +74,14 @@ __device__ long long g_t2_prof[32 * 16];
 template <int BANK> struct MelBank { typedef void type; };
 template <> struct MelBank<1> { typedef melprog::Bank1 type; };
 template <> struct MelBank<2> { typedef melprog::Bank2 type; };
-template <> struct MelBank<3> { typedef melprog::Bank3 type; };
 
 template <class PL>
 struct TileCfg {
   // The tile kernel exists for the (n_fft, win_length) pairs of the shipped recipes, each with the straight-line
   // Mel program of the recipe's filterbank (sfe_melprog.h); sfe_plan_create checks that the plan's filterbank has
   // that band structure, every other configuration runs the gather kernel (sfe_fused.cuh).
-  static constexpr int BANK = (PL::M == 256 && PL::WIN == 400) ? 1 : (PL::M == 200 && PL::WIN == 400) ? 2
-                            : (PL::M == 512 && PL::WIN == 1024) ? 3 : 0;
+  // (n_fft 1024 — fewer, fatter warps — measured slower than the gather kernel on this design: 285 vs 232 us for C3)
+  static constexpr int BANK = (PL::M == 256 && PL::WIN == 400) ? 1 : (PL::M == 200 && PL::WIN == 400) ? 2 : 0;
   static constexpr bool SUPPORTED = (BANK != 0);
   static constexpr int TS = (PL::M <= 256) ? 16 : 8;   // pairs per tile: 2*TS rows, one lane per row in the Mel stage
 #ifdef SFE_T2_NPB  // tuning experiments (tools/variant.py)
@@ -286,8 +285,7 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
   const int P_lo = s_misc[1], npairs = s_misc[2];
   const int ntiles = (npairs + TS - 1) / TS;
 
-  mbar_wait(tbar, 0u);  // tables have landed
-  SFE_PF_G(pf_g2)
+  if (warp >= NF) mbar_wait(tbar, 0u);  // (Mel warps) tables have landed
 
   if (warp >= NF) {
     // ================================ Mel warps: warp NF + pb owns buffer pb ================================
@@ -378,8 +376,7 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
 #define SFE_MOVE(from, to) rowp[to] = rowp[from];
         float oa[4] = {0.f, 0.f, 0.f, 0.f}, ob[4] = {0.f, 0.f, 0.f, 0.f};  // finished filters waiting for a 128-bit store
         if constexpr (TileCfg<PL>::BANK == 1) { SFE_MELPROG_1(SFE_LD, SFE_FA, SFE_FB, SFE_EA, SFE_EB, SFE_SA, SFE_SB, SFE_EA1, SFE_EB1, SFE_PA, SFE_JOIN, SFE_MOVE) }
-        else if constexpr (TileCfg<PL>::BANK == 2) { SFE_MELPROG_2(SFE_LD, SFE_FA, SFE_FB, SFE_EA, SFE_EB, SFE_SA, SFE_SB, SFE_EA1, SFE_EB1, SFE_PA, SFE_JOIN, SFE_MOVE) }
-        else { SFE_MELPROG_3(SFE_LD, SFE_FA, SFE_FB, SFE_EA, SFE_EB, SFE_SA, SFE_SB, SFE_EA1, SFE_EB1, SFE_PA, SFE_JOIN, SFE_MOVE) }
+        else { SFE_MELPROG_2(SFE_LD, SFE_FA, SFE_FB, SFE_EA, SFE_EB, SFE_SA, SFE_SB, SFE_EA1, SFE_EB1, SFE_PA, SFE_JOIN, SFE_MOVE) }
 #undef SFE_SA
 #undef SFE_SB
 #undef SFE_EA1
@@ -617,7 +614,9 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
   };
 
   uint32_t sparity = 0u;  // phase of sbar the next bulk pair completes
-  Pair nx = claim();
+  Pair nx = claim();      // the first pair's samples fly while the tables land
+  mbar_wait(tbar, 0u);
+  SFE_PF_G(pf_g2)
   SFE_PF_DECL
   while (true) {
     const Pair cu = nx;

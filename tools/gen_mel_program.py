@@ -26,7 +26,6 @@ from speechain_b200.module.frontend._common import mel_filterbank  # noqa: E402
 BANKS = [
     ("16000_512_80", 1, (16000, 512, 80, 0.0, 8000.0, "slaney", True)),    # BASELINE C1/C2/C4
     ("16000_400_80", 2, (16000, 400, 80, 0.0, 8000.0, "slaney", True)),    # ASR recipes: n_fft = win_length
-    ("22050_1024_80", 3, (22050, 1024, 80, 0.0, 8000.0, "slaney", True)),  # TTS recipes (BASELINE C3/C5)
 ]
 
 
