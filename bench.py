@@ -375,6 +375,15 @@ def main():
     from speechain_b200.module.acoustic_frontend import AcousticFrontend
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    if world > 1 and not os.environ.get("SFE_BENCH_NOBIND"):
+        # one block of host cores per rank: eight interpreters that wander over the same cores (and their
+        # hyper-thread siblings) were the scaling limit of round 1, not the GPUs
+        try:
+            cpus = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cpus) // world)
+            os.sched_setaffinity(0, set(cpus[local * per:(local + 1) * per]))
+        except (AttributeError, OSError):
+            pass
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
@@ -568,7 +577,8 @@ def main():
     }
     if also is not None:
         line["also"] = also
-    line["roofline"]["kernel"] = os.environ.get("SFE_KERNEL", "default: tile kernel for the recipe plans, else gather")
+    gather = os.environ.get("SFE_KERNEL", "").startswith("g") or args.workload in ("c3", "c5")
+    line["roofline"]["kernel"] = "sfe::fused_frontend_kernel" if gather else "sfe::tile_frontend_kernel"
     traffic_file = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
     if os.path.exists(traffic_file):
         with open(traffic_file) as f:

@@ -271,3 +271,29 @@ def test_torch_randint_restatement_matches_torch():
         rng = O.TorchCpuRandint(seed)
         for lo, hi, size in [(0, 31, (64, 2)), (0, 50, (64, 2)), (6, 100, (1,)), (3, 2000, (5, 7))]:
             assert np.array_equal(torch.randint(lo, hi, size).numpy(), rng.randint(lo, hi, size))
+
+
+def test_staged_reference_modules_equal_the_port():
+    """bench.py's CPU arm: oracle/_ref (the reference's own modules, staged by oracle/build_ref.py) and the port
+    (oracle/ref_port_torch.py) must be interchangeable bit for bit, masks included."""
+    import torch
+
+    from oracle import build_ref, ref_modules
+    from oracle import ref_port_torch as port
+    if not build_ref.build(quiet=True):
+        pytest.skip("no /root/reference and nothing staged under oracle/_ref")
+    import bench
+    for name, lens in (("c2", [50000, 40000, 32123, 8000]), ("c3", [44100, 22050]), ("c4", [48000, 30000])):
+        w = dict(bench.WORKLOADS[name])
+        fc = w["frontend"]
+        sr = fc.get("sr", 16000)
+        win = int(fc["win_length"] * sr) if isinstance(fc["win_length"], float) else fc["win_length"]
+        args = (sr, fc.get("n_fft") or win, fc["n_mels"], fc.get("fmin", 0.0), fc.get("fmax"))
+        wav = bench.make_batch(w, lens, 3, "cpu")
+        wl = torch.tensor(lens)
+        bench.cpu_pass(dict(w), wav.clone(), wl.clone(), ref_modules.mel_weight(*args), ref_modules)  # (builds the modules: nn.Conv1d init draws)
+        torch.manual_seed(1)
+        a = bench.cpu_pass(dict(w), wav.clone(), wl.clone(), ref_modules.mel_weight(*args), ref_modules)
+        torch.manual_seed(1)
+        b = bench.cpu_pass(dict(w), wav.clone(), wl.clone(), port.mel_weight(*args), port)
+        assert torch.equal(a.nan_to_num(), b.nan_to_num()), name
