@@ -486,20 +486,22 @@ def main():
     res_host = torch.empty(B, dtype=torch.int64).pin_memory()
     main_stream = torch.cuda.current_stream()
 
-    def e2e_loop(n):
+    def e2e_loop(n, upload=None):
         # double-buffered: the copy of step i+1 overlaps the kernels of step i
+        if upload is None:
+            upload = lambda k, slot: ops.upload_waveforms(host[k], wl_host, out=dbuf[slot])  # noqa: E731
         for s in range(2):
             free[s].record(main_stream)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(free[0])
-            ops.upload_waveforms(host[0], wl_host, out=dbuf[0])
+            upload(0, 0)
             ready[0].record(copy_stream)
         for i in range(n):
             s = i % 2
             if i + 1 < n:
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(free[1 - s])
-                    ops.upload_waveforms(host[(i + 1) % 2], wl_host, out=dbuf[1 - s])
+                    upload((i + 1) % 2, 1 - s)
                     ready[1 - s].record(copy_stream)
             main_stream.wait_event(ready[s])
             ylen = chain(dbuf[s], wl_host, epoch=epoch)[1]       # lengths arrive on the host, like a collated batch
@@ -521,6 +523,24 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
+
+    # ---- (3b) the same loop with 16-bit PCM on the host (the corpus' own sample type): half the bytes on PCIe,
+    #      the int16 -> float32 conversion of the data loader (soundfile) moves to the GPU ----
+    host16 = [(h * 32768.0).round().clamp_(-32768, 32767).to(torch.int16).pin_memory() for h in host]
+    stage16 = [torch.empty((ops.upload_i16_stage_bytes(B, T),), dtype=torch.uint8, device=dev) for _ in range(2)]
+    up16 = lambda k, slot: ops.upload_waveforms_i16(host16[k], wl_host, out=dbuf[slot], stage=stage16[slot])  # noqa: E731
+    e2e_loop(4, up16)
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    e2e_loop(e2e_steps, up16)
+    g1.record()
+    barrier()
+    t = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e16_ms = float(t.item())
+    del host16, stage16
     also = None
     if not args.no_also and args.workload == "c2":
         del batches, host, dbuf
@@ -575,6 +595,11 @@ def main():
                      "step_algorithmic_bytes": step_bytes,
                      "step_gbs": step_bytes / (ms_total / steps * 1e-3) / 1e9},
     }
+    line["e2e_pcm16"] = {"value": total_audio * e2e_steps / (e2e16_ms * 1e-3), "unit": "audio-s/s",
+                         "h2d_bytes_per_step": ops.upload_bytes(wl_host) // 2 + 8 * B, "d2h_bytes_per_step": 8 * B,
+                         "note": "as e2e, but the pinned host batch holds 16-bit PCM (what the corpus files hold): "
+                                 "ops.upload_waveforms_i16 moves two bytes per sample and converts x/32768 on the GPU, "
+                                 "bit-identical to the float path (tests/test_gpu_parity.py)"}
     if also is not None:
         line["also"] = also
     gather = os.environ.get("SFE_KERNEL", "").startswith("g") or args.workload in ("c3", "c5")

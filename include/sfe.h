@@ -214,6 +214,14 @@ int sfe_upload_waveforms(const float* wav_host, int64_t host_pitch, const int64_
                          float* wav_dev, int64_t dev_pitch, void* stream);
 /* Bytes sfe_upload_waveforms moves for these lengths (valid samples + the padding inside row groups). */
 int64_t sfe_upload_bytes(const int64_t* len_host, int32_t B);
+/* The same staging for 16-bit PCM, the sample type speech corpora are stored in: half the bytes cross PCIe and
+ * the GPU does the conversion soundfile does on the CPU (utilbox/data_loading_util.py:71-78, sf.read(dtype=
+ * "float32"): x / 32768, exact in fp32).  The valid prefix of every int16 row is copied into `stage_dev`
+ * (sfe_upload_i16_stage_bytes(B, T) bytes: the lengths, then the rows) and one kernel writes the fp32 rows
+ * of `wav_dev` (B, dev_pitch); device samples beyond a row's length are not written. */
+int64_t sfe_upload_i16_stage_bytes(int32_t B, int64_t T);
+int sfe_upload_waveforms_i16(const int16_t* wav_host, int64_t host_pitch, const int64_t* len_host, int32_t B,
+                             void* stage_dev, int64_t stage_bytes, float* wav_dev, int64_t dev_pitch, void* stream);
 
 /* DeltaFeature.forward (delta_feat.py:57-81): (B, F, D) -> (B, F, D*(order+1)). */
 int sfe_delta(const float* feat, int32_t B, int64_t F, int32_t D, int32_t order, int32_t N,

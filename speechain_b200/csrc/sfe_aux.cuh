@@ -188,6 +188,8 @@ __device__ __forceinline__ void cubic_w(float t, float (&w)[4]) {
 }
 
 __global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ NormParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float nsm[];  // mean[D] | 1/std[D] | fmask[D]
   const int b = blockIdx.y, D = p.D;
   float* s_mean = nsm;
@@ -533,6 +535,35 @@ __global__ void __launch_bounds__(M2L_THREADS) mel2linear_kernel(const float* __
         if (f >= len && len != max_len) v = 0.f;  // only utterances shorter than the longest are silenced
         lin[row * K + k] = fmaxf(v, clampv);
       }
+    }
+  }
+}
+
+// 16-bit PCM rows -> fp32 rows (x / 32768: what soundfile's float32 read does, utilbox/data_loading_util.py:71-78).
+// grid (chunks, B); a thread converts eight samples: one 128-bit load, two 128-bit stores.
+__global__ void __launch_bounds__(256) pcm16_to_float_kernel(const long long* __restrict__ len, const short* __restrict__ src,
+                                                             long long src_pitch, float* __restrict__ dst,
+                                                             long long dst_pitch, int vec_ok) {
+  const int b = blockIdx.y;
+  const long long n = len[b];
+  const short* s = src + static_cast<long long>(b) * src_pitch;
+  float* d = dst + static_cast<long long>(b) * dst_pitch;
+  const float k = 1.f / 32768.f;
+  for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x * 8) {
+    if (vec_ok && i + 8 <= n) {
+      const int4 v = *reinterpret_cast<const int4*>(s + i);
+      const int w[4] = {v.x, v.y, v.z, v.w};
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        o[2 * j] = static_cast<float>(static_cast<short>(w[j] & 0xffff)) * k;
+        o[2 * j + 1] = static_cast<float>(static_cast<short>(w[j] >> 16)) * k;
+      }
+      *reinterpret_cast<float4*>(d + i) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(d + i + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    } else {
+      for (long long j = i; j < n && j < i + 8; ++j) d[j] = static_cast<float>(s[j]) * k;
     }
   }
 }

@@ -143,6 +143,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// Programmatic dependent launch (no-ops when the launch does not carry the attribute): let the next kernel of
+// the stream start its prologue on SMs this grid has left / wait until the previous grid has completed and its
+// memory is visible.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
@@ -403,6 +408,8 @@ __global__ void __launch_bounds__((PL::MAXW + 1) * 32, 1) fused_frontend_kernel(
     mbar_expect_tx(tbar, bytes);
     bulk_g2s(smem_u32(tab), p.tables, bytes, tbar);
   }
+  pdl_launch_dependents();
+  pdl_wait();  // (the tables above are constants of the plan; everything below may depend on the previous kernel)
   if (lane == 0 && !producer) {
     mbar_init(bar, 1);       // "full": the unit's descriptor is written and its samples have landed
     mbar_init(bar + 8, 1);   // "empty": the warp has consumed its staging buffer

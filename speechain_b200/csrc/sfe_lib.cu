@@ -104,6 +104,30 @@ static cudaError_t raise_dyn_smem(const void* fn, int bytes) {
   return e;
 }
 
+// Launch with programmatic stream serialisation: the kernel may start (its prologue, up to griddepcontrol.wait)
+// while the previous kernel of the stream drains.  SFE_PDL=0 turns it off (A/B runs).
+template <class Params>
+static cudaError_t launch_pdl(void (*fn)(const Params), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const Params& P) {
+  static const bool on = [] {
+    const char* ev = getenv("SFE_PDL");
+    return !(ev && ev[0] == '0');
+  }();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at;
+  memset(&at, 0, sizeof(at));
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = on ? 1 : 0;
+  void* args[1] = {const_cast<Params*>(&P)};
+  return cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(fn), args);
+}
+
 // SM count of the current device, looked up once per device (hot host path: no driver query per call)
 static int cached_sm_count() {
   static std::mutex mu;
@@ -619,9 +643,10 @@ static int frontend_forward_impl(const sfe_plan* pl, const float* wav, int64_t w
     long long g2 = pl->n_sm;
     if (g2 > nu) g2 = nu;
     const fused_fn fn = energy ? pl->fft->t2[2] : pl->fft->t2[pl->cfg.has_preemphasis ? 1 : 0];
-    fn<<<static_cast<unsigned>(g2), pl->fft->t2_nw * 32, pl->t2_smem, st>>>(P);
+    SFE_CUDA(launch_pdl<FwdParams>(fn, dim3(static_cast<unsigned>(g2)), dim3(pl->fft->t2_nw * 32), pl->t2_smem, st, P));
   } else {
-    pl->fft->fn[pl->cfg.has_preemphasis ? 1 : 0]<<<static_cast<unsigned>(grid), (pl->warps_per_cta + 1) * 32, pl->smem_bytes, st>>>(P);
+    SFE_CUDA(launch_pdl<FwdParams>(pl->fft->fn[pl->cfg.has_preemphasis ? 1 : 0], dim3(static_cast<unsigned>(grid)),
+                                   dim3((pl->warps_per_cta + 1) * 32), pl->smem_bytes, st, P));
   }
   SFE_CUDA(cudaGetLastError());
   return SFE_OK;
@@ -780,7 +805,7 @@ static int normalize_impl(const float* src, float* dst, const int64_t* feat_len,
   const int fpc = static_cast<int>(fpc64 > 0x3fffffff ? 0x3fffffff : fpc64);
   P.frames_per_cta = fpc;
   dim3 grid(static_cast<unsigned>((F + fpc - 1) / fpc), static_cast<unsigned>(B));
-  normalize_kernel<<<grid, 256, 3 * D * sizeof(float), static_cast<cudaStream_t>(stream)>>>(P);
+  SFE_CUDA(launch_pdl<NormParams>(normalize_kernel, grid, dim3(256), 3 * D * sizeof(float), static_cast<cudaStream_t>(stream), P));
   SFE_CUDA(cudaGetLastError());
   return SFE_OK;
 }
@@ -880,6 +905,54 @@ extern "C" int sfe_upload_waveforms(const float* wav_host, int64_t host_pitch, c
     }
     b = e;
   }
+  return SFE_OK;
+}
+
+extern "C" int64_t sfe_upload_i16_stage_bytes(int32_t B, int64_t T) {
+  if (B <= 0 || T <= 0) return 0;
+  const int64_t pitch = (T + 7) / 8 * 8;  // rows start on 16 bytes
+  return (static_cast<int64_t>(B) * 8 + 255) / 256 * 256 + static_cast<int64_t>(B) * pitch * 2;
+}
+
+extern "C" int sfe_upload_waveforms_i16(const int16_t* wav_host, int64_t host_pitch, const int64_t* len_host, int32_t B,
+                                        void* stage_dev, int64_t stage_bytes, float* wav_dev, int64_t dev_pitch,
+                                        void* stream) {
+  if (!wav_host || !len_host || !stage_dev || !wav_dev || B <= 0)
+    return fail(SFE_ERR_BAD_ARG, "sfe_upload_waveforms_i16: bad argument");
+  int64_t T = 0;
+  for (int b = 0; b < B; ++b) {
+    if (len_host[b] < 0 || len_host[b] > host_pitch || len_host[b] > dev_pitch)
+      return fail(SFE_ERR_BAD_ARG, "sfe_upload_waveforms_i16: length exceeds the row pitch");
+    T = std::max<int64_t>(T, len_host[b]);
+  }
+  if (T == 0) return SFE_OK;
+  if (stage_bytes < sfe_upload_i16_stage_bytes(B, T)) return fail(SFE_ERR_BAD_ARG, "sfe_upload_waveforms_i16: staging buffer too small");
+  if (reinterpret_cast<uintptr_t>(stage_dev) & 15) return fail(SFE_ERR_BAD_ARG, "sfe_upload_waveforms_i16: staging buffer must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t pitch = (T + 7) / 8 * 8;
+  long long* len_dev = static_cast<long long*>(stage_dev);
+  short* rows = reinterpret_cast<short*>(static_cast<unsigned char*>(stage_dev) + (static_cast<int64_t>(B) * 8 + 255) / 256 * 256);
+  SFE_CUDA(cudaMemcpyAsync(len_dev, len_host, sizeof(int64_t) * B, cudaMemcpyHostToDevice, st));
+  for (int b = 0; b < B;) {  // same row groups as the fp32 upload
+    int64_t w;
+    const int e = upload_next_group(len_host, B, b, &w);
+    if (w > 0) {
+      if (e - b == 1)
+        SFE_CUDA(cudaMemcpyAsync(rows + b * pitch, wav_host + b * host_pitch, static_cast<size_t>(w) * 2, cudaMemcpyHostToDevice, st));
+      else
+        SFE_CUDA(cudaMemcpy2DAsync(rows + b * pitch, static_cast<size_t>(pitch) * 2, wav_host + b * host_pitch,
+                                   static_cast<size_t>(host_pitch) * 2, static_cast<size_t>(w) * 2,
+                                   static_cast<size_t>(e - b), cudaMemcpyHostToDevice, st));
+    }
+    b = e;
+  }
+  const int vec_ok = !(reinterpret_cast<uintptr_t>(wav_dev) & 15) && (dev_pitch % 4 == 0);
+  int64_t chunks = (T + 256 * 8 - 1) / (256 * 8);
+  const int64_t cap = std::max<int64_t>(1, static_cast<int64_t>(cached_sm_count()) * 8 / B);
+  if (chunks > cap) chunks = cap;
+  pcm16_to_float_kernel<<<dim3(static_cast<unsigned>(chunks), static_cast<unsigned>(B)), 256, 0, st>>>(
+      len_dev, rows, pitch, wav_dev, dev_pitch, vec_ok);
+  SFE_CUDA(cudaGetLastError());
   return SFE_OK;
 }
 

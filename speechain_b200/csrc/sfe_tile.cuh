@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
     bulk_g2s(smem_u32(tab), p.tables, b1, tbar);
     if (b2) bulk_g2s(smem_u32(tab + p.o_mtab), p.tables + p.t2_o_sched_g, b2, tbar);
   }
+  pdl_launch_dependents();
   // the bins behind the spectrum carry zero weights in the Mel program: keep them finite (no emit ever lands there)
   for (int i = tid; i < NPB * 2 * TS * (p.t2_rowf - K); i += blockDim.x) {
     const int r = i / (p.t2_rowf - K), c = i - r * (p.t2_rowf - K);
@@ -215,6 +216,7 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
     mbar_init(smem_u32(smem + p.t2_warp + warp * p.t2_warp_bytes + p.t2_stage), 1);
     fence_mbar_init();
   }
+  pdl_wait();  // (so far only shared memory and the plan's constant tables were touched)
   if (blockIdx.x == 0 && p.feat_len)
     for (int b = tid; b < B; b += blockDim.x) p.feat_len[b] = frames_of(__ldg(p.len + b));
   if (warp == 0) {

@@ -412,6 +412,37 @@ def upload_waveforms(wav_host: torch.Tensor, len_host: torch.Tensor, out: Option
     return out
 
 
+def upload_waveforms_i16(wav_host: torch.Tensor, len_host: torch.Tensor, out: Optional[torch.Tensor] = None,
+                         stage: Optional[torch.Tensor] = None, device=None) -> torch.Tensor:
+    """``upload_waveforms`` for 16-bit PCM: wav_host (B, T, 1) or (B, T) int16 CPU (pinned for an asynchronous copy) —
+    the samples as they sit in the corpus files — cross PCIe at two bytes each and become fp32 ``x / 32768`` on the
+    device, bit for bit what ``soundfile.read(dtype="float32")`` hands the reference's data loader
+    (utilbox/data_loading_util.py:71-78).  ``stage`` is an optional reusable uint8 device buffer of at least
+    ``upload_i16_stage_bytes(B, T)`` bytes; returns the fp32 device tensor (samples beyond each length NOT initialised)."""
+    if wav_host.is_cuda or len_host.is_cuda:
+        raise RuntimeError("upload_waveforms_i16 expects host tensors")
+    if wav_host.dtype != torch.int16:
+        raise TypeError(f"upload_waveforms_i16 expects int16 PCM, got {wav_host.dtype}")
+    if not wav_host.is_contiguous():
+        wav_host = wav_host.contiguous()
+    len_host = len_host.long().contiguous()
+    B, T = wav_host.shape[0], wav_host.shape[1]
+    if out is None:
+        out = torch.empty(wav_host.shape, dtype=torch.float32, device=device if device is not None else "cuda")
+    lib = _lib.load()
+    need = int(lib.sfe_upload_i16_stage_bytes(B, T))
+    if stage is None or stage.numel() < need:
+        stage = torch.empty((need,), dtype=torch.uint8, device=out.device)
+    with _on_device(out.device):
+        _lib.check(lib.sfe_upload_waveforms_i16(wav_host.data_ptr(), T, len_host.data_ptr(), B, stage.data_ptr(),
+                                                stage.numel(), out.data_ptr(), T, _stream()))
+    return out
+
+
+def upload_i16_stage_bytes(B: int, T: int) -> int:
+    return int(_lib.load().sfe_upload_i16_stage_bytes(B, T))
+
+
 def upload_bytes(len_host: torch.Tensor) -> int:
     """Bytes ``upload_waveforms`` moves for these lengths (valid samples + the padding inside its row groups)."""
     len_host = len_host.long().contiguous()

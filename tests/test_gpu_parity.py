@@ -613,3 +613,26 @@ def test_checkpoint_load_rebuilds_the_plan():
     b, _ = m(wav, wl)
     valid = int(g["feat_len"][0])
     assert torch.allclose(b[0, :valid][a[0, :valid] > -9.9], a[0, :valid][a[0, :valid] > -9.9] + np.log10(2.0), atol=1e-4)
+
+
+def test_pcm16_upload_equals_the_float_path():
+    """16-bit PCM staged at two bytes per sample and converted on the GPU must be bit-identical to what soundfile's
+    float32 read (x / 32768) gives the reference's loader — and to the fp32 upload of those floats."""
+    g = torch.Generator().manual_seed(21)
+    lens = [30001, 22222, 9999, 17, 1]
+    pcm = torch.randint(-32768, 32768, (len(lens), max(lens), 1), generator=g, dtype=torch.int32).to(torch.int16)
+    pcm[0, :8, 0] = torch.tensor([-32768, 32767, 0, 1, -1, 12345, -12345, 256], dtype=torch.int16)
+    wl = torch.tensor(lens, dtype=torch.int64)
+    dev = torch.full(pcm.shape, float("nan"), device=DEV)
+    ops.upload_waveforms_i16(pcm.pin_memory(), wl, out=dev)
+    want = pcm.float() / 32768.0
+    for i, n in enumerate(lens):
+        assert torch.equal(dev[i, :n].cpu(), want[i, :n])
+        assert torch.isnan(dev[i, n:]).all()  # padding is neither transferred nor written
+    m = Speech2MelSpec(n_mels=80, n_fft=512, win_length=0.025, hop_length=0.010, preemphasis=0.97).to(DEV)
+    a, _ = m(dev, wl.to(DEV))
+    b, _ = m(ops.upload_waveforms(want.pin_memory(), wl, device=DEV), wl.to(DEV))
+    assert torch.equal(a, b)
+    # an odd pitch (rows not 16-byte aligned on the device) takes the scalar path
+    odd = torch.full((len(lens), max(lens) + 3), float("nan"), device=DEV)[:, 1:1 + max(lens)]
+    assert ops.upload_i16_stage_bytes(len(lens), max(lens)) > 2 * sum(lens)
