@@ -204,6 +204,25 @@ int sfe_normalize(const float* src, float* dst, const int64_t* feat_len, int32_t
                   float* std_out, int32_t src_has_pad, float pad_value, const sfe_warp* warp,
                   const sfe_masks* masks, void* stream);
 
+/* Waveform pre-normalisation before the STFT (the `pre_stft_norm` key, speech2linear.py:165-187): pre-emphasis
+ * y[n] = x[n] - a x[n-1] with samples at or beyond each length forced to zero, then over the WHOLE padded row
+ * (padding included, like the reference) mode 1 "mean_std": (y - mean) / std (unbiased; B must be 1 — the reference
+ * only broadcasts for one utterance), mode 2 "min_max": (y - min) / (max - min) * 2 - 1.  `out` (B, out_pitch)
+ * receives full rows (the padding is no longer silence afterwards: the STFT that follows reads whole rows);
+ * `scratch` holds 2 * B doubles. */
+int sfe_prestft_norm(const float* wav, int64_t wav_pitch, const int64_t* wav_len, int32_t B, int64_t T,
+                     int32_t has_preemphasis, float preemphasis, int32_t mode, double* scratch, float* out,
+                     int64_t out_pitch, void* stream);
+
+/* sfe_normalize writing bfloat16 (round to nearest even, what `.to(torch.bfloat16)` does): the layout and dtype the
+ * first consumer takes under AMP — Conv2dPrenet.forward, prenet/conv2d.py:220-276, unsqueezes (B, F, D) and runs its
+ * Conv2d under the model's autocast — so the cast pass over the feature tensor disappears and the last write of the
+ * path is two bytes per element.  Never in place (src stays fp32). */
+int sfe_normalize_bf16(const float* src, uint16_t* dst_bf16, const int64_t* feat_len, int32_t B, int64_t F, int32_t D,
+                       const void* stats, int32_t stats_fixed, float clamp, int32_t use_mean, int32_t use_std,
+                       const float* mean, const float* std, int32_t per_utt, int32_t src_has_pad, float pad_value,
+                       const sfe_warp* warp, const sfe_masks* masks, void* stream);
+
 /* Ragged host->device staging of a padded waveform batch (the step before the path:
  * Model.batch_to_cuda, model/abs.py:329-352, copies the zero padding too).  Copies the first
  * len_host[b] samples of every row from (pinned) host memory; neighbouring rows of similar length

@@ -64,6 +64,9 @@ SYMBOLS = {
     "sfe_running_update": (C.c_int, [_vp, _i32, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "sfe_normalize": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i32, _vp, _i32, _f32, _i32, _i32, _vp, _vp, _i32, _vp, _vp,
                                 _i32, _f32, C.POINTER(SfeWarp), C.POINTER(SfeMasks), _vp]),
+    "sfe_prestft_norm": (C.c_int, [_vp, _i64, _vp, _i32, _i64, _i32, _f32, _i32, _vp, _vp, _i64, _vp]),
+    "sfe_normalize_bf16": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i32, _vp, _i32, _f32, _i32, _i32, _vp, _vp, _i32,
+                                     _i32, _f32, C.POINTER(SfeWarp), C.POINTER(SfeMasks), _vp]),
     "sfe_upload_waveforms": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _i64, _vp]),
     "sfe_upload_bytes": (C.c_int64, [_vp, _i32]),
     "sfe_upload_i16_stage_bytes": (C.c_int64, [_i32, _i64]),

@@ -155,6 +155,7 @@ __global__ void running_update_kernel(const float* __restrict__ packed, int D, f
 struct NormParams {
   const float* src;
   float* dst;
+  unsigned short* dst16;  // if set, the result is written here as bfloat16 (round to nearest even) instead of dst
   const long long* flen;
   int B;
   long long F;
@@ -177,6 +178,16 @@ struct NormParams {
   int frames_per_cta;
   long long* zero_sums;  // optional (B, D, 2) sums buffer to clear for the next step (double-buffered scratch)
 };
+
+// fp32 -> bf16 bits, round to nearest even (NaN stays NaN): what torch's .to(torch.bfloat16) does
+__device__ __forceinline__ unsigned int bf16_bits(float f) {
+  const unsigned int u = __float_as_uint(f);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (u >> 16) | 0x40u;
+  return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
+}
+__device__ __forceinline__ uint2 bf16x4(float4 x) {
+  return make_uint2(bf16_bits(x.x) | (bf16_bits(x.y) << 16), bf16_bits(x.z) | (bf16_bits(x.w) << 16));
+}
 
 __device__ __forceinline__ void cubic_w(float t, float (&w)[4]) {
   const float A = -0.75f;
@@ -245,8 +256,9 @@ __global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ 
   const long long t1 = min(p.F, t0 + p.frames_per_cta);
   const float* src = p.src + static_cast<long long>(b) * p.F * D;
   float* dst = p.dst + static_cast<long long>(b) * p.F * D;
+  unsigned short* dst16 = p.dst16 ? p.dst16 + static_cast<long long>(b) * p.F * D : nullptr;
   const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.src) & 15) == 0) &&
-                   ((reinterpret_cast<uintptr_t>(p.dst) & 15) == 0);
+                   (p.dst16 ? ((reinterpret_cast<uintptr_t>(p.dst16) & 7) == 0) : ((reinterpret_cast<uintptr_t>(p.dst) & 15) == 0));
   const int W = vec ? D / 4 : D;  // work items per frame
   // thread -> (row within a group of rows, column chunk): no per-element index arithmetic
   const int rows = max(1, static_cast<int>(blockDim.x) / W);
@@ -281,7 +293,8 @@ __global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ 
           if (tmask || fv[e] != 0.f) v = fillv;
           xv[e] = v;
         }
-        __stcs(dp + static_cast<long long>(t) * W, x);
+        if (dst16) __stcs(reinterpret_cast<uint2*>(dst16) + static_cast<long long>(t) * W + c, bf16x4(x));
+        else __stcs(dp + static_cast<long long>(t) * W, x);
       };
       const float4 padv = make_float4(p.pad_value, p.pad_value, p.pad_value, p.pad_value);
       const bool synth = !p.src_has_pad;
@@ -337,7 +350,8 @@ __global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ 
           if (tmask || fv[e] != 0.f) v = fillv;
           xv[e] = v;
         }
-        *(reinterpret_cast<float4*>(dst + t * D) + c) = x;
+        if (dst16) *(reinterpret_cast<uint2*>(dst16 + t * D) + c) = bf16x4(x);
+        else *(reinterpret_cast<float4*>(dst + t * D) + c) = x;
       } else {
         float v;
         if (is_pad) v = p.pad_value;
@@ -348,7 +362,8 @@ __global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ 
         } else v = src[t * D + c];
         v = (v - mv[0]) * rv[0];
         if (tmask || fv[0] != 0.f) v = fillv;
-        dst[t * D + c] = v;
+        if (dst16) dst16[t * D + c] = static_cast<unsigned short>(bf16_bits(v));
+        else dst[t * D + c] = v;
       }
     }
   }
@@ -565,6 +580,75 @@ __global__ void __launch_bounds__(256) pcm16_to_float_kernel(const long long* __
     } else {
       for (long long j = i; j < n && j < i + 8; ++j) d[j] = static_cast<float>(s[j]) * k;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// waveform pre-normalisation before the STFT                               speech2linear.py:165-187
+// y[n] = x[n] - a x[n-1] (n < len, else 0), statistics over the WHOLE padded row like the reference
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float prenorm_sample(const float* __restrict__ x, long long n, long long len, int has_pre, float a) {
+  if (n >= len) return 0.f;
+  float v = x[n];
+  if (has_pre && n > 0) v = v - a * x[n - 1];
+  return v;
+}
+
+// grid (B): mode 1 -> scratch[b] = {sum, sum of squares} (fp64), mode 2 -> {min, max}
+__global__ void __launch_bounds__(1024) prenorm_stats_kernel(const float* __restrict__ wav, long long pitch,
+                                                             const long long* __restrict__ len, long long T, int has_pre,
+                                                             float a, int mode, double* __restrict__ scratch) {
+  const int b = blockIdx.x;
+  const float* x = wav + static_cast<long long>(b) * pitch;
+  const long long n_valid = min(len[b], T);
+  double u = (mode == 1) ? 0.0 : 3.0e38, v = (mode == 1) ? 0.0 : -3.0e38;
+  for (long long n = threadIdx.x; n < T; n += blockDim.x) {
+    const double y = static_cast<double>(prenorm_sample(x, n, n_valid, has_pre, a));
+    if (mode == 1) { u += y; v = fma(y, y, v); }
+    else { u = fmin(u, y); v = fmax(v, y); }
+  }
+  __shared__ double su[32], sv[32];
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ou = __shfl_xor_sync(0xffffffffu, u, o), ov = __shfl_xor_sync(0xffffffffu, v, o);
+    if (mode == 1) { u += ou; v += ov; } else { u = fmin(u, ou); v = fmax(v, ov); }
+  }
+  if ((threadIdx.x & 31) == 0) { su[threadIdx.x >> 5] = u; sv[threadIdx.x >> 5] = v; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int nw = blockDim.x >> 5;
+    u = (threadIdx.x < nw) ? su[threadIdx.x] : ((mode == 1) ? 0.0 : 3.0e38);
+    v = (threadIdx.x < nw) ? sv[threadIdx.x] : ((mode == 1) ? 0.0 : -3.0e38);
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ou = __shfl_xor_sync(0xffffffffu, u, o), ov = __shfl_xor_sync(0xffffffffu, v, o);
+      if (mode == 1) { u += ou; v += ov; } else { u = fmin(u, ou); v = fmax(v, ov); }
+    }
+    if (threadIdx.x == 0) { scratch[2 * b] = u; scratch[2 * b + 1] = v; }
+  }
+}
+
+// grid (chunks, B): mode 1 (y - mean) / std (unbiased), mode 2 (y - min) / (max - min) * 2 - 1, whole row
+__global__ void __launch_bounds__(256) prenorm_apply_kernel(const float* __restrict__ wav, long long pitch,
+                                                            const long long* __restrict__ len, long long T, int has_pre,
+                                                            float a, int mode, const double* __restrict__ scratch,
+                                                            float* __restrict__ out, long long out_pitch) {
+  const int b = blockIdx.y;
+  const float* x = wav + static_cast<long long>(b) * pitch;
+  float* o = out + static_cast<long long>(b) * out_pitch;
+  const long long n_valid = min(len[b], T);
+  float c0, c1;
+  if (mode == 1) {
+    const double s1 = scratch[2 * b], s2 = scratch[2 * b + 1], dn = static_cast<double>(T);
+    const double mean = s1 / dn;
+    c0 = static_cast<float>(mean);
+    c1 = static_cast<float>(sqrt(fmax((s2 - s1 * mean) / (dn - 1.0), 0.0)));
+  } else {
+    c0 = static_cast<float>(scratch[2 * b]);
+    c1 = static_cast<float>(scratch[2 * b + 1]) - c0;
+  }
+  for (long long n = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; n < T;
+       n += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float y = prenorm_sample(x, n, n_valid, has_pre, a);
+    o[n] = (mode == 1) ? (y - c0) / c1 : (y - c0) / c1 * 2.f - 1.f;
   }
 }
 

@@ -733,7 +733,17 @@ static int normalize_impl(const float* src, float* dst, const int64_t* feat_len,
                           const void* stats, int32_t stats_fixed, float clamp, int32_t use_mean, int32_t use_std,
                           const float* mean, const float* std, int32_t per_utt, float* mean_out, float* std_out,
                           int32_t src_has_pad, float pad_value, const sfe_warp* warp, const sfe_masks* masks,
-                          void* stream, int64_t* zero_sums);
+                          void* stream, int64_t* zero_sums, uint16_t* dst16 = nullptr);
+
+extern "C" int sfe_normalize_bf16(const float* src, uint16_t* dst_bf16, const int64_t* feat_len, int32_t B, int64_t F,
+                                  int32_t D, const void* stats, int32_t stats_fixed, float clamp, int32_t use_mean,
+                                  int32_t use_std, const float* mean, const float* std, int32_t per_utt, int32_t src_has_pad,
+                                  float pad_value, const sfe_warp* warp, const sfe_masks* masks, void* stream) {
+  if (!dst_bf16) return fail(SFE_ERR_BAD_ARG, "sfe_normalize_bf16: NULL destination");
+  return normalize_impl(src, reinterpret_cast<float*>(dst_bf16), feat_len, B, F, D, stats, stats_fixed, clamp, use_mean,
+                        use_std, mean, std, per_utt, nullptr, nullptr, src_has_pad, pad_value, warp, masks, stream, nullptr,
+                        dst_bf16);
+}
 
 extern "C" int sfe_normalize(const float* src, float* dst, const int64_t* feat_len, int32_t B, int64_t F, int32_t D,
                              const void* stats, int32_t stats_fixed, float clamp, int32_t use_mean, int32_t use_std,
@@ -748,12 +758,12 @@ static int normalize_impl(const float* src, float* dst, const int64_t* feat_len,
                           const void* stats, int32_t stats_fixed, float clamp, int32_t use_mean, int32_t use_std,
                           const float* mean, const float* std, int32_t per_utt, float* mean_out, float* std_out,
                           int32_t src_has_pad, float pad_value, const sfe_warp* warp, const sfe_masks* masks,
-                          void* stream, int64_t* zero_sums) {
+                          void* stream, int64_t* zero_sums, uint16_t* dst16) {
   if (!src || !dst || !feat_len) return fail(SFE_ERR_BAD_ARG, "sfe_normalize: NULL argument");
   if (B <= 0 || F <= 0 || D <= 0 || D > 4096) return fail(SFE_ERR_BAD_ARG, "sfe_normalize: bad shape");
   const bool warp_on = warp && warp->enabled;
   if (warp_on) {
-    if (src == dst) return fail(SFE_ERR_BAD_ARG, "sfe_normalize: the time warp cannot run in place");
+    if (!dst16 && src == dst) return fail(SFE_ERR_BAD_ARG, "sfe_normalize: the time warp cannot run in place");
     if (!(warp->center > 0 && warp->center < warp->minlen && warp->pos > 0 && warp->pos < warp->minlen &&
           warp->minlen <= F))
       return fail(SFE_ERR_BAD_ARG, "sfe_normalize: inconsistent warp descriptor");
@@ -761,7 +771,8 @@ static int normalize_impl(const float* src, float* dst, const int64_t* feat_len,
   NormParams P;
   memset(&P, 0, sizeof(P));
   P.src = src;
-  P.dst = dst;
+  P.dst = dst16 ? nullptr : dst;
+  P.dst16 = dst16;
   P.flen = reinterpret_cast<const long long*>(feat_len);
   P.B = B;
   P.F = F;
@@ -905,6 +916,27 @@ extern "C" int sfe_upload_waveforms(const float* wav_host, int64_t host_pitch, c
     }
     b = e;
   }
+  return SFE_OK;
+}
+
+extern "C" int sfe_prestft_norm(const float* wav, int64_t wav_pitch, const int64_t* wav_len, int32_t B, int64_t T,
+                                int32_t has_preemphasis, float preemphasis, int32_t mode, double* scratch, float* out,
+                                int64_t out_pitch, void* stream) {
+  if (!wav || !wav_len || !scratch || !out || B <= 0 || T <= 0 || wav_pitch < T || out_pitch < T)
+    return fail(SFE_ERR_BAD_ARG, "sfe_prestft_norm: bad argument");
+  if (mode != 1 && mode != 2) return fail(SFE_ERR_BAD_ARG, "sfe_prestft_norm: mode must be 1 (mean_std) or 2 (min_max)");
+  if (mode == 1 && B != 1)
+    return fail(SFE_ERR_BAD_ARG, "pre_stft_norm='mean_std' only broadcasts for batch size 1 (speech2linear.py:179 has no keepdim)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  prenorm_stats_kernel<<<static_cast<unsigned>(B), 1024, 0, st>>>(wav, wav_pitch, reinterpret_cast<const long long*>(wav_len),
+                                                                 T, has_preemphasis, preemphasis, mode, scratch);
+  SFE_CUDA(cudaGetLastError());
+  int64_t chunks = (T + 256 * 8 - 1) / (256 * 8);
+  const int64_t cap = std::max<int64_t>(1, static_cast<int64_t>(cached_sm_count()) * 8 / B);
+  if (chunks > cap) chunks = cap;
+  prenorm_apply_kernel<<<dim3(static_cast<unsigned>(chunks), static_cast<unsigned>(B)), 256, 0, st>>>(
+      wav, wav_pitch, reinterpret_cast<const long long*>(wav_len), T, has_preemphasis, preemphasis, mode, scratch, out, out_pitch);
+  SFE_CUDA(cudaGetLastError());
   return SFE_OK;
 }
 

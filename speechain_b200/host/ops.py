@@ -347,10 +347,25 @@ def running_update(packed: torch.Tensor, D: int, weight: float, first: bool, upd
 
 def normalize(src: torch.Tensor, feat_len: torch.Tensor, *, dst: Optional[torch.Tensor] = None, stats=None,
               clamp: float = 1e-10, use_mean=True, use_std=True, mean=None, std=None, per_utt=False,
-              want_utt_stats=False, src_has_pad=True, pad_value=0.0, warp=None, masks: Optional[DeviceMasks] = None):
-    """(x-mean)/std [+ warp] [+ masks]; in place unless ``dst`` is given or a warp is requested."""
+              want_utt_stats=False, src_has_pad=True, pad_value=0.0, warp=None, masks: Optional[DeviceMasks] = None,
+              out_bf16: bool = False):
+    """(x-mean)/std [+ warp] [+ masks]; in place unless ``dst`` is given or a warp is requested.
+    ``out_bf16``: the result is written as a new bfloat16 tensor (sfe_normalize_bf16) — the dtype an AMP prenet takes."""
     _need_cuda(src, "feat")
     B, F, D = src.shape
+    if out_bf16:
+        if want_utt_stats:
+            raise ValueError("per-utterance statistics outputs are not available with out_bf16")
+        out = torch.empty((B, F, D), dtype=torch.bfloat16, device=src.device)
+        w = _lib.SfeWarp(1, int(warp[0]), int(warp[1]), int(warp[2])) if warp is not None else None
+        ms = masks.struct() if masks is not None else None
+        with _on_device(src.device):
+            _lib.check(_lib.load().sfe_normalize_bf16(
+                _ptr(src), _ptr(out), _ptr(feat_len), B, F, D, _ptr(stats),
+                int(stats is not None and stats.dtype == torch.int64), float(clamp), int(use_mean), int(use_std),
+                _ptr(mean), _ptr(std), int(per_utt), int(src_has_pad), float(pad_value),
+                C.byref(w) if w is not None else None, C.byref(ms) if ms is not None else None, _stream()))
+        return out, None, None
     if warp is not None and dst is None:
         dst = torch.empty_like(src)
     if dst is None:
@@ -370,6 +385,24 @@ def normalize(src: torch.Tensor, feat_len: torch.Tensor, *, dst: Optional[torch.
             _ptr(mean), _ptr(std), int(per_utt), _ptr(mo), _ptr(so), int(src_has_pad), float(pad_value),
             C.byref(w) if w is not None else None, C.byref(ms) if ms is not None else None, _stream()))
     return dst, mo, so
+
+
+def prestft_norm(wav: torch.Tensor, wav_len: torch.Tensor, *, preemphasis: Optional[float], mode: str) -> torch.Tensor:
+    """Pre-emphasis + zero beyond each length + waveform normalisation over the whole padded row
+    (speech2linear.py:165-187) -> new (B, T) fp32 tensor; see sfe_prestft_norm."""
+    _need_cuda(wav, "speech")
+    B, T = wav.shape
+    if mode == "mean_std" and B != 1:
+        raise RuntimeError("pre_stft_norm='mean_std' only broadcasts for batch size 1 (speech2linear.py:179 has no keepdim)")
+    if wav.stride(1) != 1:
+        wav = wav.contiguous()
+    out = torch.empty((B, T), dtype=torch.float32, device=wav.device)
+    scratch = torch.empty((B, 2), dtype=torch.float64, device=wav.device)
+    with _on_device(wav.device):
+        _lib.check(_lib.load().sfe_prestft_norm(
+            _ptr(wav), int(wav.stride(0)), _ptr(wav_len), B, T, int(preemphasis is not None),
+            float(preemphasis or 0.0), 1 if mode == "mean_std" else 2, _ptr(scratch), _ptr(out), T, _stream()))
+    return out
 
 
 def delta(feat: torch.Tensor, order: int, N: int) -> torch.Tensor:

@@ -28,10 +28,19 @@ from .norm.feat_norm import FeatureNormalization
 
 
 class AcousticFrontend(Module):
-    def module_init(self, frontend: dict, normalize=None, specaug: Optional[dict] = None):
+    def module_init(self, frontend: dict, normalize=None, specaug: Optional[dict] = None, out_dtype=None):
         """``frontend`` / ``normalize`` / ``specaug`` take the same YAML blocks as ASREncoder
         (encoder/asr.py:44-68): frontend = {type:…, conf:{…}} or the conf dict itself;
-        normalize = True | dict | None; specaug = dict | None."""
+        normalize = True | dict | None; specaug = dict | None.
+        ``out_dtype="bfloat16"`` (extension): the last pass of the chain writes bfloat16 (B, F, D) — the layout and
+        dtype Conv2dPrenet consumes under AMP (prenet/conv2d.py:220-276) — instead of fp32 followed by autocast's
+        cast pass."""
+        if out_dtype in ("bfloat16", "bf16", torch.bfloat16):
+            self.out_dtype = torch.bfloat16
+        elif out_dtype in (None, "float32", "fp32", torch.float32):
+            self.out_dtype = None
+        else:
+            raise ValueError(f"out_dtype must be float32 or bfloat16, got {out_dtype!r}")
         conf = frontend.get("conf", frontend) if isinstance(frontend, dict) else {}
         self.frontend = Speech2MelSpec(**conf)
         self.frontend.collect_stats = False
@@ -52,7 +61,10 @@ class AcousticFrontend(Module):
         s2l = fe.speech2linear
         norm: Optional[FeatureNormalization] = getattr(self, "normalize", None)
         aug: Optional[SpecAugment] = getattr(self, "specaug", None) if self.training else None
+        bf16 = getattr(self, "out_dtype", None) == torch.bfloat16
         if fe.delta_order is not None or fe.return_energy or s2l.pre_stft_norm is not None:
+            if bf16:
+                raise NotImplementedError("out_dtype=bfloat16 is available for the fused log-Mel chain only")
             return self._unfused(feat, feat_len, epoch, domain)
         if norm is not None and not (norm.mean_norm or norm.std_norm):
             norm = None
@@ -71,6 +83,8 @@ class AcousticFrontend(Module):
         if aug is not None:
             warp, masks = aug.draw_device(wav.size(0), fe.output_size, flen_host, wav.device)
             if masks is not None and not aug.feat_norm:
+                if bf16:
+                    raise NotImplementedError("out_dtype=bfloat16 is available for the fused log-Mel chain only")
                 return self._unfused(feat, feat_len, epoch, domain, drawn=(warp, masks))
         # masks ride in a kernel epilogue; a time warp needs one out-of-place gather pass, which also
         # carries the normalisation and the masks when the statistics are only known after the first pass
@@ -94,7 +108,7 @@ class AcousticFrontend(Module):
                 std = norm.get_buffer(f"{prefix}_std") if norm.std_norm else None
                 y, ylen = plan.chain(wav, len_dev, norm_mode=1, mean=mean, std=std, use_mean=norm.mean_norm,
                                      use_std=norm.std_norm, masks=fused_masks)
-            elif warp is None and plan.mel_logging and (kind == "utterance" or (kind == "batch" and not norm.training)):
+            elif not bf16 and warp is None and plan.mel_logging and (kind == "utterance" or (kind == "batch" and not norm.training)):
                 y, ylen = plan.chain(wav, len_dev, norm_mode=2, clamp=norm.clamp, use_mean=norm.mean_norm,
                                      use_std=norm.std_norm, masks=fused_masks)
             else:
@@ -104,11 +118,15 @@ class AcousticFrontend(Module):
                 y._sfe_stats = (y._version, out["stats"])
                 HostLengths.remember(ylen, flen_host)
                 y, ylen = norm.forward(y, ylen, group_ids=domain, epoch=epoch, masks=masks, inplace=True,
-                                       src_has_pad=not plan.mel_logging, pad_value=plan.pad_mel, warp=warp)
+                                       src_has_pad=not plan.mel_logging, pad_value=plan.pad_mel, warp=warp,
+                                       out_dtype=torch.bfloat16 if bf16 else None)
                 warp_done = True
         HostLengths.remember(ylen, flen_host)
         if not warp_done:
-            y, _, _ = ops.normalize(y, ylen, warp=warp, masks=masks)
+            y, _, _ = ops.normalize(y, ylen, warp=warp, masks=masks, out_bf16=bf16)
+        elif bf16 and y.dtype != torch.bfloat16:
+            # single-pass schedules end in the frontend kernel (fp32): one conversion pass of the normalise kernel
+            y, _, _ = ops.normalize(y, ylen, use_mean=False, use_std=False, out_bf16=True)
         return y, ylen
 
     def _unfused(self, feat, feat_len, epoch, domain, drawn=None):

@@ -4,6 +4,7 @@ from typing import Optional
 
 import torch
 
+from ...host import ops
 from ...host.ops import FrontendPlan, HostLengths
 from ..abs import Module
 from ._common import ConstHolder, as_float, lengths_pair, make_window, squeeze_speech, to_samples
@@ -75,22 +76,13 @@ class Speech2LinearSpec(Module):
         len_dev, len_host = lengths_pair(speech_len, wav.device)
         in_kernel = True
         if self.pre_stft_norm is not None:
-            # Rare path (no shipped recipe sets it): the statistics need the pre-emphasised signal
-            # including padding (speech2linear.py:177-187), so this one is done with tensor ops.
+            # Rare path (no shipped recipe sets it): the statistics need the pre-emphasised signal including padding
+            # (speech2linear.py:177-187): one reduction + one apply kernel write the normalised rows, and the frontend
+            # kernel then runs without pre-emphasis over whole rows.
             in_kernel = False
-            if self.preemphasis is not None:
-                y = wav.clone()
-                y[:, 1:] -= self.preemphasis * wav[:, :-1]
-                idx = torch.arange(wav.size(1), device=wav.device)[None, :]
-                wav = y.masked_fill(idx >= len_dev[:, None], 0.0)
-            if self.pre_stft_norm == "mean_std":
-                if wav.size(0) != 1:
-                    raise RuntimeError("pre_stft_norm='mean_std' only broadcasts for batch size 1 "
-                                       "(speech2linear.py:179 has no keepdim)")
-                wav = (wav - wav.mean(dim=1, keepdim=True)) / wav.std(dim=1, keepdim=True)
-            else:
-                lo, hi = wav.amin(dim=1, keepdim=True), wav.amax(dim=1, keepdim=True)
-                wav = (wav - lo) / (hi - lo) * 2 - 1
+            if self.pre_stft_norm not in ("mean_std", "min_max"):
+                raise ValueError(f"pre_stft_norm must be 'mean_std' or 'min_max', got {self.pre_stft_norm!r}")
+            wav = ops.prestft_norm(wav, len_dev, preemphasis=self.preemphasis, mode=self.pre_stft_norm)
         return wav, len_dev, len_host, in_kernel
 
     def _kernel_lengths(self, wav, len_dev, in_kernel):
@@ -104,20 +96,19 @@ class Speech2LinearSpec(Module):
         spectra of the padding; reset them like speech2linear.py:226-233 / linear2mel.py:177-187 do."""
         if in_kernel:
             return
-        n = len_dev + 2 * (self.n_fft // 2) if self.stft_config["center"] else len_dev
-        feat_len = torch.div(n - self.n_fft, self.hop_length, rounding_mode="floor") + 1
-        F = next(v for k, v in out.items() if k in ("mel", "lin") and v is not None).size(1)
-        pad = torch.arange(F, device=len_dev.device)[None, :] >= feat_len[:, None]
+        # rows beyond each length: the normalise kernel synthesises them (identity statistics, pad value)
+        feat_len = torch.from_numpy(self._feat_len_host(HostLengths.get(len_dev))).to(len_dev.device)
         if out.get("mel") is not None:
-            out["mel"].masked_fill_(pad[..., None], plan.pad_mel)
+            ops.normalize(out["mel"], feat_len, use_mean=False, use_std=False, src_has_pad=False, pad_value=plan.pad_mel)
         if out.get("lin") is not None:
             import math
             pad_lin = 0.0
             if self.logging:
                 pad_lin = math.log(self.clamp) / (math.log(self.log_base) if self.log_base is not None else 1.0)
-            out["lin"].masked_fill_(pad[..., None], pad_lin)
+            ops.normalize(out["lin"], feat_len, use_mean=False, use_std=False, src_has_pad=False, pad_value=pad_lin)
         if out.get("energy") is not None:
-            out["energy"].masked_fill_(pad, 0.0)
+            ops.normalize(out["energy"].unsqueeze(-1), feat_len, use_mean=False, use_std=False, src_has_pad=False,
+                          pad_value=0.0)
         out["feat_len"] = feat_len
 
     def _feat_len_host(self, len_host):

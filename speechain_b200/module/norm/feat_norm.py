@@ -82,10 +82,14 @@ class FeatureNormalization(Module):
     # ------------------------------------------------------------------------------------
     def forward(self, feat: torch.Tensor, feat_len: torch.Tensor, group_ids=None, epoch: int = None,
                 masks: Optional[DeviceMasks] = None, inplace: bool = False, src_has_pad: bool = True,
-                pad_value: float = 0.0, warp=None):
+                pad_value: float = 0.0, warp=None, out_dtype=None):
         """feat (batch, length, channel) or (batch, length) fp32 CUDA; feat_len (batch,).
         ``masks`` / ``warp`` / ``inplace`` / ``src_has_pad`` are extensions used by AcousticFrontend to fuse
-        SpecAugment (time warp gather + masking) into the same pass; the reference signature is the first four."""
+        SpecAugment (time warp gather + masking) into the same pass; ``out_dtype=torch.bfloat16`` makes that pass
+        write bfloat16 (what an AMP prenet consumes); the reference signature is the first four."""
+        if out_dtype not in (None, torch.float32, torch.bfloat16):
+            raise ValueError(f"out_dtype must be float32 or bfloat16, got {out_dtype}")
+        bf16 = out_dtype == torch.bfloat16
         if self.norm_type == "group":
             assert group_ids is not None, (
                 "You are using group-level feature normalization, but group_ids is not given. "
@@ -112,8 +116,10 @@ class FeatureNormalization(Module):
             HostLengths.remember(feat_len, host.numpy())
         B, _, D = feat.shape
         dst = feat if (inplace and warp is None) else None  # the warp gathers neighbouring rows: never in place
-        common = dict(masks=masks, src_has_pad=src_has_pad, pad_value=pad_value, warp=warp)
-        if dst is None:
+        common = dict(masks=masks, src_has_pad=src_has_pad, pad_value=pad_value, warp=warp, out_bf16=bf16)
+        if bf16:
+            dst = None  # (ops.normalize allocates the bfloat16 result)
+        elif dst is None:
             dst = torch.empty_like(feat)
         if not (self.mean_norm or self.std_norm):
             out, _, _ = ops.normalize(feat, feat_len, dst=dst, **common)

@@ -636,3 +636,45 @@ def test_pcm16_upload_equals_the_float_path():
     # an odd pitch (rows not 16-byte aligned on the device) takes the scalar path
     odd = torch.full((len(lens), max(lens) + 3), float("nan"), device=DEV)[:, 1:1 + max(lens)]
     assert ops.upload_i16_stage_bytes(len(lens), max(lens)) > 2 * sum(lens)
+
+
+@pytest.mark.parametrize("norm", [None, dict(norm_type="utterance"), dict(norm_type="global")])
+def test_bf16_output_is_the_fp32_output_rounded(norm):
+    """the chain can hand the prenet bfloat16 (prenet/conv2d.py:220-276 runs under autocast) — it
+    must be exactly the fp32 result rounded to nearest even, masks included, in training and in eval mode."""
+    lens = [48000, 40001, 33333, 8000]
+    wav = _wave(31, lens).to(DEV)
+    wl = torch.tensor(lens, device=DEV)
+    conf = dict(n_mels=80, n_fft=512, win_length=0.025, hop_length=0.010, sr=16000, preemphasis=0.97)
+    aug = dict(time_warp=False, freq_mask_width=30, freq_mask_num=2, time_mask_width=0.05, time_mask_num=2)
+    a = AcousticFrontend(frontend=dict(conf=conf), normalize=norm, specaug=aug if norm is not None else None).to(DEV)
+    b = AcousticFrontend(frontend=dict(conf=conf), normalize=norm, specaug=aug if norm is not None else None,
+                         out_dtype="bfloat16").to(DEV)
+    for mode in ("train", "eval"):
+        getattr(a, mode)()
+        getattr(b, mode)()
+        torch.manual_seed(5)
+        y32, l32 = a(wav[..., None], wl, epoch=None)
+        torch.manual_seed(5)
+        y16, l16 = b(wav[..., None], wl, epoch=None)
+        assert y16.dtype == torch.bfloat16 and y16.shape == y32.shape and torch.equal(l16, l32)
+        assert torch.equal(y16, y32.to(torch.bfloat16)), f"{norm} {mode}"
+
+
+def test_an_older_larger_plan_still_launches_after_a_smaller_one_was_created():
+    """cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the kernel FUNCTION, and plans share kernel instances
+    (same n_fft): a later, smaller plan must not shrink the limit under an earlier one (recover() builds a no-mel
+    plan next to the training plan; two frontends may differ only in hop or n_mels)."""
+    lens = [24000, 16000]
+    wav = _wave(33, lens).to(DEV)
+    wl = torch.tensor(lens, device=DEV)
+    big = Speech2MelSpec(n_mels=80, n_fft=512, win_length=400, hop_length=160, preemphasis=0.97).to(DEV)
+    a, _ = big(wav[..., None], wl)
+    # smaller users of the same kernel functions: shorter hop (smaller staging), fewer mels, no mel stage at all
+    for small in (Speech2MelSpec(n_mels=80, n_fft=512, win_length=400, hop_length=80, preemphasis=0.97),
+                  Speech2MelSpec(n_mels=40, n_fft=512, win_length=400, hop_length=160, preemphasis=0.97),
+                  Speech2LinearSpec(n_fft=512, win_length=400, hop_length=160, preemphasis=0.97)):
+        small.to(DEV)(wav[..., None], wl)
+        b, _ = big(wav[..., None], wl)
+        torch.cuda.synchronize()
+        assert torch.equal(a, b)
