@@ -132,12 +132,17 @@ int  sfe_mel_schedule(const float* mel_weight_host, int32_t n_mels, int32_t n_bi
  *   masks      NULL or SpecAugment masks applied in the epilogue (needs min over feat_len
  *              already folded into the drawn positions)
  *   skip_pad   if non-zero, mel rows t >= feat_len are left unwritten (a following
- *              sfe_normalize call synthesises them) */
+ *              sfe_normalize call synthesises them)
+ *   wav_len_host  NULL, or a HOST copy of wav_len (the collated batch's lengths, which the data
+ *              loader holds on the host anyway: model/abs.py:329-352 copies them to the device).
+ *              With it the library cuts the batch into per-SM ranges on the host and the kernel
+ *              starts without its length-load -> scan -> search prologue (~2 us per launch).  The
+ *              values must equal wav_len's; results do not depend on whether it is passed. */
 int sfe_frontend_forward(const sfe_plan* plan, const float* wav, int64_t wav_pitch,
                          const int64_t* wav_len, int32_t B, int64_t T_max, float* mel, float* lin,
                          float* energy, int64_t* feat_len, int64_t* stats, const float* norm_mean,
                          const float* norm_std, const sfe_masks* masks, int32_t skip_pad,
-                         void* stream);
+                         void* stream, const int64_t* wav_len_host);
 
 /* The frontend -> normalise -> SpecAugment-mask chain of ASREncoder.forward (encoder/asr.py:103-119)
  * in one call and at most two launches (no time warp; see sfe_normalize for that):
@@ -151,13 +156,15 @@ int sfe_frontend_forward(const sfe_plan* plan, const float* wav, int64_t wav_pit
  *                by the caller between calls; ws_half (0/1) names the half this call accumulates into
  *                and must alternate from call to call on the same scratch; after a failed call zero
  *                the scratch again.
- * mean_out/std_out (B, n_mels), optional: the per-utterance statistics of norm_mode 2. */
+ * mean_out/std_out (B, n_mels), optional: the per-utterance statistics of norm_mode 2.
+ * wav_len_host: as in sfe_frontend_forward (optional host copy of wav_len). */
 int sfe_chain_forward(const sfe_plan* plan, const float* wav, int64_t wav_pitch,
                       const int64_t* wav_len, int32_t B, int64_t T_max, float* mel,
                       int64_t* feat_len, int64_t* stats_ws, int32_t ws_half, int32_t norm_mode,
                       const float* mean,
                       const float* std, float clamp, int32_t use_mean, int32_t use_std,
-                      float* mean_out, float* std_out, const sfe_masks* masks, void* stream);
+                      float* mean_out, float* std_out, const sfe_masks* masks, void* stream,
+                      const int64_t* wav_len_host);
 
 /* LinearSpec2MelSpec.forward on an existing linear spectrogram (linear2mel.py:163-189).
  * lin (B*F, n_fft/2+1) -> mel (B*F, n_mels). */

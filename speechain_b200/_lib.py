@@ -55,9 +55,9 @@ SYMBOLS = {
     "sfe_plan_query": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "sfe_mel_schedule": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _i32]),
     "sfe_frontend_forward": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                       C.POINTER(SfeMasks), _i32, _vp]),
+                                       C.POINTER(SfeMasks), _i32, _vp, _vp]),
     "sfe_chain_forward": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _f32, _i32, _i32,
-                                    _vp, _vp, C.POINTER(SfeMasks), _vp]),
+                                    _vp, _vp, C.POINTER(SfeMasks), _vp, _vp]),
     "sfe_linear2mel_forward": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "sfe_stats_accumulate": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp]),
     "sfe_stats_finalize": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),

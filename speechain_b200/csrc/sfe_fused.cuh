@@ -49,6 +49,7 @@ constexpr int MEL_PAD_BINS = 4;           // zeroed bins behind the power spectr
 constexpr int MASK_INLINE_MAX = 768;      // SFE_MASK_INLINE_MAX
 constexpr int UNIT_TABLE_MAX_B = 256;     // batches up to this size get a per-utterance cost table
 constexpr int REAL_UNIT_COST = 8;         // a unit with real frames costs this many pad-only units
+constexpr int HOST_SPLIT_MAX_GRID = 160;  // tile kernel: grids up to this size can take their work split from the host
 
 // SpecAugment interval descriptors: device arrays, or (small batches) carried in the parameter block
 struct MaskDesc {
@@ -109,6 +110,13 @@ struct FwdParams {
   // [tables (window, twiddles) | emit schedule | control block | stage x2 | power-spectrum tiles x2 | warp scratch]
   int t2_ctrl, t2_stage, t2_stage_floats, t2_p2, t2_pp, t2_rowf, t2_warp, t2_warp_bytes;
   int t2_o_sched_g, t2_sched_floats;  // float offset of the schedule in the device blob; its length
+  // Work split made on the host (the caller knew the lengths there: sfe_frontend_forward's wav_len_host): the CTA
+  // starts without the length load -> scan -> search chain.  hs_cta[c] = {first pair, number of pairs, utterance
+  // of the first pair}; hs_len / hs_pc = samples of every utterance / pair index at which it starts.
+  int hs_on;
+  int hs_cta[HOST_SPLIT_MAX_GRID][3];
+  int hs_len[UNIT_TABLE_MAX_B];
+  int hs_pc[UNIT_TABLE_MAX_B + 1];
   int ms_ng, ms_two, ms_b_ld, ms_d_split, ms_b_off, ms_c_split, ms_tail_a, ms_tail_b;  // sfe_melsched.h
 };
 

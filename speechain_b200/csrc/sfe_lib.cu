@@ -573,20 +573,70 @@ static int fill_masks(const sfe_masks* m, int B, MaskDesc* out, float* fill, con
 static int frontend_forward_impl(const sfe_plan* pl, const float* wav, int64_t wav_pitch, const int64_t* wav_len,
                                  int32_t B, int64_t T_max, float* mel, float* lin, float* energy, int64_t* feat_len,
                                  int64_t* stats, const float* norm_mean, const float* norm_std, const sfe_masks* masks,
-                                 int32_t skip_pad, void* stream, bool zero_stats);
+                                 int32_t skip_pad, void* stream, bool zero_stats, const int64_t* wav_len_host);
 
 extern "C" int sfe_frontend_forward(const sfe_plan* pl, const float* wav, int64_t wav_pitch, const int64_t* wav_len,
                                     int32_t B, int64_t T_max, float* mel, float* lin, float* energy, int64_t* feat_len,
                                     int64_t* stats, const float* norm_mean, const float* norm_std,
-                                    const sfe_masks* masks, int32_t skip_pad, void* stream) {
+                                    const sfe_masks* masks, int32_t skip_pad, void* stream,
+                                    const int64_t* wav_len_host) {
   return frontend_forward_impl(pl, wav, wav_pitch, wav_len, B, T_max, mel, lin, energy, feat_len, stats, norm_mean,
-                               norm_std, masks, skip_pad, stream, true);
+                               norm_std, masks, skip_pad, stream, true, wav_len_host);
+}
+
+// The tile kernel's work split, made on the host when the caller has the lengths there: the same equal-cost cut of
+// the utterance-major pair axis the kernel makes for itself (tile_frontend_kernel's set-up), written into the
+// parameter block.  Returns false (kernel splits for itself) when the batch or the grid is beyond the tables.
+static bool host_split(const sfe_plan* pl, const int64_t* len_host, int B, int64_t F, int upu, bool compact, int grid,
+                       FwdParams* P) {
+  if (!len_host || B > UNIT_TABLE_MAX_B || grid > HOST_SPLIT_MAX_GRID) return false;
+  const int n_fft = pl->cfg.n_fft, hop = pl->cfg.hop_length;
+  long long cum[UNIT_TABLE_MAX_B + 1];
+  int nreal[UNIT_TABLE_MAX_B];
+  long long c = 0, np = 0;
+  for (int b = 0; b < B; ++b) {
+    const long long len = len_host[b];
+    if (len < 0 || len > 0x7ff00000LL) return false;
+    long long fl = (pl->cfg.center ? (len + 2 * (n_fft / 2)) - n_fft : len - n_fft) / hop + 1;
+    fl = fl < 0 ? 0 : (fl > F ? F : fl);
+    const int nr = static_cast<int>((fl + FPW - 1) / FPW);
+    const int n = compact ? nr : upu;
+    nreal[b] = nr;
+    cum[b] = c;
+    P->hs_len[b] = static_cast<int>(len);
+    P->hs_pc[b] = static_cast<int>(np);
+    c += static_cast<long long>(REAL_UNIT_COST) * nr + (n - nr);
+    np += n;
+  }
+  cum[B] = c;
+  P->hs_pc[B] = static_cast<int>(np);
+  auto pair_at_cost = [&](long long x) -> int {
+    int lo = 0, hi = B - 1;  // smallest b whose range ends beyond x
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cum[mid + 1] > x) hi = mid; else lo = mid + 1;
+    }
+    const long long off = x - cum[lo];
+    const long long nr = nreal[lo];
+    const long long tu = (off <= REAL_UNIT_COST * nr) ? (off + REAL_UNIT_COST - 1) / REAL_UNIT_COST : nr + (off - REAL_UNIT_COST * nr);
+    return P->hs_pc[lo] + static_cast<int>(tu);
+  };
+  int b0 = 0;
+  for (int g = 0; g < grid; ++g) {
+    const int plo = pair_at_cost(c * g / grid), phi = pair_at_cost(c * (g + 1) / grid);
+    while (b0 + 1 < B && P->hs_pc[b0 + 1] <= plo) ++b0;
+    P->hs_cta[g][0] = plo;
+    P->hs_cta[g][1] = phi - plo;
+    P->hs_cta[g][2] = b0;
+  }
+  P->hs_on = 1;
+  return true;
 }
 
 static int frontend_forward_impl(const sfe_plan* pl, const float* wav, int64_t wav_pitch, const int64_t* wav_len,
                                  int32_t B, int64_t T_max, float* mel, float* lin, float* energy, int64_t* feat_len,
                                  int64_t* stats, const float* norm_mean, const float* norm_std, const sfe_masks* masks,
-                                 int32_t skip_pad, void* stream, bool zero_stats) {
+                                 int32_t skip_pad, void* stream, bool zero_stats, const int64_t* wav_len_host) {
   if (!pl) return fail(SFE_ERR_BAD_ARG, "sfe_frontend_forward: NULL plan");
   if (!wav || !wav_len) return fail(SFE_ERR_BAD_ARG, "sfe_frontend_forward: wav / wav_len is NULL");
   if (B <= 0 || T_max <= 0 || wav_pitch < T_max) return fail(SFE_ERR_BAD_ARG, "sfe_frontend_forward: bad B / T_max / pitch");
@@ -643,6 +693,13 @@ static int frontend_forward_impl(const sfe_plan* pl, const float* wav, int64_t w
     long long g2 = pl->n_sm;
     if (g2 > nu) g2 = nu;
     const fused_fn fn = energy ? pl->fft->t2[2] : pl->fft->t2[pl->cfg.has_preemphasis ? 1 : 0];
+    static const bool hs_off = [] {  // SFE_HOST_SPLIT=0: A/B runs
+      const char* ev = getenv("SFE_HOST_SPLIT");
+      return ev && ev[0] == '0';
+    }();
+    P.hs_on = 0;
+    if (!hs_off)
+      host_split(pl, wav_len_host, B, F, P.units_per_utt, skip_pad && !lin && !energy, static_cast<int>(g2), &P);
     SFE_CUDA(launch_pdl<FwdParams>(fn, dim3(static_cast<unsigned>(g2)), dim3(pl->fft->t2_nw * 32), pl->t2_smem, st, P));
   } else {
     SFE_CUDA(launch_pdl<FwdParams>(pl->fft->fn[pl->cfg.has_preemphasis ? 1 : 0], dim3(static_cast<unsigned>(grid)),
@@ -825,15 +882,15 @@ extern "C" int sfe_chain_forward(const sfe_plan* pl, const float* wav, int64_t w
                                  int32_t B, int64_t T_max, float* mel, int64_t* feat_len, int64_t* stats_ws,
                                  int32_t ws_half, int32_t norm_mode, const float* mean, const float* std, float clamp,
                                  int32_t use_mean, int32_t use_std, float* mean_out, float* std_out,
-                                 const sfe_masks* masks, void* stream) {
+                                 const sfe_masks* masks, void* stream, const int64_t* wav_len_host) {
   if (!pl) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: NULL plan");
   if (!mel || !feat_len) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: mel / feat_len is NULL");
   if (norm_mode == 0)
     return sfe_frontend_forward(pl, wav, wav_pitch, wav_len, B, T_max, mel, nullptr, nullptr, feat_len, nullptr,
-                                nullptr, nullptr, masks, 0, stream);
+                                nullptr, nullptr, masks, 0, stream, wav_len_host);
   if (norm_mode == 1)
     return sfe_frontend_forward(pl, wav, wav_pitch, wav_len, B, T_max, mel, nullptr, nullptr, feat_len, nullptr,
-                                use_mean ? mean : nullptr, use_std ? std : nullptr, masks, 0, stream);
+                                use_mean ? mean : nullptr, use_std ? std : nullptr, masks, 0, stream, wav_len_host);
   if (norm_mode != 2) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: norm_mode must be 0, 1 or 2");
   if (!stats_ws) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: norm_mode 2 needs stats_ws");
   if (!pl->cfg.mel_logging) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: norm_mode 2 needs a log-mel plan");
@@ -844,7 +901,7 @@ extern "C" int sfe_chain_forward(const sfe_plan* pl, const float* wav, int64_t w
   int64_t* cur = stats_ws + (ws_half ? half : 0);
   int64_t* other = stats_ws + (ws_half ? 0 : half);
   if (int rc = frontend_forward_impl(pl, wav, wav_pitch, wav_len, B, T_max, mel, nullptr, nullptr, feat_len, cur,
-                                     nullptr, nullptr, nullptr, 1, stream, false))
+                                     nullptr, nullptr, nullptr, 1, stream, false, wav_len_host))
     return rc;
   if (int rc = normalize_impl(mel, mel, feat_len, B, sfe_plan_num_frames(pl, T_max), pl->cfg.n_mels, cur, 1, clamp,
                               use_mean, use_std, nullptr, nullptr, 0, mean_out, std_out, 0, pl->proto.pad_mel, nullptr,

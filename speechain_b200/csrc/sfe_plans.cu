@@ -62,6 +62,14 @@ extern "C" int sfe_debug_trace(unsigned long long* t, unsigned int* tag, int cap
 }
 #endif
 
+#if defined(SFE_T2_TRACE)
+extern "C" int sfe_debug_span(unsigned long long* out) {  // development only: [cta][warp][entry, exit] ns
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, sfe::g_t2_span, sizeof(unsigned long long) * 2 * 32 * 256);
+  return 0;
+}
+#endif
+
 #if defined(SFE_T2_PROF)
 extern "C" int sfe_debug_prof(long long* out) {  // development only (tools/prof_tile.py)
   cudaDeviceSynchronize();

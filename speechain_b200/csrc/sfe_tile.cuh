@@ -53,8 +53,18 @@ __device__ __forceinline__ void t2_trace(int tag, int idx) {
   }
 }
 #define SFE_TR(tag, idx) t2_trace(tag, idx)
+// ... and when every warp of every CTA entered / left the kernel (slot = 2 * (32 * cta + warp))
+__device__ unsigned long long g_t2_span[2 * 32 * 256];
+__device__ __forceinline__ void t2_span(int which) {
+  if ((threadIdx.x & 31) != 0 || blockIdx.x >= 256) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  g_t2_span[2 * (32 * blockIdx.x + (threadIdx.x >> 5)) + which] = t;
+}
+#define SFE_SPAN(which) t2_span(which)
 #else
 #define SFE_TR(tag, idx)
+#define SFE_SPAN(which)
 #endif
 // -DSFE_T2_PROF: per-warp cycle totals of the phases of CTA 0 (registers only while running)
 #ifdef SFE_T2_PROF
@@ -164,6 +174,8 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
 
   long long pf_g0 = 0, pf_g1 = 0, pf_g2 = 0;  // (profile builds: kernel entry, set-up done, tables landed)
   SFE_PF_G(pf_g0)
+  SFE_SPAN(0);
+  SFE_TR(1, 0);
   float* tab = reinterpret_cast<float*>(smem);
   unsigned char* ctrl = smem + p.t2_ctrl;
   const uint32_t tbar = smem_u32(ctrl);          // tables landed
@@ -216,10 +228,27 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
     mbar_init(smem_u32(smem + p.t2_warp + warp * p.t2_warp_bytes + p.t2_stage), 1);
     fence_mbar_init();
   }
-  pdl_wait();  // (so far only shared memory and the plan's constant tables were touched)
+  if (p.hs_on) {
+    // The host knew the lengths and cut the batch: tables and this CTA's range come with the parameter block —
+    // nothing here waits for global memory (the length load -> scan -> search chain below is ~2 us of every launch)
+    for (int b = tid; b < B; b += blockDim.x) {
+      const int len = p.hs_len[b];
+      s_len[b] = len;
+      const int fl = (p.center ? (len + 2 * (p.n_fft / 2)) - p.n_fft : len - p.n_fft) / hop + 1;
+      s_flen[b] = fl < 0 ? 0 : (fl > F ? F : fl);
+      s_pc[b] = p.hs_pc[b];
+    }
+    if (tid == 0) {
+      s_pc[B] = p.hs_pc[B];
+      s_misc[1] = p.hs_cta[blockIdx.x][0];
+      s_misc[2] = p.hs_cta[blockIdx.x][1];
+      s_misc[3] = p.hs_cta[blockIdx.x][2];
+    }
+  }
+  pdl_wait();  // (so far only shared memory, the parameter block and the plan's constant tables were touched)
   if (blockIdx.x == 0 && p.feat_len)
     for (int b = tid; b < B; b += blockDim.x) p.feat_len[b] = frames_of(__ldg(p.len + b));
-  if (warp == 0) {
+  if (warp == 0 && !p.hs_on) {
     if (tabled) {
       // exclusive scans of the utterances' costs (a pair with real frames costs REAL_UNIT_COST, one that only
       // holds rows past the utterance's length 1) and pair counts
@@ -283,6 +312,7 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
   }
   __syncthreads();  // barrier inits, the tables of the work split and this CTA's range are visible
   SFE_PF_G(pf_g1)
+  SFE_TR(2, 0);
 
   const int P_lo = s_misc[1], npairs = s_misc[2];
   const int ntiles = (npairs + TS - 1) / TS;
@@ -537,6 +567,7 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
       }
     }
     SFE_PF_DUMP(warp)
+    SFE_SPAN(1);
     return;
   }
 
@@ -619,6 +650,7 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
   Pair nx = claim();      // the first pair's samples fly while the tables land
   mbar_wait(tbar, 0u);
   SFE_PF_G(pf_g2)
+  SFE_TR(3, 0);
   SFE_PF_DECL
   while (true) {
     const Pair cu = nx;
@@ -787,6 +819,7 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
     SFE_TR(25, q);
   }
   SFE_PF_DUMP(warp)
+  SFE_SPAN(1);
 }
 
 }  // namespace sfe

@@ -44,6 +44,15 @@ class _on_device:
         return False
 
 
+def _host_len_ptr(len_host, B: int):
+    """Address of a host copy of the lengths for the C ABI's optional `wav_len_host` (None when there is none or it
+    is not a contiguous int64 array of B entries)."""
+    if (isinstance(len_host, np.ndarray) and len_host.dtype == np.int64 and len_host.ndim == 1
+            and len_host.shape[0] == B and len_host.flags.c_contiguous):
+        return len_host.ctypes.data
+    return None
+
+
 def _need_cuda(t: torch.Tensor, name: str):
     if not t.is_cuda:
         raise RuntimeError(
@@ -210,8 +219,9 @@ class FrontendPlan:
 
     def forward(self, wav: torch.Tensor, wav_len: torch.Tensor, *, want_mel=True, want_lin=False, want_energy=False,
                 want_stats=False, norm_mean=None, norm_std=None, masks: Optional[DeviceMasks] = None,
-                skip_pad=False, out_mel=None, out_stats=None):
-        """wav (B, T) fp32 CUDA (any row pitch), wav_len (B,) int64 CUDA."""
+                skip_pad=False, out_mel=None, out_stats=None, len_host: Optional[np.ndarray] = None):
+        """wav (B, T) fp32 CUDA (any row pitch), wav_len (B,) int64 CUDA; len_host: its host copy (contiguous
+        numpy int64) when the caller has one — the library then cuts the batch into per-SM ranges on the host."""
         _need_cuda(wav, "speech")
         B, T = wav.shape
         if wav.dtype != torch.float32:
@@ -238,16 +248,18 @@ class FrontendPlan:
             _lib.check(self._lib.sfe_frontend_forward(
                 self._h, _ptr(wav), int(wav.stride(0)), _ptr(wav_len), B, T, _ptr(mel), _ptr(lin), _ptr(energy),
                 _ptr(feat_len), _ptr(stats), _ptr(norm_mean), _ptr(norm_std),
-                C.byref(ms) if ms is not None else None, int(skip_pad), _stream()))
+                C.byref(ms) if ms is not None else None, int(skip_pad), _stream(), _host_len_ptr(len_host, B)))
         if want_stats and not fused_stats:
             stats = stats_accumulate(mel, feat_len)  # linear-domain mel: general fp64 sums in a second pass
         out.update(mel=mel, lin=lin, energy=energy, stats=stats, feat_len=feat_len)
         return out
 
     def chain(self, wav: torch.Tensor, wav_len: torch.Tensor, *, norm_mode: int, mean=None, std=None,
-              clamp: float = 1e-10, use_mean=True, use_std=True, masks: Optional[DeviceMasks] = None):
+              clamp: float = 1e-10, use_mean=True, use_std=True, masks: Optional[DeviceMasks] = None,
+              len_host: Optional[np.ndarray] = None):
         """frontend -> normalise -> masks in one library call (see sfe_chain_forward).  Lean on purpose:
-        the caller has validated `wav` (B, T) fp32 CUDA with unit inner stride and `wav_len` int64 CUDA."""
+        the caller has validated `wav` (B, T) fp32 CUDA with unit inner stride and `wav_len` int64 CUDA;
+        `len_host` is the host copy of `wav_len` (contiguous numpy int64) or None."""
         B, T = wav.shape
         dev = wav.device
         F = self.num_frames(T)
@@ -267,7 +279,8 @@ class FrontendPlan:
                 self._h, wav.data_ptr(), wav.stride(0), wav_len.data_ptr(), B, T, mel.data_ptr(), feat_len.data_ptr(),
                 ws.data_ptr() if ws is not None else None, half, norm_mode,
                 mean.data_ptr() if mean is not None else None, std.data_ptr() if std is not None else None,
-                clamp, int(use_mean), int(use_std), None, None, C.byref(ms) if ms is not None else None, _stream())
+                clamp, int(use_mean), int(use_std), None, None, C.byref(ms) if ms is not None else None, _stream(),
+                _host_len_ptr(len_host, B))
         if rc:
             _lib.check(rc)
         if ws is not None:

@@ -92,7 +92,7 @@ class AcousticFrontend(Module):
         warp_done = warp is None
 
         if norm is None:
-            y, ylen = plan.chain(wav, len_dev, norm_mode=0, masks=fused_masks)
+            y, ylen = plan.chain(wav, len_dev, norm_mode=0, masks=fused_masks, len_host=len_host)
         else:
             kind = norm.norm_type
             if kind == "group":
@@ -107,13 +107,13 @@ class AcousticFrontend(Module):
                 mean = norm.get_buffer(f"{prefix}_mean") if norm.mean_norm else None
                 std = norm.get_buffer(f"{prefix}_std") if norm.std_norm else None
                 y, ylen = plan.chain(wav, len_dev, norm_mode=1, mean=mean, std=std, use_mean=norm.mean_norm,
-                                     use_std=norm.std_norm, masks=fused_masks)
+                                     use_std=norm.std_norm, masks=fused_masks, len_host=len_host)
             elif not bf16 and warp is None and plan.mel_logging and (kind == "utterance" or (kind == "batch" and not norm.training)):
                 y, ylen = plan.chain(wav, len_dev, norm_mode=2, clamp=norm.clamp, use_mean=norm.mean_norm,
-                                     use_std=norm.std_norm, masks=fused_masks)
+                                     use_std=norm.std_norm, masks=fused_masks, len_host=len_host)
             else:
                 # raw rows + sums, then ONE pass: statistics (exchanged across ranks if needed), warp, masks
-                out = plan.forward(wav, len_dev, want_stats=True, skip_pad=plan.mel_logging)
+                out = plan.forward(wav, len_dev, want_stats=True, skip_pad=plan.mel_logging, len_host=len_host)
                 y, ylen = out["mel"], out["feat_len"]
                 y._sfe_stats = (y._version, out["stats"])
                 HostLengths.remember(ylen, flen_host)

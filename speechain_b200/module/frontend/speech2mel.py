@@ -50,7 +50,7 @@ class Speech2MelSpec(Module):
         if not in_kernel and kernel_kw.get("want_stats"):
             kernel_kw = dict(kernel_kw, want_stats=False)  # sums of the padded rows would be wrong on this path
         out = plan.forward(wav, s2l._kernel_lengths(wav, len_dev, in_kernel), want_mel=True,
-                           want_energy=self.return_energy, **kernel_kw)
+                           want_energy=self.return_energy, len_host=len_host if in_kernel else None, **kernel_kw)
         s2l._fix_padded_rows(out, len_dev, in_kernel, plan)
         out["feat_len_host"] = s2l._feat_len_host(len_host)
         out["pad_value"] = plan.pad_mel
