@@ -99,15 +99,26 @@ struct TileCfg {
 #else
   static constexpr int NPB = (PL::M <= 256) ? 3 : 2;   // power-spectrum buffers = Mel warps
 #endif
+#ifdef SFE_T2_MS  // tuning experiments (tools/variant.py)
+  static constexpr int MS = SFE_T2_MS;
+#else
+  // Mel warps per tile buffer.  2: the Mel program's two streams (bins below / above B_LD) run on two warps and each
+  // reads out half of the rows — what matters is the LATENCY of a tile's Mel stage, not its instruction count: it is
+  // the tail of every launch (the last tile's Mel stage runs on an otherwise idle SM) and the depth of the
+  // FFT -> Mel pipeline (FFT warps wait for a buffer only the Mel stage can free).
+  static constexpr int MS = 2;
+#endif
 #ifdef SFE_T2_NF  // tuning experiments (tools/variant.py)
   static constexpr int NF = SFE_T2_NF;
 #else
-  static constexpr int NF = (PL::M <= 256) ? 17 : 14;  // FFT warps (n_fft 1024: 9.5 KB of scratch + staging per warp)
+  // FFT warps (measured on C1 / C2: 12 ... 17 all within 2 %, fewer or more are slower)
+  static constexpr int NF = (PL::M <= 256) ? 13 : 14;
 #endif
   // Two frames in flight per warp (G = 16) store their rows at the same time: rows 16 banks apart (4 rows with the
   // pitch below) make that store conflict-free, so pair s owns rows 8 (s / 4) + s % 4 and that + 4
   static constexpr bool PERM = (PL::C == 2);
-  static constexpr int NW = NF + NPB;                  // + Mel warps: 20 = 5 warps per SM sub-partition at <= 96 registers
+  static constexpr int NW = NF + MS * NPB;             // + Mel warps: <= 20 warps = 5 per SM sub-partition at <= 96 registers
+  static_assert(MS == 1 || (MS == 2 && (TS / 2) % 4 == 0), "a Mel warp reads out whole groups of four pairs");
 };
 // Row pitch of a power-spectrum tile: the spectrum plus the zero-weight bins its Mel program rounds up to, an ODD
 // multiple of 16 bytes (one lane per row reads 128 bits at a time: conflict-free).
@@ -131,6 +142,14 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// named barriers between the two Mel warps of a tile buffer (whole warps arrive: .aligned)
+__device__ __forceinline__ void named_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 template <bool PERM> __device__ __forceinline__ int t2_row(int s, int f) {  // tile row of frame f of pair s
@@ -320,8 +339,10 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
   if (warp >= NF) mbar_wait(tbar, 0u);  // (Mel warps) tables have landed
 
   if (warp >= NF) {
-    // ================================ Mel warps: warp NF + pb owns buffer pb ================================
-    const int pb = warp - NF;
+    // ================== Mel warps: warps NF + MS pb ... NF + MS pb + MS - 1 own buffer pb ==================
+    constexpr int MS = TileCfg<PL>::MS, TSH = TS / MS;
+    const int pb = (warp - NF) / MS, half = (warp - NF) % MS;  // half 0: stream A (+ the tail), half 1: stream B
+    const int bid = 1 + 3 * pb;                                // named barriers bid, bid + 1, bid + 2 (MS == 2)
     float* p2buf = p2_0 + pb * p2_floats;
     const float4* wprog = reinterpret_cast<const float4*>(tab + p.o_mtab);  // Mel weights in the program's layout
     const int n_fmask = p.mk.n_fmask, n_tmask = p.mk.n_tmask;
@@ -358,25 +379,6 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
       const unsigned va_bits = __ballot_sync(FULLM, va), ex_bits = __ballot_sync(FULLM, ex);
       const unsigned tm_bits = __ballot_sync(FULLM, tm);
 
-      // ---- linear spectrogram output (before the Mel stage overwrites the rows) ----
-      if (p.lin) {
-        for (int r = 0; r < 2 * TS; ++r) {
-          const int rb = __shfl_sync(FULLM, myb, r), rt = __shfl_sync(FULLM, myt, r);
-          const bool ract = __shfl_sync(FULLM, static_cast<int>(rowact && (trow[srow].kind != U_DONE)), r) != 0;
-          if (ract && rt < F) {
-            float* dst = p.lin + (static_cast<long long>(rb) * F + rt) * K;
-            const bool v = (va_bits >> r) & 1u;
-            const float* src = p2buf + r * PP;
-            for (int k = lane; k < K; k += 32) {
-              float x = v ? src[k] : 0.f;
-              if (p.lin_log) x = fast_log(x, p.lin_clamp, p.lin_lmul);
-              dst[k] = x;
-            }
-          }
-        }
-        __syncwarp();
-      }
-
       SFE_PF(1)
       // ---- banded Mel: the recipe filterbank's straight-line program (sfe_melprog.h) ----
       // One packed FMA per bin into (even filter, odd filter); a finished filter's raw sum is stored over a bin
@@ -384,31 +386,37 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
       // (bins below / above B_LD) for instruction-level parallelism, joined at the end.  The logarithm is
       // taken by the read-out.  (A data-driven version of this loop — flag tests and branches around the
       // emits — cost 5 900 instructions and ~30 us of one warp per tile, the whole CTA waiting for it.)
-      if (rowact) {
-        float* rowp = p2buf + lane * PP;
+      float* rowp = p2buf + lane * PP;  // (dereferenced by active rows only)
+      float2 aA = make_float2(0.f, 0.f), aB = make_float2(0.f, 0.f);
+      {
         const float4* pA = reinterpret_cast<const float4*>(rowp);
         const float4* pB = reinterpret_cast<const float4*>(rowp + BK::B_LD);
         float4 xA[2], xB[2], wA0[2], wA1[2], wB0[2], wB1[2];
-        float2 aA = make_float2(0.f, 0.f), aB = make_float2(0.f, 0.f);
-#define SFE_LD(g, buf)                                                                            \
-  xA[buf] = pA[g]; xB[buf] = pB[g];                                                               \
-  wA0[buf] = wprog[4 * (g)]; wA1[buf] = wprog[4 * (g) + 1]; wB0[buf] = wprog[4 * (g) + 2]; wB1[buf] = wprog[4 * (g) + 3];
+        float oa[4] = {0.f, 0.f, 0.f, 0.f}, ob[4] = {0.f, 0.f, 0.f, 0.f};  // finished filters waiting for a 128-bit store
+        // HF: which streams this warp runs — 0 stream A, 1 stream B, 2 both (one Mel warp per buffer)
+#define SFE_LD(g, buf)                                                                                              \
+  if (HF != 1) { xA[buf] = pA[g]; wA0[buf] = wprog[4 * (g)]; wA1[buf] = wprog[4 * (g) + 1]; }                       \
+  if (HF != 0) { xB[buf] = pB[g]; wB0[buf] = wprog[4 * (g) + 2]; wB1[buf] = wprog[4 * (g) + 3]; }
 #define SFE_W(u_, v_, i) ((i) == 0 ? make_float2(u_.x, u_.y) : (i) == 1 ? make_float2(u_.z, u_.w) : (i) == 2 ? make_float2(v_.x, v_.y) : make_float2(v_.z, v_.w))
 #define SFE_X(v_, i) ((i) == 0 ? v_.x : (i) == 1 ? v_.y : (i) == 2 ? v_.z : v_.w)
-#define SFE_FA(buf, i) aA = f2fma(SFE_W(wA0[buf], wA1[buf], i), make_float2(SFE_X(xA[buf], i), SFE_X(xA[buf], i)), aA);
-#define SFE_FB(buf, i) aB = f2fma(SFE_W(wB0[buf], wB1[buf], i), make_float2(SFE_X(xB[buf], i), SFE_X(xB[buf], i)), aB);
-#define SFE_EA(slot, k) if (slot) { oa[k] = aA.y; aA.y = 0.f; } else { oa[k] = aA.x; aA.x = 0.f; }
-#define SFE_EB(slot, k) if (slot) { ob[k] = aB.y; aB.y = 0.f; } else { ob[k] = aB.x; aB.x = 0.f; }
-#define SFE_SA(pos) *reinterpret_cast<float4*>(rowp + (pos)) = make_float4(oa[0], oa[1], oa[2], oa[3]);
-#define SFE_SB(pos) *reinterpret_cast<float4*>(rowp + (pos)) = make_float4(ob[0], ob[1], ob[2], ob[3]);
-#define SFE_EA1(slot, pos) if (slot) { rowp[pos] = aA.y; aA.y = 0.f; } else { rowp[pos] = aA.x; aA.x = 0.f; }
-#define SFE_EB1(slot, pos) if (slot) { rowp[pos] = aB.y; aB.y = 0.f; } else { rowp[pos] = aB.x; aB.x = 0.f; }
-#define SFE_PA(k, pos) rowp[pos] = oa[k];
-#define SFE_JOIN(slot, pos) rowp[pos] += (slot) ? aA.y : aA.x; rowp[(pos) + 1] += (slot) ? aA.x : aA.y;
-#define SFE_MOVE(from, to) rowp[to] = rowp[from];
-        float oa[4] = {0.f, 0.f, 0.f, 0.f}, ob[4] = {0.f, 0.f, 0.f, 0.f};  // finished filters waiting for a 128-bit store
-        if constexpr (TileCfg<PL>::BANK == 1) { SFE_MELPROG_1(SFE_LD, SFE_FA, SFE_FB, SFE_EA, SFE_EB, SFE_SA, SFE_SB, SFE_EA1, SFE_EB1, SFE_PA, SFE_JOIN, SFE_MOVE) }
-        else { SFE_MELPROG_2(SFE_LD, SFE_FA, SFE_FB, SFE_EA, SFE_EB, SFE_SA, SFE_SB, SFE_EA1, SFE_EB1, SFE_PA, SFE_JOIN, SFE_MOVE) }
+#define SFE_FA(buf, i) if (HF != 1) aA = f2fma(SFE_W(wA0[buf], wA1[buf], i), make_float2(SFE_X(xA[buf], i), SFE_X(xA[buf], i)), aA);
+#define SFE_FB(buf, i) if (HF != 0) aB = f2fma(SFE_W(wB0[buf], wB1[buf], i), make_float2(SFE_X(xB[buf], i), SFE_X(xB[buf], i)), aB);
+#define SFE_EA(slot, k) if (HF != 1) { if (slot) { oa[k] = aA.y; aA.y = 0.f; } else { oa[k] = aA.x; aA.x = 0.f; } }
+#define SFE_EB(slot, k) if (HF != 0) { if (slot) { ob[k] = aB.y; aB.y = 0.f; } else { ob[k] = aB.x; aB.x = 0.f; } }
+#define SFE_SA(pos) if (HF != 1) *reinterpret_cast<float4*>(rowp + (pos)) = make_float4(oa[0], oa[1], oa[2], oa[3]);
+#define SFE_SB(pos) if (HF != 0) *reinterpret_cast<float4*>(rowp + (pos)) = make_float4(ob[0], ob[1], ob[2], ob[3]);
+#define SFE_EA1(slot, pos) if (HF != 1) { if (slot) { rowp[pos] = aA.y; aA.y = 0.f; } else { rowp[pos] = aA.x; aA.x = 0.f; } }
+#define SFE_EB1(slot, pos) if (HF != 0) { if (slot) { rowp[pos] = aB.y; aB.y = 0.f; } else { rowp[pos] = aB.x; aB.x = 0.f; } }
+#define SFE_PA(k, pos) if (HF != 1) rowp[pos] = oa[k];
+#define SFE_PROG                                                                                                       \
+  if constexpr (TileCfg<PL>::BANK == 1) { SFE_MELPROG_1(SFE_LD, SFE_FA, SFE_FB, SFE_EA, SFE_EB, SFE_SA, SFE_SB, SFE_EA1, SFE_EB1, SFE_PA) } \
+  else { SFE_MELPROG_2(SFE_LD, SFE_FA, SFE_FB, SFE_EA, SFE_EB, SFE_SA, SFE_SB, SFE_EA1, SFE_EB1, SFE_PA) }
+        if (rowact) {
+          if (MS == 1) { constexpr int HF = 2; SFE_PROG }
+          else if (half == 0) { constexpr int HF = 0; SFE_PROG }
+          else { constexpr int HF = 1; SFE_PROG }
+        }
+#undef SFE_PROG
 #undef SFE_SA
 #undef SFE_SB
 #undef SFE_EA1
@@ -421,10 +429,21 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
 #undef SFE_FB
 #undef SFE_EA
 #undef SFE_EB
+      }
+      // tail: filters fed by both streams are joined, stream A's last outputs move next to stream B's (the read-out's
+      // layout) — after BOTH streams are through
+      __syncwarp();
+      if (MS == 2) named_sync(bid, 64);
+      if (rowact && half == 0) {
+#define SFE_JOIN(slot, pos) rowp[pos] += (slot) ? aA.y : aA.x; rowp[(pos) + 1] += (slot) ? aA.x : aA.y;
+#define SFE_MOVE(from, to) rowp[to] = rowp[from];
+        if constexpr (TileCfg<PL>::BANK == 1) { SFE_MELTAIL_1(SFE_JOIN, SFE_MOVE) }
+        else { SFE_MELTAIL_2(SFE_JOIN, SFE_MOVE) }
 #undef SFE_JOIN
 #undef SFE_MOVE
       }
       __syncwarp();
+      if (MS == 2) named_sync(bid + 1, 64);
 
       SFE_TR(11, j);
       SFE_PF(2)
@@ -472,15 +491,17 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
         };
         // The usual tile: 2*TS consecutive real frames of ONE utterance, nothing but the logarithm (and the sums)
         // between the row and HBM — straight-line, every offset an immediate, the loads of all steps in flight.
+        // (this warp's share of the tile: pairs it0 ... it0 + TSH - 1)
+        const int it0 = half * TSH;
         const int b0 = __shfl_sync(FULLM, myb, 0), t0 = __shfl_sync(FULLM, myt, 0);
         const bool plain = !fancy && nsl == TS && dolog &&
                            __all_sync(FULLM, lane >= 2 * TS || (va && ex && myb == b0 && myt == t0 + 2 * srow + grow));
         if (plain) {
-          float* dst0 = p.mel + (static_cast<long long>(b0) * F + t0) * BK::D + h * BK::D;
-          const float* src0 = p2buf + (t2_row<PERM>(0, 1) * h) * PP;
+          float* dst0 = p.mel + (static_cast<long long>(b0) * F + t0 + 2 * it0) * BK::D + h * BK::D;
+          const float* src0 = p2buf + (t2_row<PERM>(it0, 0) + t2_row<PERM>(0, 1) * h) * PP;
           if (stats_on) {
 #pragma unroll
-            for (int it = 0; it < TS; ++it) {
+            for (int it = 0; it < TSH; ++it) {
               const float4 x4 = *reinterpret_cast<const float4*>(src0 + t2_row<PERM>(it, 0) * PP + so4);
               float x[5] = {x4.x, x4.y, x4.z, x4.w, src0[t2_row<PERM>(it, 0) * PP + so1]};
 #pragma unroll
@@ -495,7 +516,7 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
             flush(b0);
           } else {
 #pragma unroll
-            for (int it = 0; it < TS; ++it) {
+            for (int it = 0; it < TSH; ++it) {
               const float4 x4 = *reinterpret_cast<const float4*>(src0 + t2_row<PERM>(it, 0) * PP + so4);
               float x[5] = {x4.x, x4.y, x4.z, x4.w, src0[t2_row<PERM>(it, 0) * PP + so1]};
 #pragma unroll
@@ -507,7 +528,7 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
         }
         int curb = -1;
         unsigned fm = 0u;
-        for (int it = 0; it < (plain ? 0 : nsl); ++it) {
+        for (int it = it0; it < (plain ? 0 : min(nsl, it0 + TSH)); ++it) {
           const T2Row rd = trow[it];
           if (rd.b != curb) {
             if (curb >= 0 && stats_on) flush(curb);
@@ -557,12 +578,17 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
         if (curb >= 0 && stats_on) flush(curb);
       }
 
-      // hand the buffer back: tile j + NPB may write its rows
+      // hand the buffer back: tile j + NPB may write its rows (MS == 2: once the other warp is through as well —
+      // it only arrives, the warp that publishes waits)
       __syncwarp();
       SFE_TR(12, j);
       SFE_PF(3)
-      if (lane == 0) {
-        __threadfence_block();  // release: every lane's reads of the tile (__syncwarp above) are done
+      if (MS == 2) {
+        if (half == 0) named_sync(bid + 2, 64);
+        else named_arrive(bid + 2, 64);
+      }
+      if (half == 0 && lane == 0) {
+        __threadfence_block();  // release: every lane's reads of the tile (__syncwarp / barrier above) are done
         pgen[pb] = j + NPB;
       }
     }

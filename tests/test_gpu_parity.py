@@ -678,3 +678,36 @@ def test_an_older_larger_plan_still_launches_after_a_smaller_one_was_created():
         b, _ = big(wav[..., None], wl)
         torch.cuda.synchronize()
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("skip_pad", [False, True])
+def test_host_made_work_split_equals_the_kernels_own(skip_pad):
+    """`wav_len_host` only moves the cutting of the batch into per-SM ranges from the kernel's prologue to the host:
+    features, feature lengths and the fixed-point sums must be bit-identical with and without it (ragged batch with
+    an utterance shorter than a frame hop, an empty one, and more utterances than a warp scans at once)."""
+    g = torch.Generator().manual_seed(77)
+    lens = sorted(torch.randint(3000, 90000, (70,), generator=g).tolist(), reverse=True)
+    lens[0], lens[-1], lens[-2] = 90000, 0, 100
+    wav = _wave(51, lens, zero_seg=False).to(DEV)
+    wl = torch.tensor(lens, device=DEV)
+    host = np.asarray(lens, dtype=np.int64)
+    m = Speech2MelSpec(n_mels=80, n_fft=512, win_length=400, hop_length=160, preemphasis=0.97).to(DEV)
+    plan = m.speech2linear._plan(wav.device, preemph=True, mel=m.linear2mel.mel_conf())
+    F = plan.num_frames(wav.size(1))
+    outs = []
+    for lh in (None, host):
+        mel = torch.full((len(lens), F, 80), -7.0, device=DEV)  # rows the kernel skips keep the marker in both runs
+        o = plan.forward(wav, wl, want_stats=True, skip_pad=skip_pad, out_mel=mel, len_host=lh)
+        torch.cuda.synchronize()
+        outs.append(o)
+    a, b = outs
+    assert torch.equal(a["feat_len"], b["feat_len"])
+    assert torch.equal(a["stats"], b["stats"])
+    assert torch.equal(a["mel"], b["mel"])
+    # and the split really was the host's: lengths that disagree with the device's change what is computed
+    wrong = host.copy()
+    wrong[0] = 45000
+    mel = torch.full((len(lens), F, 80), -7.0, device=DEV)
+    c = plan.forward(wav, wl, want_stats=True, skip_pad=skip_pad, out_mel=mel, len_host=wrong)
+    torch.cuda.synchronize()
+    assert not torch.equal(c["mel"][0], outs[1]["mel"][0])

@@ -136,8 +136,8 @@ def main():
                "// bin i of the group (stream A / B); EA/EB(slot, k) move accumulator slot (0 even filter, 1 odd) to\n"
                "// output register k of the stream and clear it; SA/SB(pos) store the stream's four output registers to\n"
                "// row[pos..pos+3]; EA1/EB1(slot, pos) store the slot to row[pos] directly and clear it; PA(k, pos) store\n"
-               "// output register k of stream A to row[pos]; JOIN(slot, pos) add stream A's leftovers to row[pos],\n"
-               "// row[pos+1]; MOVE(from, to) row[to] = row[from].\n#pragma once\n\nnamespace sfe {\nnamespace melprog {\n")
+               "// output register k of stream A to row[pos]; tail (after BOTH streams): JOIN(slot, pos) add stream A's\n"
+               "// leftovers to row[pos], row[pos+1]; MOVE(from, to) row[to] = row[from].\n#pragma once\n\nnamespace sfe {\nnamespace melprog {\n")
     for name, bank, args in BANKS:
         W = mel_filterbank(*args).numpy()
         meta, pre, curs, ops = build(name, W)
@@ -148,14 +148,21 @@ def main():
         # host-side identity check: per bin, the filter index held by the accumulator's low slot
         vals = ", ".join(str(int(c)) for c in curs)
         out.append(f"static const unsigned char kCur{bank}[{len(curs)}] = {{{vals}}};\n")
-        lines, cur = [], "  "
-        for op in ops:
-            if len(cur) + len(op) + 1 > 116:
-                lines.append(cur.rstrip() + " \\\n")
-                cur = "  "
-            cur += op + " "
-        lines.append(cur.rstrip() + "\n")
-        out.append(f"#define SFE_MELPROG_{bank}(LD, FA, FB, EA, EB, SA, SB, EA1, EB1, PA, JOIN, MOVE) \\\n" + "".join(lines) + "\n")
+        def wrap(seq):
+            lines, cur = [], "  "
+            for op in seq:
+                if len(cur) + len(op) + 1 > 116:
+                    lines.append(cur.rstrip() + " \\\n")
+                    cur = "  "
+                cur += op + " "
+            lines.append(cur.rstrip() + "\n")
+            return "".join(lines)
+        # the two streams never touch each other's bins or outputs before the tail (JOIN, MOVE): they may run on
+        # two warps, the tail after both are done
+        cut = next(i for i, op in enumerate(ops) if op.startswith("JOIN"))
+        assert all(op.startswith(("JOIN", "MOVE")) for op in ops[cut:]) and not any(op.startswith(("JOIN", "MOVE")) for op in ops[:cut])
+        out.append(f"#define SFE_MELPROG_{bank}(LD, FA, FB, EA, EB, SA, SB, EA1, EB1, PA) \\\n" + wrap(ops[:cut]) + "\n")
+        out.append(f"#define SFE_MELTAIL_{bank}(JOIN, MOVE) \\\n" + wrap(ops[cut:]) + "\n")
     out.append("}  // namespace melprog\n}  // namespace sfe\n")
     path = os.path.join(ROOT, "speechain_b200", "csrc", "sfe_melprog.h")
     with open(path, "w") as f:
