@@ -111,8 +111,9 @@ struct TileCfg {
 #ifdef SFE_T2_NF  // tuning experiments (tools/variant.py)
   static constexpr int NF = SFE_T2_NF;
 #else
-  // FFT warps (measured on C1 / C2: 12 ... 17 all within 2 %, fewer or more are slower)
-  static constexpr int NF = (PL::M <= 256) ? 13 : 14;
+  // FFT warps (measured, C1 / C2 us with two Mel warps per buffer: 13: 34.8 / 53.5, 14: 34.3 / 53.6, 15: 34.1 / 54.9,
+  // 16: 33.9 / 53.5; 16 + 6 warps run at 80 registers)
+  static constexpr int NF = (PL::M <= 256) ? 16 : 14;
 #endif
   // Two frames in flight per warp (G = 16) store their rows at the same time: rows 16 banks apart (4 rows with the
   // pitch below) make that store conflict-free, so pair s owns rows 8 (s / 4) + s % 4 and that + 4
@@ -142,6 +143,17 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// acquire / release on a shared-memory word (a membar.cta — what __threadfence_block() is — is a sequentially
+// consistent fence: it drains every outstanding access of the warp)
+__device__ __forceinline__ int ld_acquire_shared(const volatile int* p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"(smem_u32(const_cast<const int*>(p))) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_shared(volatile int* p, int v) {
+  asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(smem_u32(const_cast<int*>(p))), "r"(v) : "memory");
 }
 
 // named barriers between the two Mel warps of a tile buffer (whole warps arrive: .aligned)
@@ -587,10 +599,8 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
         if (half == 0) named_sync(bid + 2, 64);
         else named_arrive(bid + 2, 64);
       }
-      if (half == 0 && lane == 0) {
-        __threadfence_block();  // release: every lane's reads of the tile (__syncwarp / barrier above) are done
-        pgen[pb] = j + NPB;
-      }
+      // (release: every lane's reads of the tile — __syncwarp / barrier above — are done)
+      if (half == 0 && lane == 0) st_release_shared(pgen + pb, j + NPB);
     }
     SFE_PF_DUMP(warp)
     SFE_SPAN(1);
@@ -688,8 +698,8 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
     float* p2buf = p2_0 + pb * p2_floats;
     // rows of buffer pb may be overwritten once the Mel stage of tile j - NPB has consumed them
     auto p2_wait = [&]() {
-      while (pgen[pb] != j) __nanosleep(64);  // (almost always already true: one shared-memory load)
-      __threadfence_block();                  // acquire: the Mel warp's reads of the rows are behind us
+      // (almost always already true: one shared-memory load; acquire: the Mel warps' reads of the rows are behind us)
+      while (ld_acquire_shared(pgen + pb) != j) __nanosleep(64);
     };
     auto publish = [&]() {
       __syncwarp();

@@ -74,6 +74,8 @@ class HostLengths:
 
     @classmethod
     def remember(cls, dev: torch.Tensor, host) -> None:
+        """`host`: the numpy int64 copy, or a zero-argument callable that makes it when somebody asks (the chain's
+        output lengths: nothing on the hot path reads them on the host)."""
         setattr(dev, cls._ATTR, (dev._version, dev.data_ptr(), host))
 
     @classmethod
@@ -82,7 +84,11 @@ class HostLengths:
             return t.numpy() if t.dtype == torch.int64 else t.long().numpy()
         hit = getattr(t, cls._ATTR, None)
         if hit is not None and hit[0] == t._version and hit[1] == t.data_ptr():
-            return hit[2]
+            host = hit[2]
+            if callable(host):
+                host = host()
+                setattr(t, cls._ATTR, (hit[0], hit[1], host))
+            return host
         host = t.cpu().long().numpy()
         cls.remember(t, host)
         return host
@@ -200,6 +206,7 @@ class FrontendPlan:
         self._h = handle
         self._lib = lib
         self._ws = {}   # per-batch-size scratch for the fixed-point sums (stream-ordered reuse)
+        self._frames = {}  # padded length -> frame count
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -256,13 +263,15 @@ class FrontendPlan:
 
     def chain(self, wav: torch.Tensor, wav_len: torch.Tensor, *, norm_mode: int, mean=None, std=None,
               clamp: float = 1e-10, use_mean=True, use_std=True, masks: Optional[DeviceMasks] = None,
-              len_host: Optional[np.ndarray] = None):
+              len_host=None):
         """frontend -> normalise -> masks in one library call (see sfe_chain_forward).  Lean on purpose:
-        the caller has validated `wav` (B, T) fp32 CUDA with unit inner stride and `wav_len` int64 CUDA;
-        `len_host` is the host copy of `wav_len` (contiguous numpy int64) or None."""
-        B, T = wav.shape
+        the caller has validated `wav` (B, T) or (B, T, 1) fp32 CUDA with unit stride along T and `wav_len` int64
+        CUDA; `len_host` is the host copy of `wav_len` (contiguous numpy int64, or the address of B int64), or None."""
+        B, T = wav.shape[0], wav.shape[1]  # (B, T) or (B, T, 1)
         dev = wav.device
-        F = self.num_frames(T)
+        F = self._frames.get(T)
+        if F is None:
+            F = self._frames[T] = self.num_frames(T)
         mel = torch.empty((B, F, self.n_mels), dtype=torch.float32, device=dev)
         feat_len = torch.empty((B,), dtype=torch.int64, device=dev)
         ws, half = None, 0
@@ -274,13 +283,23 @@ class FrontendPlan:
             ws, half = ent
             ent[1] = -1  # marks the scratch dirty until the call below has been enqueued completely
         ms = masks.struct() if masks is not None else None
-        with _on_device(dev):
+        idx = dev.index
+        prev = torch._C._cuda_getDevice()
+        if idx is not None and idx != prev:
+            torch.cuda.set_device(idx)
+        else:
+            idx = prev
+        try:
             rc = self._lib.sfe_chain_forward(
                 self._h, wav.data_ptr(), wav.stride(0), wav_len.data_ptr(), B, T, mel.data_ptr(), feat_len.data_ptr(),
                 ws.data_ptr() if ws is not None else None, half, norm_mode,
                 mean.data_ptr() if mean is not None else None, std.data_ptr() if std is not None else None,
-                clamp, int(use_mean), int(use_std), None, None, C.byref(ms) if ms is not None else None, _stream(),
-                _host_len_ptr(len_host, B))
+                clamp, int(use_mean), int(use_std), None, None, C.byref(ms) if ms is not None else None,
+                torch._C._cuda_getCurrentRawStream(idx),
+                len_host if isinstance(len_host, int) else _host_len_ptr(len_host, B))
+        finally:
+            if idx != prev:
+                torch.cuda.set_device(prev)
         if rc:
             _lib.check(rc)
         if ws is not None:

@@ -69,19 +69,25 @@ class AcousticFrontend(Module):
         if norm is not None and not (norm.mean_norm or norm.std_norm):
             norm = None
 
-        wav = squeeze_speech(feat)
+        if feat.dim() == 3 and feat.size(2) == 1 and feat.dtype == torch.float32:
+            wav = feat  # (B, T, 1): the kernels take pointer, row pitch and (B, T) — no view needed
+        else:
+            wav = squeeze_speech(feat)
         if not wav.is_cuda:
             raise RuntimeError("speechain_b200 frontend: `speech` must be a CUDA tensor — there is no CPU path.")
         if wav.stride(1) != 1:
-            wav = wav.contiguous()
+            wav = squeeze_speech(feat).contiguous()
         len_dev, len_host = lengths_pair(feat_len, wav.device)
-        flen_host = s2l._feat_len_host(len_host)
+        # feature lengths on the host: the shortest one now (the SpecAugment draws are bounded by it), the array only
+        # if somebody asks for it (HostLengths.get on the returned lengths)
+        flen_min = s2l._feat_len_of(int(len_host.min()))
+        flen_host = None
         plan = s2l._plan(wav.device, preemph=True, mel=fe.linear2mel.mel_conf())
 
         # SpecAugment draws need only host-side lengths, so they happen before any launch
         warp = masks = None
         if aug is not None:
-            warp, masks = aug.draw_device(wav.size(0), fe.output_size, flen_host, wav.device)
+            warp, masks = aug.draw_device(wav.size(0), fe.output_size, None, wav.device, minlen=flen_min)
             if masks is not None and not aug.feat_norm:
                 if bf16:
                     raise NotImplementedError("out_dtype=bfloat16 is available for the fused log-Mel chain only")
@@ -113,15 +119,18 @@ class AcousticFrontend(Module):
                                      use_std=norm.std_norm, masks=fused_masks, len_host=len_host)
             else:
                 # raw rows + sums, then ONE pass: statistics (exchanged across ranks if needed), warp, masks
+                if wav.dim() == 3:
+                    wav = wav.select(2, 0)
                 out = plan.forward(wav, len_dev, want_stats=True, skip_pad=plan.mel_logging, len_host=len_host)
                 y, ylen = out["mel"], out["feat_len"]
                 y._sfe_stats = (y._version, out["stats"])
+                flen_host = s2l._feat_len_host(len_host)
                 HostLengths.remember(ylen, flen_host)
                 y, ylen = norm.forward(y, ylen, group_ids=domain, epoch=epoch, masks=masks, inplace=True,
                                        src_has_pad=not plan.mel_logging, pad_value=plan.pad_mel, warp=warp,
                                        out_dtype=torch.bfloat16 if bf16 else None)
                 warp_done = True
-        HostLengths.remember(ylen, flen_host)
+        HostLengths.remember(ylen, flen_host if flen_host is not None else (lambda: s2l._feat_len_host(len_host)))
         if not warp_done:
             y, _, _ = ops.normalize(y, ylen, warp=warp, masks=masks, out_bf16=bf16)
         elif bf16 and y.dtype != torch.bfloat16:

@@ -85,14 +85,17 @@ class SpecAugment(Module):
             tpos = tpos.numpy()
         return warp, fpos, flen, tpos, tlen
 
-    def draw_device(self, batch_size, feat_dim, feat_len_host, device, generator=None):
-        """Draw and hand to the device: returns (warp, DeviceMasks or None).
+    def draw_device(self, batch_size, feat_dim, feat_len_host, device, generator=None, minlen=None):
+        """Draw and hand to the device: returns (warp, DeviceMasks or None).  ``minlen``: min of the feature lengths
+        when the caller already has it (``feat_len_host`` may then be None).
 
-        Small batches (the descriptors fit the kernel parameter block) take a lean path: the same ``torch.randint``
-        calls as ``draw`` — same order, bounds and shapes, hence the same stream — write int32 straight into
-        persistent host arrays (``out=``), whose ctypes descriptor is built once.  The returned object is valid
-        until the next draw of this module."""
-        minlen = int(feat_len_host.min())
+        Small batches (the descriptors fit the kernel parameter block) take a lean path: the draws of ``draw`` —
+        same order, bounds and shapes, hence the same stream — are written as int32 straight into persistent host
+        arrays, whose ctypes descriptor is built once: ``t.random_(low, high)`` is what ``torch.randint(low, high,
+        size, out=t)`` runs after parsing its arguments (ATen's randint_out: resize, then random_(low, high)), two
+        thirds of its host time.  The returned object is valid until the next draw of this module."""
+        if minlen is None:
+            minlen = int(feat_len_host.min())
         nf = self.freq_mask_num if self.freq_mask else 0
         nt = self.time_mask_num if self.time_mask else 0
         if generator is not None or not 0 < 2 * batch_size * (nf + nt) <= ops._lib.MASK_INLINE_MAX:
@@ -119,8 +122,8 @@ class SpecAugment(Module):
                 assert self.feat_dim == feat_dim and self.freq_mask_width[1] < feat_dim, (
                     "The number of maximum frequency masking bins cannot be larger than the feature dimension! "
                     f"self.freq_mask_width[1]={self.freq_mask_width[1]} and feat_dim={feat_dim}.")
-            torch.randint(self.freq_mask_width[0], self.freq_mask_width[1] + 1, (batch_size, nf), out=t_flen)
-            torch.randint(0, max(1, feat_dim - int(masks._host[1].max())), (batch_size, nf), out=t_fpos)
+            t_flen.random_(self.freq_mask_width[0], self.freq_mask_width[1] + 1)
+            t_fpos.random_(0, max(1, feat_dim - int(masks._host[1].max())))
         if nt:
             lo, hi = self.time_mask_width
             if isinstance(lo, float):
@@ -128,8 +131,8 @@ class SpecAugment(Module):
             if isinstance(hi, float):
                 hi = int(hi * minlen)
             hi = min(hi, minlen)
-            torch.randint(lo, hi + 1, (batch_size, nt), out=t_tlen)
-            torch.randint(0, max(1, minlen - int(masks._host[-1].max())), (batch_size, nt), out=t_tpos)
+            t_tlen.random_(lo, hi + 1)
+            t_tpos.random_(0, max(1, minlen - int(masks._host[-1].max())))
         return warp, masks
 
     def forward(self, feat: torch.Tensor, feat_len: torch.Tensor):

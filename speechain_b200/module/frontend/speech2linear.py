@@ -113,8 +113,14 @@ class Speech2LinearSpec(Module):
 
     def _feat_len_host(self, len_host):
         """numpy int64 feature lengths from numpy sample lengths (speech2linear.py:201-212)."""
-        n = len_host + 2 * (self.n_fft // 2) if self.stft_config["center"] else len_host
-        return (n - self.n_fft) // self.hop_length + 1
+        # (x // hop + 1 == (x + hop) // hop: two array operations instead of four)
+        c = (2 * (self.n_fft // 2) if self.stft_config["center"] else 0) - self.n_fft + self.hop_length
+        return (len_host + c) // self.hop_length
+
+    def _feat_len_of(self, n: int) -> int:
+        """the same for one length (a Python int)"""
+        c = (2 * (self.n_fft // 2) if self.stft_config["center"] else 0) - self.n_fft
+        return (n + c) // self.hop_length + 1
 
     def __getstate__(self):
         # compiled plans hold raw library handles: never pickle / deepcopy them

@@ -34,6 +34,7 @@ torch.cuda.synchronize()
 af.squeeze_speech = timed("squeeze_speech", af.squeeze_speech)
 af.lengths_pair = timed("lengths_pair", af.lengths_pair)
 Speech2LinearSpec._feat_len_host = timed("_feat_len_host", Speech2LinearSpec._feat_len_host)
+Speech2LinearSpec._feat_len_of = timed("_feat_len_of", Speech2LinearSpec._feat_len_of)
 Speech2LinearSpec._plan = timed("_plan", Speech2LinearSpec._plan)
 SpecAugment.draw_device = timed("draw_device", SpecAugment.draw_device)
 SpecAugment.draw = timed("  draw", SpecAugment.draw)
