@@ -541,6 +541,23 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e16_ms = float(t.item())
     del host16, stage16
+    # ---- (3c) what the host -> device link gives a plain contiguous copy with all ranks copying at once: the ceiling
+    #      of `e2e` on this box (the ranks share the host's memory system and, in pairs, its PCIe uplinks) ----
+    probe_h = torch.empty(32 << 20, dtype=torch.float32).pin_memory()  # 128 MB
+    probe_d = torch.empty(32 << 20, dtype=torch.float32, device=dev)
+    probe_d.copy_(probe_h, non_blocking=True)
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(6):
+        probe_d.copy_(probe_h, non_blocking=True)
+    g1.record()
+    barrier()
+    t = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    h2d_plain_gbs = 6 * probe_h.numel() * 4 / (float(t.item()) * 1e-3) / 1e9
+    del probe_h, probe_d
     also = None
     if not args.no_also and args.workload == "c2":
         del batches, host, dbuf
@@ -584,10 +601,12 @@ def main():
         "e2e": {"value": total_audio * e2e_steps / (e2e_ms * 1e-3), "unit": "audio-s/s",
                 "h2d_bytes_per_step": ops.upload_bytes(wl_host) + 8 * B, "d2h_bytes_per_step": 8 * B, "steps": e2e_steps,
                 "h2d_gbs_per_gpu": (ops.upload_bytes(wl_host) + 8 * B) * e2e_steps / (e2e_ms * 1e-3) / 1e9,
+                "h2d_plain_copy_gbs_per_gpu": h2d_plain_gbs,
                 "note": "pinned host (B,T,1) waveforms -> ops.upload_waveforms (valid samples; rows of similar length "
                         "as one pitched copy) -> public API "
                         "AcousticFrontend.forward; copy of step i+1 overlapped with step i; D2H = feature lengths "
-                        "(the features stay on the GPU for the model)"},
+                        "(the features stay on the GPU for the model); h2d_plain_copy_gbs_per_gpu = a plain 128 MB "
+                        "pinned copy with all ranks copying at once (slowest rank): the link's ceiling on this box"},
         "gpu_launches": steps * ({"utterance": 2, "global": 4}.get((w["normalize"] or {}).get("norm_type"), 1)),
         "roofline": {"bound": "hbm", "kernel": "sfe::fused_frontend_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

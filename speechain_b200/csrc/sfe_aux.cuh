@@ -198,20 +198,43 @@ __device__ __forceinline__ void cubic_w(float t, float (&w)[4]) {
   w[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
 }
 
-__global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ NormParams p) {
+#ifndef SFE_NORM_MINB
+#define SFE_NORM_MINB 4
+#endif
+__global__ void __launch_bounds__(256, SFE_NORM_MINB) normalize_kernel(const __grid_constant__ NormParams p) {
   pdl_launch_dependents();
-  pdl_wait();
   extern __shared__ float nsm[];  // mean[D] | 1/std[D] | fmask[D]
   const int b = blockIdx.y, D = p.D;
   float* s_mean = nsm;
   float* s_rstd = nsm + D;
   float* s_fm = nsm + 2 * D;
-  const long long n_valid = min(p.flen[b], p.F);
   const int n_fmask = p.mk.n_fmask, n_tmask = p.mk.n_tmask;
-  const int* m_fpos = p.mk.inl_on ? p.mk.inl : p.mk.fpos;
-  const int* m_flen = p.mk.inl_on ? p.mk.inl + p.B * n_fmask : p.mk.flen;
-  const int* m_tpos = p.mk.inl_on ? p.mk.inl + 2 * p.B * n_fmask : p.mk.tpos;
-  const int* m_tlen = p.mk.inl_on ? p.mk.inl + 2 * p.B * n_fmask + p.B * n_tmask : p.mk.tlen;
+  // this utterance's time-mask intervals [lo, hi) -> shared memory (n_tmask <= 64)
+  __shared__ int s_tlo[64], s_thi[64];
+  __shared__ int2 s_tiv[64];  // {first frame, length}: one unsigned compare per interval in the streaming loop
+  if (p.mk.inl_on) {
+    // descriptors that travel in the parameter block need nothing from the previous kernel: before the wait
+    const int* m_fpos = p.mk.inl;
+    const int* m_flen = p.mk.inl + p.B * n_fmask;
+    const int* m_tpos = p.mk.inl + 2 * p.B * n_fmask;
+    const int* m_tlen = p.mk.inl + 2 * p.B * n_fmask + p.B * n_tmask;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      bool fm = false;
+      for (int q = 0; q < n_fmask; ++q) {
+        const int ps = m_fpos[b * n_fmask + q], ln = m_flen[b * n_fmask + q];
+        fm |= (d >= ps) && (d < ps + ln);
+      }
+      s_fm[d] = fm ? 1.f : 0.f;
+    }
+    for (int q = threadIdx.x; q < n_tmask; q += blockDim.x) {
+      const int ps = m_tpos[b * n_tmask + q];
+      s_tlo[q] = ps;
+      s_thi[q] = ps + m_tlen[b * n_tmask + q];
+      s_tiv[q] = make_int2(ps, max(m_tlen[b * n_tmask + q], 0));
+    }
+  }
+  pdl_wait();
+  const long long n_valid = min(p.flen[b], p.F);
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float m = 0.f, s = 1.f;
     if (p.stats) {
@@ -234,21 +257,22 @@ __global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ 
     }
     s_mean[d] = m;
     s_rstd[d] = 1.0f / s;  // (x-m)*(1/s): within 1 ulp of the reference's division
-    bool fm = false;
-    for (int q = 0; q < n_fmask; ++q) {
-      const int ps = m_fpos[b * n_fmask + q], ln = m_flen[b * n_fmask + q];
-      fm |= (d >= ps) && (d < ps + ln);
+    if (!p.mk.inl_on) {
+      bool fm = false;
+      for (int q = 0; q < n_fmask; ++q) {
+        const int ps = p.mk.fpos[b * n_fmask + q], ln = p.mk.flen[b * n_fmask + q];
+        fm |= (d >= ps) && (d < ps + ln);
+      }
+      s_fm[d] = fm ? 1.f : 0.f;
     }
-    s_fm[d] = fm ? 1.f : 0.f;
   }
-  // this utterance's time-mask intervals [lo, hi) -> shared memory (n_tmask <= 64)
-  __shared__ int s_tlo[64], s_thi[64];
-  __shared__ int2 s_tiv[64];  // {first frame, length}: one unsigned compare per interval in the streaming loop
-  for (int q = threadIdx.x; q < n_tmask; q += blockDim.x) {
-    const int ps = m_tpos[b * n_tmask + q];
-    s_tlo[q] = ps;
-    s_thi[q] = ps + m_tlen[b * n_tmask + q];
-    s_tiv[q] = make_int2(ps, max(m_tlen[b * n_tmask + q], 0));
+  if (!p.mk.inl_on) {
+    for (int q = threadIdx.x; q < n_tmask; q += blockDim.x) {
+      const int ps = p.mk.tpos[b * n_tmask + q];
+      s_tlo[q] = ps;
+      s_thi[q] = ps + p.mk.tlen[b * n_tmask + q];
+      s_tiv[q] = make_int2(ps, max(p.mk.tlen[b * n_tmask + q], 0));
+    }
   }
   __syncthreads();
   const float fillv = p.fill_dev ? *p.fill_dev : p.fill;

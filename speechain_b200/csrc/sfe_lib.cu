@@ -865,7 +865,12 @@ static int normalize_impl(const float* src, float* dst, const int64_t* feat_len,
     return v;
   }();
   const int n_sm = cached_sm_count();
+#ifdef SFE_NORM_CEIL
   long long blocks_per_utt = (static_cast<long long>(n_sm) * per_sm + B - 1) / B;
+#else
+  // (rounded DOWN: the grid must fit the resident CTAs — one wave; a second, partly filled one costs a quarter)
+  long long blocks_per_utt = static_cast<long long>(n_sm) * per_sm / B;
+#endif
   if (blocks_per_utt < 1) blocks_per_utt = 1;
   long long fpc64 = (F + blocks_per_utt - 1) / blocks_per_utt;
   const long long fmin = 8192 / D > 1 ? 8192 / D : 1;
