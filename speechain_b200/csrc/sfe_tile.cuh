@@ -118,6 +118,7 @@ struct TileCfg {
   // Two frames in flight per warp (G = 16) store their rows at the same time: rows 16 banks apart (4 rows with the
   // pitch below) make that store conflict-free, so pair s owns rows 8 (s / 4) + s % 4 and that + 4
   static constexpr bool PERM = (PL::C == 2);
+  static_assert(NPB >= 2 && NPB <= 4, "control block layout (T2_CTRL_BYTES) and named barrier ids");
   static constexpr int NW = NF + MS * NPB;             // + Mel warps: <= 20 warps = 5 per SM sub-partition at <= 96 registers
   static_assert(MS == 1 || (MS == 2 && (TS / 2) % 4 == 0), "a Mel warp reads out whole groups of four pairs");
 };
@@ -171,8 +172,9 @@ struct T2Row {  // a pair as the Mel stage sees it: frames tA, tA+1 of utterance
   int b, tA, flen, kind;
 };
 static_assert(sizeof(T2Row) == 16, "descriptor layout");
-// control block: barriers and counters (96 bytes), rows[3][TS]
-constexpr int T2_CTRL_BYTES(int TS) { return 96 + 3 * TS * 16; }
+// control block: barriers and counters (96 bytes), rows[NPB <= 4][TS]
+constexpr int T2_MAX_NPB = 4;
+constexpr int T2_CTRL_BYTES(int TS) { return 96 + T2_MAX_NPB * TS * 16; }
 
 // try_wait with a suspend-time hint: the warp sleeps in hardware until the phase flips (or ~1 us passes) — it
 // neither eats the issue slots of the warps it waits for nor adds a polling interval to the hand-over
