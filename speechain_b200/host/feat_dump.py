@@ -108,9 +108,14 @@ def build_module(feat_type: str, feat_config: dict, sample_rate: int):
 
 
 def dump_features(idx2wav: str, feat_type: str, feat_config: dict, feat_path: str, device="cuda:0", max_batch: int = 256,
-                  writers: int = 8, reader: Optional[Callable[[str], Tuple[np.ndarray, int]]] = None) -> Optional[str]:
+                  writers: int = 8, reader: Optional[Callable[[str], Tuple[np.ndarray, int]]] = None,
+                  chunk: int = 2048) -> Optional[str]:
     """Extracts ``feat_type`` features of every utterance of ``idx2wav`` on ``device`` and writes the reference's
-    file layout under ``feat_path``.  Returns the path of ``idx2feat`` (None if it already existed: run skipped)."""
+    file layout under ``feat_path``.  Returns the path of ``idx2feat`` (None if it already existed: run skipped).
+
+    The index is walked in chunks of ``chunk`` files (decoded by the thread pool, grouped by sampling rate and
+    identical length, launched, written): host memory is bounded by one chunk of waveforms plus the features still
+    on their way to disk, whatever the size of the corpus (the reference extracts file by file)."""
     import torch
 
     os.makedirs(feat_path, exist_ok=True)
@@ -119,25 +124,30 @@ def dump_features(idx2wav: str, feat_type: str, feat_config: dict, feat_path: st
         return None
     reader = reader or read_wav
     items = list(load_idx2data_file(idx2wav).items())
+    modules, pairs = {}, []
     with ThreadPoolExecutor(max_workers=max(1, writers)) as pool:
-        loaded = list(pool.map(lambda kv: reader(kv[1]), items))
-        by_sr = defaultdict(list)
-        for i, (_, sr) in enumerate(loaded):
-            by_sr[int(sr)].append(i)
-        pending = []
-        for sr, ids in by_sr.items():
-            module = build_module(feat_type, feat_config, sr).to(device).eval()
-            for grp in group_by_length([len(loaded[i][0]) for i in ids], max_batch):
-                rows = [ids[j] for j in grp]
-                wav = torch.from_numpy(np.stack([loaded[i][0] for i in rows])).to(device)[..., None]
-                n = wav.size(1)
-                if n == 0:
-                    raise ValueError(f"empty waveform: {items[rows[0]][0]}")
-                out = module(wav, torch.full((len(rows),), n, dtype=torch.int64, device=device))
-                feat, flen = out[0].cpu().numpy(), out[1].cpu().numpy()
-                for r, i in enumerate(rows):
-                    pending.append(pool.submit(save_feat, feat_path, items[i][0], feat[r, :int(flen[r])].copy(), sr))
-        pairs = [f.result() for f in pending]
+        for c0 in range(0, len(items), max(1, chunk)):
+            part = items[c0:c0 + max(1, chunk)]
+            loaded = list(pool.map(lambda kv: reader(kv[1]), part))
+            by_sr = defaultdict(list)
+            for i, (_, sr) in enumerate(loaded):
+                by_sr[int(sr)].append(i)
+            pending = []
+            for sr, ids in by_sr.items():
+                module = modules.get(sr)
+                if module is None:
+                    module = modules[sr] = build_module(feat_type, feat_config, sr).to(device).eval()
+                for grp in group_by_length([len(loaded[i][0]) for i in ids], max_batch):
+                    rows = [ids[j] for j in grp]
+                    wav = torch.from_numpy(np.stack([loaded[i][0] for i in rows])).to(device)[..., None]
+                    n = wav.size(1)
+                    if n == 0:
+                        raise ValueError(f"empty waveform: {part[rows[0]][0]}")
+                    out = module(wav, torch.full((len(rows),), n, dtype=torch.int64, device=device))
+                    feat, flen = out[0].cpu().numpy(), out[1].cpu().numpy()
+                    for r, i in enumerate(rows):
+                        pending.append(pool.submit(save_feat, feat_path, part[i][0], feat[r, :int(flen[r])].copy(), sr))
+            pairs += [f.result() for f in pending]  # (the chunk's files are on disk before the next one is decoded)
     return write_idx2feat(feat_path, pairs)
 
 

@@ -63,7 +63,8 @@ def test_dump_equals_solo_module_runs(tmp_path):
         lines.append(f"u{i} {p}")
     (tmp_path / "idx2wav").write_text("\n".join(lines) + "\n")
     conf = dict(n_mels=80, hop_length=0.010, win_length=0.025, preemphasis=0.97, sr=8000)  # sr is overridden
-    out = FD.dump_features(str(tmp_path / "idx2wav"), "logmel", conf, str(tmp_path / "feat"))
+    # (chunk=4: the index is walked in two chunks — host memory is bounded by a chunk, not by the corpus)
+    out = FD.dump_features(str(tmp_path / "idx2wav"), "logmel", conf, str(tmp_path / "feat"), chunk=4)
     rows = [r.split(" ", 1) for r in open(out).read().splitlines()]
     assert [r[0] for r in rows] == sorted(f"u{i}" for i in range(len(lens)))
     m = Speech2MelSpec(n_mels=80, hop_length=0.010, win_length=0.025, preemphasis=0.97, sr=16000).to("cuda:0")
