@@ -546,17 +546,19 @@ def main():
     probe_h = torch.empty(32 << 20, dtype=torch.float32).pin_memory()  # 128 MB
     probe_d = torch.empty(32 << 20, dtype=torch.float32, device=dev)
     probe_d.copy_(probe_h, non_blocking=True)
-    barrier()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    for _ in range(6):
-        probe_d.copy_(probe_h, non_blocking=True)
-    g1.record()
-    barrier()
-    t = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    h2d_plain_gbs = 6 * probe_h.numel() * 4 / (float(t.item()) * 1e-3) / 1e9
+    h2d_plain_gbs = 0.0
+    for _ in range(3):  # the best of three rounds: a ceiling
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(4):
+            probe_d.copy_(probe_h, non_blocking=True)
+        g1.record()
+        barrier()
+        t = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        h2d_plain_gbs = max(h2d_plain_gbs, 4 * probe_h.numel() * 4 / (float(t.item()) * 1e-3) / 1e9)
     del probe_h, probe_d
     also = None
     if not args.no_also and args.workload == "c2":
@@ -606,7 +608,7 @@ def main():
                         "as one pitched copy) -> public API "
                         "AcousticFrontend.forward; copy of step i+1 overlapped with step i; D2H = feature lengths "
                         "(the features stay on the GPU for the model); h2d_plain_copy_gbs_per_gpu = a plain 128 MB "
-                        "pinned copy with all ranks copying at once (slowest rank): the link's ceiling on this box"},
+                        "pinned copy with all ranks copying at once (slowest rank, best of three rounds): the link's ceiling on this box"},
         "gpu_launches": steps * ({"utterance": 2, "global": 4}.get((w["normalize"] or {}).get("norm_type"), 1)),
         "roofline": {"bound": "hbm", "kernel": "sfe::fused_frontend_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
