@@ -84,7 +84,7 @@ typedef struct sfe_masks {
 /* Batch-shared SpecAugment time warp (specaug.py:96-124): rows [0,center) are resampled to
  * [0,pos) and [center,minlen) to [pos,minlen) by cubic convolution (A=-0.75, align_corners). */
 typedef struct sfe_warp {
-  int32_t enabled;
+  int32_t enabled;  /* 0 off, 1 bicubic (the reference's default time_warp_mode), 2 bilinear; both align_corners=True */
   int32_t center;
   int32_t pos;
   int32_t minlen;

@@ -483,6 +483,7 @@ class TorchCpuRandint:
 class SpecAugCfg:
     time_warp: bool = True
     time_warp_window: int = 5
+    time_warp_mode: str = "bicubic"
     freq_mask: bool = True
     freq_mask_width: object = 30
     freq_mask_num: int = 2
@@ -506,12 +507,13 @@ class SpecAugDraw:
     time_pos: Optional[np.ndarray] = None           # (B, Nt)
     time_len: Optional[np.ndarray] = None
     time_minlen: int = 0
+    warp_mode: str = "bicubic"
 
 
 def specaug_draw(rng: TorchCpuRandint, B: int, D: int, flen: Sequence[int], cfg: SpecAugCfg) -> SpecAugDraw:
     """The exact randint call sequence of specaug.py:96-108,145-158,167-191."""
     minlen = int(min(flen))
-    d = SpecAugDraw(time_minlen=minlen)
+    d = SpecAugDraw(time_minlen=minlen, warp_mode=cfg.time_warp_mode)
     if cfg.time_warp and minlen > 2 * cfg.time_warp_window + 1:
         w = cfg.time_warp_window
         center = int(rng.randint(w + 1, minlen - w, (1,))[0])
@@ -542,9 +544,10 @@ def _cubic_coeffs(t: np.ndarray, A: float = -0.75):
     return c2(t + 1.0), c1(t), c1(1.0 - t), c2(2.0 - t)
 
 
-def _resample_time(x: np.ndarray, out_len: int) -> np.ndarray:
-    """(B, L, D) -> (B, out_len, D): bicubic with align_corners=True along time only; the
-    feature axis keeps its size so its interpolation is the identity."""
+def _resample_time(x: np.ndarray, out_len: int, mode: str = "bicubic") -> np.ndarray:
+    """(B, L, D) -> (B, out_len, D): bicubic (torch upsample_bicubic2d) or bilinear (upsample_bilinear2d: taps i0 and
+    min(i0 + 1, L - 1) with weights 1 - t, t) with align_corners=True along time only; the feature axis keeps its
+    size so its interpolation is the identity."""
     B, L, D = x.shape
     dt = x.dtype
     if out_len == 0:
@@ -553,6 +556,10 @@ def _resample_time(x: np.ndarray, out_len: int) -> np.ndarray:
     src = (scale * np.arange(out_len, dtype=dt)).astype(dt)
     i0 = np.floor(src).astype(np.int64)
     t = (src - i0.astype(dt)).astype(dt)
+    if mode == "bilinear":
+        i1 = np.minimum(i0 + 1, L - 1)
+        return ((dt.type(1) - t)[None, :, None] * x[:, i0, :] + t[None, :, None] * x[:, i1, :]).astype(dt)
+    assert mode == "bicubic", mode
     ws = _cubic_coeffs(t)
     out = np.zeros((B, out_len, D), dtype=dt)
     for k, w in enumerate(ws):
@@ -561,11 +568,11 @@ def _resample_time(x: np.ndarray, out_len: int) -> np.ndarray:
     return out
 
 
-def time_warp(feat: np.ndarray, center: int, pos: int, minlen: int) -> np.ndarray:
+def time_warp(feat: np.ndarray, center: int, pos: int, minlen: int, mode: str = "bicubic") -> np.ndarray:
     """specaug.py:111-124: [0,center)->[0,pos) and [center,minlen)->[pos,minlen)."""
     out = feat.copy()
-    out[:, :pos] = _resample_time(feat[:, :center], pos)
-    out[:, pos:minlen] = _resample_time(feat[:, center:minlen], minlen - pos)
+    out[:, :pos] = _resample_time(feat[:, :center], pos, mode)
+    out[:, pos:minlen] = _resample_time(feat[:, center:minlen], minlen - pos, mode)
     return out
 
 
@@ -587,7 +594,7 @@ def specaug_mask(B: int, F: int, D: int, d: SpecAugDraw) -> np.ndarray:
 def specaug_apply(feat: np.ndarray, flen: Sequence[int], d: SpecAugDraw, feat_norm: bool = True) -> np.ndarray:
     B, F, D = feat.shape
     if d.warp is not None:
-        feat = time_warp(feat, d.warp[0], d.warp[1], d.time_minlen)
+        feat = time_warp(feat, d.warp[0], d.warp[1], d.time_minlen, d.warp_mode)
     mask = specaug_mask(B, F, D, d)
     if d.freq_pos is None and d.time_pos is None:
         return feat

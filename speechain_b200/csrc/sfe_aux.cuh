@@ -351,7 +351,12 @@ __global__ void __launch_bounds__(256, SFE_NORM_MINB) normalize_kernel(const __g
         const float scale = out_len > 1 ? static_cast<float>(in_len - 1) / static_cast<float>(out_len - 1) : 0.f;
         const float real = scale * static_cast<float>(tt);
         const int i0 = static_cast<int>(floorf(real));
-        cubic_w(real - static_cast<float>(i0), cw);
+        if (p.warp_on == 2) {  // bilinear (align_corners=True): taps i0, i0 + 1 with weights 1 - f, f
+          const float f = real - static_cast<float>(i0);
+          cw[0] = 0.f; cw[1] = 1.f - f; cw[2] = f; cw[3] = 0.f;
+        } else {
+          cubic_w(real - static_cast<float>(i0), cw);
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) idx[q] = lo + min(max(i0 - 1 + q, 0), in_len - 1);
       }

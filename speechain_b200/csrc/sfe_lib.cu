@@ -848,7 +848,7 @@ static int normalize_impl(const float* src, float* dst, const int64_t* feat_len,
   P.pad_value = pad_value;
   P.zero_sums = reinterpret_cast<long long*>(zero_sums);
   if (warp_on) {
-    P.warp_on = 1;
+    P.warp_on = (warp->enabled == 2) ? 2 : 1;  // 1 bicubic, 2 bilinear
     P.warp_center = warp->center;
     P.warp_pos = warp->pos;
     P.warp_minlen = warp->minlen;

@@ -389,7 +389,7 @@ def normalize(src: torch.Tensor, feat_len: torch.Tensor, *, dst: Optional[torch.
         if want_utt_stats:
             raise ValueError("per-utterance statistics outputs are not available with out_bf16")
         out = torch.empty((B, F, D), dtype=torch.bfloat16, device=src.device)
-        w = _lib.SfeWarp(1, int(warp[0]), int(warp[1]), int(warp[2])) if warp is not None else None
+        w = _lib.SfeWarp(int(warp[3]) if len(warp) > 3 else 1, int(warp[0]), int(warp[1]), int(warp[2])) if warp is not None else None
         ms = masks.struct() if masks is not None else None
         with _on_device(src.device):
             _lib.check(_lib.load().sfe_normalize_bf16(
@@ -408,7 +408,7 @@ def normalize(src: torch.Tensor, feat_len: torch.Tensor, *, dst: Optional[torch.
         so = torch.empty((B, D), dtype=torch.float32, device=src.device)
     w = None
     if warp is not None:
-        w = _lib.SfeWarp(1, int(warp[0]), int(warp[1]), int(warp[2]))
+        w = _lib.SfeWarp(int(warp[3]) if len(warp) > 3 else 1, int(warp[0]), int(warp[1]), int(warp[2]))
     ms = masks.struct() if masks is not None else None
     with _on_device(src.device):
         _lib.check(_lib.load().sfe_normalize(

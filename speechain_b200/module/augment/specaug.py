@@ -28,8 +28,10 @@ class SpecAugment(Module):
         self.time_warp = time_warp
         self.time_warp_window = time_warp_window
         self.time_warp_mode = time_warp_mode
-        if time_warp and time_warp_mode != "bicubic":
-            raise NotImplementedError("only time_warp_mode='bicubic' (the reference default) is implemented")
+        # F.interpolate(..., align_corners=True) on the (B, 1, T, D) tensor (specaug.py:111-122) only accepts these two
+        if time_warp and time_warp_mode not in ("bicubic", "bilinear"):
+            raise ValueError(f"time_warp_mode must be 'bicubic' or 'bilinear' (align_corners=True interpolation of a "
+                             f"4-D tensor), got {time_warp_mode!r}")
         self.freq_mask = freq_mask
         if isinstance(freq_mask_width, int):
             freq_mask_width = [0, freq_mask_width]
@@ -60,7 +62,7 @@ class SpecAugment(Module):
             w = self.time_warp_window
             center = torch.randint(low=w + 1, high=time_minlen - w, size=(1,), **kw)[0].item()
             pos = torch.randint(low=center - w, high=center + w, size=(1,), **kw)[0].item()
-            warp = (center, pos, time_minlen)
+            warp = (center, pos, time_minlen, 2 if self.time_warp_mode == "bilinear" else 1)
         fpos = flen = tpos = tlen = None
         if self.freq_mask:
             if self.feat_dim is None:
@@ -114,7 +116,7 @@ class SpecAugment(Module):
             w = self.time_warp_window
             center = torch.randint(low=w + 1, high=minlen - w, size=(1,))[0].item()
             pos = torch.randint(low=center - w, high=center + w, size=(1,))[0].item()
-            warp = (center, pos, minlen)
+            warp = (center, pos, minlen, 2 if self.time_warp_mode == "bilinear" else 1)
         t_fpos, t_flen, t_tpos, t_tlen = masks.views
         if nf:
             if self.feat_dim is None:

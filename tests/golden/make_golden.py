@@ -234,6 +234,7 @@ def main():
         ("sa_time_only", dict(time_warp=False, freq_mask=False, time_mask_width=[0.02, 0.2]), 15),
         ("sa_warp", dict(time_warp=True), 16),
         ("sa_warp_only", dict(time_warp=True, freq_mask=False, time_mask=False, time_warp_window=8), 17),
+        ("sa_warp_bilinear", dict(time_warp=True, time_warp_mode="bilinear"), 19),
     ]:
         sa = SpecAugment(input_size=80, **conf)
         sa.train()

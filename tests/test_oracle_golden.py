@@ -180,6 +180,7 @@ SA_CASES = {
     "sa_time_only": dict(time_warp=False, freq_mask=False, time_mask_width=[0.02, 0.2]),
     "sa_warp": dict(time_warp=True),
     "sa_warp_only": dict(time_warp=True, freq_mask=False, time_mask=False, time_warp_window=8),
+    "sa_warp_bilinear": dict(time_warp=True, time_warp_mode="bilinear"),
     "sa_short": dict(),
 }
 
