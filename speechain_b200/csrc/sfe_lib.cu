@@ -699,7 +699,8 @@ static int frontend_forward_impl(const sfe_plan* pl, const float* wav, int64_t w
     }();
     P.hs_on = 0;
     if (!hs_off)
-      host_split(pl, wav_len_host, B, F, P.units_per_utt, skip_pad && !lin && !energy, static_cast<int>(g2), &P);
+      // (the kernel enumerates real pairs only whenever the batch fits its tables: same rule here)
+      host_split(pl, wav_len_host, B, F, P.units_per_utt, true, static_cast<int>(g2), &P);
     SFE_CUDA(launch_pdl<FwdParams>(fn, dim3(static_cast<unsigned>(g2)), dim3(pl->fft->t2_nw * 32), pl->t2_smem, st, P));
   } else {
     SFE_CUDA(launch_pdl<FwdParams>(pl->fft->fn[pl->cfg.has_preemphasis ? 1 : 0], dim3(static_cast<unsigned>(grid)),

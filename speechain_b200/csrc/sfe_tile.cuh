@@ -113,7 +113,13 @@ struct TileCfg {
 #else
   // FFT warps (measured, C1 / C2 us with two Mel warps per buffer: 13: 34.8 / 53.5, 14: 34.3 / 53.6, 15: 34.1 / 54.9,
   // 16: 33.9 / 53.5; 16 + 6 warps run at 80 registers)
-  static constexpr int NF = (PL::M <= 256) ? 16 : 14;
+#ifdef SFE_T2_NF11  // tuning experiments (tools/variant.py)
+  static constexpr int NF = (PL::M == 256) ? 16 : SFE_T2_NF11;
+#else
+  // (n_fft 400 — radix 8 x 5 x 5, three passes — is short of registers, not of warps: measured C1-shaped 67.3 / 62.2 /
+  //  61.3 / 56.5 us with 16 / 14 / 12 / 10 FFT warps)
+  static constexpr int NF = (PL::M == 256) ? 16 : 10;
+#endif
 #endif
   // Two frames in flight per warp (G = 16) store their rows at the same time: rows 16 banks apart (4 rows with the
   // pitch below) make that store conflict-free, so pair s owns rows 8 (s / 4) + s % 4 and that + 4
@@ -227,8 +233,14 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
   const int hop = p.hop, win = p.win, K = p.K, F = p.F, B = p.B;
   const int upu = p.units_per_utt;
   constexpr int PP = t2_row_pitch(MelBank<TileCfg<PL>::BANK>::type::ROWF);
-  const bool compact = p.skip_pad && !p.lin && !p.energy;  // pairs past an utterance's last frame are not enumerated
   const bool tabled = (B <= UNIT_TABLE_MAX_B);
+  // Pairs past an utterance's last frame are not enumerated: those rows hold a constant, which the FFT warps write
+  // straight to global memory once they have run out of pairs (`padfill`, below) — or nobody does, when a normalise
+  // pass follows that synthesises them (`skip_pad`).  Only batches beyond the tables still send them through the tiles.
+  const bool compact = p.skip_pad || tabled;
+  const bool padfill = !p.skip_pad && tabled;
+  int* s_padc = s_cum;  // (after the set-up) row index at which every utterance's rows past its pairs start
+  __shared__ int s_pad[2];  // [0] next chunk of those rows, [1] s_padc is ready
   auto frames_of = [&](long long len) -> long long {
     return (p.center ? (len + 2 * (p.n_fft / 2)) - p.n_fft : len - p.n_fft) / hop + 1;
   };
@@ -240,6 +252,8 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
   // ---- one-time set-up ----
   if (tid == 0) {
     s_misc[0] = 0;
+    s_pad[0] = 0;
+    s_pad[1] = 0;
     mbar_init(tbar, 1);
     for (int i = 0; i < NPB; ++i) {
       pgen[i] = i;
@@ -350,6 +364,28 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
   const int P_lo = s_misc[1], npairs = s_misc[2];
   const int ntiles = (npairs + TS - 1) / TS;
 
+  if (padfill && warp == NF) {
+    // (first Mel warp, idle until the first tile is complete) prefix over the utterances of the rows that no pair
+    // covers; the FFT warps need it at the very end of the launch
+    int carry = 0;
+    for (int b0 = 0; b0 < B; b0 += 32) {
+      const int b = b0 + lane;
+      const int n = (b < B) ? F - min(F, FPW * ((s_flen[b] + FPW - 1) / FPW)) : 0;
+      int inc = n;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULLM, inc, o);
+        if (lane >= o) inc += v;
+      }
+      if (b < B) s_padc[b] = carry + inc - n;
+      carry += __shfl_sync(FULLM, inc, 31);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      s_padc[B] = carry;
+      st_release_shared(s_pad + 1, 1);
+    }
+  }
   if (warp >= NF) mbar_wait(tbar, 0u);  // (Mel warps) tables have landed
 
   if (warp >= NF) {
@@ -496,8 +532,12 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
 #pragma unroll
             for (int e = 0; e < 5; ++e) {
               const int d = (e < 4) ? 4 * q + e : 64 + q;
+#ifdef SFE_T2_NOATOM  // (timing experiment: sums without their global atomics)
+              if (s1[e] == 123.456f) base[2 * d] = 0;
+#else
               atomicAdd(base + 2 * d, static_cast<unsigned long long>(__float2ll_rn(s1[e] * 4294967296.f)));
               atomicAdd(base + 2 * d + 1, static_cast<unsigned long long>(__float2ll_rn(s2[e] * 16777216.f)));
+#endif
             }
           }
 #pragma unroll
@@ -855,6 +895,64 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
     SFE_PF(5)
     publish();
     SFE_TR(25, q);
+  }
+  // ---------------- rows past the utterances' pairs ----------------
+  // A constant per utterance and Mel bin — log(clamp), normalised and masked like every other row (SURVEY App. A #10;
+  // energy: 0) — written by the FFT warps that have run out of pairs, while the last tiles are still in the Mel
+  // stage: the SM would idle otherwise.  (Through the tiles these rows cost more than the frames: 105 us against 47
+  // for the C2 lengths without a normalise pass behind the kernel; the gather kernel took 90.)
+  if (padfill) {
+    typedef typename MelBank<TileCfg<PL>::BANK>::type BKp;
+    constexpr int D4 = BKp::D / 4, CH = 16;
+    while (ld_acquire_shared(s_pad + 1) == 0) __nanosleep(64);
+    const long long R = s_padc[B];
+    const int lo = static_cast<int>(R * blockIdx.x / gridDim.x), hi = static_cast<int>(R * (blockIdx.x + 1) / gridDim.x);
+    const int n_fmask = p.mk.n_fmask, n_tmask = p.mk.n_tmask;
+    const bool fancy = (p.norm_mean != nullptr) || (p.norm_std != nullptr) || (n_fmask > 0) || (n_tmask > 0);
+    const int* m_fpos = p.mk.inl_on ? p.mk.inl : p.mk.fpos;
+    const int* m_flen = p.mk.inl_on ? p.mk.inl + B * n_fmask : p.mk.flen;
+    const int* m_tpos = p.mk.inl_on ? p.mk.inl + 2 * B * n_fmask : p.mk.tpos;
+    const int* m_tlen = p.mk.inl_on ? p.mk.inl + 2 * B * n_fmask + B * n_tmask : p.mk.tlen;
+    const float fillv = (fancy && p.fill_dev) ? *p.fill_dev : p.fill;
+    int ub = 0, cached = -1;  // utterance cursor (chunks come in increasing order), utterance of `vrow`
+    float4 vrow = make_float4(p.pad_mel, p.pad_mel, p.pad_mel, p.pad_mel);  // this lane's four Mel bins of a padded row
+    while (true) {
+      int c = 0;
+      if (lane == 0) c = atomicAdd(&s_pad[0], 1);
+      c = __shfl_sync(FULLM, c, 0);
+      const int r0 = lo + c * CH;
+      if (r0 >= hi) break;
+      const int r1 = min(r0 + CH, hi);
+      for (int r = r0; r < r1; ++r) {
+        while (s_padc[ub + 1] <= r) ++ub;  // (steps over utterances without such rows)
+        const int t = min(F, FPW * ((s_flen[ub] + FPW - 1) / FPW)) + (r - s_padc[ub]);
+        if (fancy && ub != cached && lane < D4) {
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int d = 4 * lane + e;
+            const float nm = p.norm_mean ? p.norm_mean[d] : 0.f;
+            const float rs = p.norm_std ? 1.f / p.norm_std[d] : 1.f;
+            v[e] = (p.pad_mel - nm) * rs;
+            for (int qq = 0; qq < n_fmask; ++qq) {
+              const int ps = m_fpos[ub * n_fmask + qq], ln = m_flen[ub * n_fmask + qq];
+              if ((d >= ps) && (d < ps + ln)) v[e] = fillv;
+            }
+          }
+          vrow = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        cached = ub;
+        bool tm = false;
+        for (int qq = 0; qq < n_tmask; ++qq) {
+          const int ps = m_tpos[ub * n_tmask + qq], ln = m_tlen[ub * n_tmask + qq];
+          tm |= (t >= ps) && (t < ps + ln);
+        }
+        if (p.mel && lane < D4)
+          *reinterpret_cast<float4*>(p.mel + (static_cast<long long>(ub) * F + t) * BKp::D + 4 * lane) =
+              tm ? make_float4(fillv, fillv, fillv, fillv) : vrow;
+        if (ENERGY && p.energy && lane == D4) p.energy[static_cast<long long>(ub) * F + t] = 0.f;
+      }
+    }
   }
   SFE_PF_DUMP(warp)
   SFE_SPAN(1);

@@ -711,3 +711,30 @@ def test_host_made_work_split_equals_the_kernels_own(skip_pad):
     c = plan.forward(wav, wl, want_stats=True, skip_pad=skip_pad, out_mel=mel, len_host=wrong)
     torch.cuda.synchronize()
     assert not torch.equal(c["mel"][0], outs[1]["mel"][0])
+
+
+def test_rows_past_each_length_are_written_by_the_frontend_kernel_itself():
+    """Ragged batch on the recipe configuration WITHOUT a normalise pass behind the kernel (the module-by-module
+    drop-in): the rows past each utterance's frames — log(clamp) for the Mel output, 0 for the energy — are written by
+    the kernel's FFT warps once they have run out of pairs.  The outputs come from `torch.empty`: poison the allocator's
+    free blocks first so that a row nobody writes cannot pass as a zero."""
+    g = torch.Generator().manual_seed(321)
+    lens = sorted(torch.randint(200, 48000, (37,), generator=g).tolist(), reverse=True)
+    lens[0], lens[-1] = 48000, 0
+    wav = _wave(61, lens, zero_seg=False)
+    conf = dict(n_mels=80, n_fft=512, win_length=400, hop_length=160, sr=16000, return_energy=True)
+    cfg = O.FrontendCfg(**conf)
+    ref, rl, ren = O.speech2mel(wav.numpy().astype(np.float64), lens, cfg)
+    m = Speech2MelSpec(**conf).to(DEV)
+    wl = torch.tensor(lens, device=DEV)
+    x = wav.to(DEV)[..., None]
+    for _ in range(2):
+        poison = [torch.full((n,), float("nan"), device=DEV) for n in (37 * 301 * 80, 37 * 301, 37 * 301 * 80)]
+        torch.cuda.synchronize()
+        del poison
+        feat, flen, en, _ = m(x, wl)
+        torch.cuda.synchronize()
+        assert np.array_equal(flen.cpu().numpy(), rl)
+        assert not torch.isnan(feat).any() and not torch.isnan(en).any()
+        assert_close(feat.cpu().numpy(), ref, what="mel incl. padded rows")
+        assert_close(en.cpu().numpy(), ren, what="energy incl. padded rows")
