@@ -68,7 +68,7 @@ typedef struct sfe_plan sfe_plan;
  * on_host = 1: they are HOST pointers and the descriptors travel inside the kernel parameter
  *              block (no H2D copy, nothing to keep alive after the call returns); allowed while
  *              2*(n_freq+n_time)*B <= SFE_MASK_INLINE_MAX, else SFE_ERR_BAD_ARG. */
-#define SFE_MASK_INLINE_MAX 768
+#define SFE_MASK_INLINE_MAX 2304
 typedef struct sfe_masks {
   const int32_t* freq_pos;
   const int32_t* freq_len;

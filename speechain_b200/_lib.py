@@ -36,7 +36,7 @@ class SfeMasks(C.Structure):
     ]
 
 
-MASK_INLINE_MAX = 768
+MASK_INLINE_MAX = 2304
 
 
 class SfeWarp(C.Structure):

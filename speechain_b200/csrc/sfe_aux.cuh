@@ -201,7 +201,9 @@ __device__ __forceinline__ void cubic_w(float t, float (&w)[4]) {
 #ifndef SFE_NORM_MINB
 #define SFE_NORM_MINB 4
 #endif
-__global__ void __launch_bounds__(256, SFE_NORM_MINB) normalize_kernel(const __grid_constant__ NormParams p) {
+// WARP: the instance with the time-warp gather (more registers: 3 CTAs per SM); the plain instance keeps 4 per SM
+template <bool WARP>
+__global__ void __launch_bounds__(256, WARP ? SFE_NORM_MINB - 1 : SFE_NORM_MINB) normalize_kernel(const __grid_constant__ NormParams p) {
   pdl_launch_dependents();
   extern __shared__ float nsm[];  // mean[D] | 1/std[D] | fmask[D]
   const int b = blockIdx.y, D = p.D;
@@ -298,9 +300,11 @@ __global__ void __launch_bounds__(256, SFE_NORM_MINB) normalize_kernel(const __g
       rv[e] = s_rstd[d];
       fv[e] = s_fm[d];
     }
-    if (vec && !p.warp_on) {
+    if (vec) {
       // common case: four independent rows in flight per thread (the pass is latency bound otherwise);
-      // 32-bit row indices, one compare per time-mask interval, 64-bit arithmetic only in the address
+      // 32-bit row indices, one compare per time-mask interval, 64-bit arithmetic only in the address.
+      // A time warp (on by default in the recipes' SpecAugment blocks) turns the load of a row below warp_minlen
+      // into the four-tap gather; every other row streams as usual.
       const int it1 = static_cast<int>(t1), nv = static_cast<int>(n_valid);
       const float4* sp = reinterpret_cast<const float4*>(src) + c;
       float4* dp = reinterpret_cast<float4*>(dst) + c;
@@ -323,17 +327,58 @@ __global__ void __launch_bounds__(256, SFE_NORM_MINB) normalize_kernel(const __g
       const float4 padv = make_float4(p.pad_value, p.pad_value, p.pad_value, p.pad_value);
       const bool synth = !p.src_has_pad;
       int t = static_cast<int>(t0) + r0;
-      for (; t + 3 * rows < it1; t += 4 * rows) {
-        float4 x[4];
+      if (!WARP || !p.warp_on) {
+        for (; t + 3 * rows < it1; t += 4 * rows) {
+          float4 x[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int tt = t + u * rows;
-          x[u] = (synth && tt >= nv) ? padv : __ldcs(sp + static_cast<long long>(tt) * W);
+          for (int u = 0; u < 4; ++u) {
+            const int tt = t + u * rows;
+            x[u] = (synth && tt >= nv) ? padv : __ldcs(sp + static_cast<long long>(tt) * W);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) finish(t + u * rows, x[u]);
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) finish(t + u * rows, x[u]);
+        for (; t < it1; t += rows) finish(t, (synth && t >= nv) ? padv : __ldcs(sp + static_cast<long long>(t) * W));
+        continue;
       }
-      for (; t < it1; t += rows) finish(t, (synth && t >= nv) ? padv : __ldcs(sp + static_cast<long long>(t) * W));
+      if constexpr (WARP) {
+        const int wmin = (WARP && p.warp_on) ? p.warp_minlen : 0;
+        auto load_row = [&](int tt) -> float4 {
+          if (synth && tt >= nv) return padv;
+          if (tt < wmin) {
+            int lo, in_len, out_len, t2;
+            if (tt < p.warp_pos) { lo = 0; in_len = p.warp_center; out_len = p.warp_pos; t2 = tt; }
+            else { lo = p.warp_center; in_len = p.warp_minlen - p.warp_center; out_len = p.warp_minlen - p.warp_pos; t2 = tt - p.warp_pos; }
+            const float scale = out_len > 1 ? static_cast<float>(in_len - 1) / static_cast<float>(out_len - 1) : 0.f;
+            const float real = scale * static_cast<float>(t2);
+            const int i0 = static_cast<int>(floorf(real));
+            float cw[4];
+            if (p.warp_on == 2) {  // bilinear (align_corners=True): taps i0, i0 + 1 with weights 1 - f, f
+              const float f = real - static_cast<float>(i0);
+              cw[0] = 0.f; cw[1] = 1.f - f; cw[2] = f; cw[3] = 0.f;
+            } else {
+              cubic_w(real - static_cast<float>(i0), cw);
+            }
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int idx = lo + min(max(i0 - 1 + q, 0), in_len - 1);
+              const float4 v = __ldg(sp + static_cast<long long>(idx) * W);
+              x.x = fmaf(cw[q], v.x, x.x); x.y = fmaf(cw[q], v.y, x.y); x.z = fmaf(cw[q], v.z, x.z); x.w = fmaf(cw[q], v.w, x.w);
+            }
+            return x;
+          }
+          return __ldcs(sp + static_cast<long long>(tt) * W);
+        };
+        for (; t + 3 * rows < it1; t += 4 * rows) {
+          float4 x[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) x[u] = load_row(t + u * rows);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) finish(t + u * rows, x[u]);
+        }
+        for (; t < it1; t += rows) finish(t, load_row(t));
+      }
       continue;
     }
     for (long long t = t0 + r0; t < t1; t += rows) {
@@ -343,7 +388,7 @@ __global__ void __launch_bounds__(256, SFE_NORM_MINB) normalize_kernel(const __g
       int idx[4];
       float cw[4];
       bool warped = false;
-      if (p.warp_on && t < p.warp_minlen) {
+      if (WARP && p.warp_on && t < p.warp_minlen) {
         warped = true;
         int lo, in_len, out_len, tt;
         if (t < p.warp_pos) { lo = 0; in_len = p.warp_center; out_len = p.warp_pos; tt = static_cast<int>(t); }

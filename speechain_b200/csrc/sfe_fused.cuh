@@ -46,7 +46,7 @@ constexpr int FPW = 2;                    // frames per unit (per warp step)
 constexpr int MAX_MEL_ROUNDS = 16;        // phases of 32 filter units (n_mels <= 256)
 constexpr int kMelUnroll = SFE_MEL_UNROLL;
 constexpr int MEL_PAD_BINS = 4;           // zeroed bins behind the power spectrum (filter units read whole 4-tap blocks)
-constexpr int MASK_INLINE_MAX = 768;      // SFE_MASK_INLINE_MAX
+constexpr int MASK_INLINE_MAX = 2304;     // SFE_MASK_INLINE_MAX (the recipes' 4 + 5 masks for up to 128 utterances)
 constexpr int UNIT_TABLE_MAX_B = 256;     // batches up to this size get a per-utterance cost table
 constexpr int REAL_UNIT_COST = 8;         // a unit with real frames costs this many pad-only units
 constexpr int HOST_SPLIT_MAX_GRID = 160;  // tile kernel: grids up to this size can take their work split from the host

@@ -870,7 +870,8 @@ static int normalize_impl(const float* src, float* dst, const int64_t* feat_len,
   long long blocks_per_utt = (static_cast<long long>(n_sm) * per_sm + B - 1) / B;
 #else
   // (rounded DOWN: the grid must fit the resident CTAs — one wave; a second, partly filled one costs a quarter)
-  long long blocks_per_utt = static_cast<long long>(n_sm) * per_sm / B;
+  // (the instance with the time-warp gather runs one CTA per SM less)
+  long long blocks_per_utt = static_cast<long long>(n_sm) * (warp_on && per_sm > 1 ? per_sm - 1 : per_sm) / B;
 #endif
   if (blocks_per_utt < 1) blocks_per_utt = 1;
   long long fpc64 = (F + blocks_per_utt - 1) / blocks_per_utt;
@@ -879,7 +880,8 @@ static int normalize_impl(const float* src, float* dst, const int64_t* feat_len,
   const int fpc = static_cast<int>(fpc64 > 0x3fffffff ? 0x3fffffff : fpc64);
   P.frames_per_cta = fpc;
   dim3 grid(static_cast<unsigned>((F + fpc - 1) / fpc), static_cast<unsigned>(B));
-  SFE_CUDA(launch_pdl<NormParams>(normalize_kernel, grid, dim3(256), 3 * D * sizeof(float), static_cast<cudaStream_t>(stream), P));
+  SFE_CUDA(launch_pdl<NormParams>(warp_on ? normalize_kernel<true> : normalize_kernel<false>, grid, dim3(256),
+                                  3 * D * sizeof(float), static_cast<cudaStream_t>(stream), P));
   SFE_CUDA(cudaGetLastError());
   return SFE_OK;
 }

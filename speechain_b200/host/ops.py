@@ -114,8 +114,8 @@ class DeviceMasks:
         self.on_host = total <= _lib.MASK_INLINE_MAX
         self.buf = None
         if not self.on_host and self._host:
-            flat = torch.from_numpy(np.concatenate([a.ravel() for a in self._host]))
-            self.buf = flat.pin_memory().to(device, non_blocking=True)
+            # (a pageable copy of a few KB: pinning a fresh buffer every step costs five times the copy)
+            self.buf = torch.from_numpy(np.concatenate([a.ravel() for a in self._host])).to(device)
 
     @classmethod
     def persistent(cls, batch_size: int, n_freq: int, n_time: int):

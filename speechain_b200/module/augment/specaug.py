@@ -113,9 +113,13 @@ class SpecAugment(Module):
         masks.fill, masks.fill_dev = 0.0, None
         warp = None
         if self.time_warp and minlen > 2 * self.time_warp_window + 1:
+            # (the two scalar draws of specaug.py:98-108 — randint(size=(1,)) — in place on a persistent tensor)
             w = self.time_warp_window
-            center = torch.randint(low=w + 1, high=minlen - w, size=(1,))[0].item()
-            pos = torch.randint(low=center - w, high=center + w, size=(1,))[0].item()
+            t1 = self.__dict__.get("_warp_draw")
+            if t1 is None:
+                t1 = self.__dict__["_warp_draw"] = torch.empty((1,), dtype=torch.int64)
+            center = t1.random_(w + 1, minlen - w).item()
+            pos = t1.random_(center - w, center + w).item()
             warp = (center, pos, minlen, 2 if self.time_warp_mode == "bilinear" else 1)
         t_fpos, t_flen, t_tpos, t_tlen = masks.views
         if nf:
