@@ -157,14 +157,18 @@ int sfe_frontend_forward(const sfe_plan* plan, const float* wav, int64_t wav_pit
  *                and must alternate from call to call on the same scratch; after a failed call zero
  *                the scratch again.
  * mean_out/std_out (B, n_mels), optional: the per-utterance statistics of norm_mode 2.
- * wav_len_host: as in sfe_frontend_forward (optional host copy of wav_len). */
+ * wav_len_host: as in sfe_frontend_forward (optional host copy of wav_len).
+ * warp / warp_out: NULL, or the SpecAugment time warp (specaug.py:89-127: the warp comes BEFORE the masks) and a second
+ *                (B, F, n_mels) buffer: the last pass then runs out of place — `mel` holds the unwarped (norm_mode 0/1:
+ *                normalised, norm_mode 2: raw) features afterwards, `warp_out` the result.  The recipes' SpecAugment
+ *                blocks leave time_warp at its default (on), so this is their training step in one call. */
 int sfe_chain_forward(const sfe_plan* plan, const float* wav, int64_t wav_pitch,
                       const int64_t* wav_len, int32_t B, int64_t T_max, float* mel,
                       int64_t* feat_len, int64_t* stats_ws, int32_t ws_half, int32_t norm_mode,
                       const float* mean,
                       const float* std, float clamp, int32_t use_mean, int32_t use_std,
                       float* mean_out, float* std_out, const sfe_masks* masks, void* stream,
-                      const int64_t* wav_len_host);
+                      const int64_t* wav_len_host, const sfe_warp* warp, float* warp_out);
 
 /* LinearSpec2MelSpec.forward on an existing linear spectrogram (linear2mel.py:163-189).
  * lin (B*F, n_fft/2+1) -> mel (B*F, n_mels). */

@@ -890,15 +890,26 @@ extern "C" int sfe_chain_forward(const sfe_plan* pl, const float* wav, int64_t w
                                  int32_t B, int64_t T_max, float* mel, int64_t* feat_len, int64_t* stats_ws,
                                  int32_t ws_half, int32_t norm_mode, const float* mean, const float* std, float clamp,
                                  int32_t use_mean, int32_t use_std, float* mean_out, float* std_out,
-                                 const sfe_masks* masks, void* stream, const int64_t* wav_len_host) {
+                                 const sfe_masks* masks, void* stream, const int64_t* wav_len_host,
+                                 const sfe_warp* warp, float* warp_out) {
   if (!pl) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: NULL plan");
   if (!mel || !feat_len) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: mel / feat_len is NULL");
-  if (norm_mode == 0)
-    return sfe_frontend_forward(pl, wav, wav_pitch, wav_len, B, T_max, mel, nullptr, nullptr, feat_len, nullptr,
-                                nullptr, nullptr, masks, 0, stream, wav_len_host);
-  if (norm_mode == 1)
-    return sfe_frontend_forward(pl, wav, wav_pitch, wav_len, B, T_max, mel, nullptr, nullptr, feat_len, nullptr,
-                                use_mean ? mean : nullptr, use_std ? std : nullptr, masks, 0, stream, wav_len_host);
+  const bool warp_on = warp && warp->enabled;
+  if (warp_on && (!warp_out || warp_out == mel))
+    return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: a time warp needs warp_out, a second (B, F, n_mels) buffer");
+  const int64_t F = sfe_plan_num_frames(pl, T_max);
+  if (norm_mode == 0 || norm_mode == 1) {
+    // masks ride in the frontend kernel's epilogue — unless a time warp comes first (SpecAugment warps, then masks):
+    // then the kernel writes the (normalised) features and ONE more pass gathers the warp and applies the masks
+    if (int rc = sfe_frontend_forward(pl, wav, wav_pitch, wav_len, B, T_max, mel, nullptr, nullptr, feat_len, nullptr,
+                                      (norm_mode == 1 && use_mean) ? mean : nullptr,
+                                      (norm_mode == 1 && use_std) ? std : nullptr, warp_on ? nullptr : masks, 0, stream,
+                                      wav_len_host))
+      return rc;
+    if (!warp_on) return SFE_OK;
+    return normalize_impl(mel, warp_out, feat_len, B, F, pl->cfg.n_mels, nullptr, 0, clamp, 0, 0, nullptr, nullptr, 0,
+                          nullptr, nullptr, 1, 0.f, warp, masks, stream, nullptr);
+  }
   if (norm_mode != 2) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: norm_mode must be 0, 1 or 2");
   if (!stats_ws) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: norm_mode 2 needs stats_ws");
   if (!pl->cfg.mel_logging) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: norm_mode 2 needs a log-mel plan");
@@ -911,9 +922,10 @@ extern "C" int sfe_chain_forward(const sfe_plan* pl, const float* wav, int64_t w
   if (int rc = frontend_forward_impl(pl, wav, wav_pitch, wav_len, B, T_max, mel, nullptr, nullptr, feat_len, cur,
                                      nullptr, nullptr, nullptr, 1, stream, false, wav_len_host))
     return rc;
-  if (int rc = normalize_impl(mel, mel, feat_len, B, sfe_plan_num_frames(pl, T_max), pl->cfg.n_mels, cur, 1, clamp,
-                              use_mean, use_std, nullptr, nullptr, 0, mean_out, std_out, 0, pl->proto.pad_mel, nullptr,
-                              masks, stream, other))
+  // in place, or out of place into warp_out with the time-warp gather
+  if (int rc = normalize_impl(mel, warp_on ? warp_out : mel, feat_len, B, F, pl->cfg.n_mels, cur, 1, clamp,
+                              use_mean, use_std, nullptr, nullptr, 0, mean_out, std_out, 0, pl->proto.pad_mel,
+                              warp_on ? warp : nullptr, masks, stream, other))
     return rc;
   return SFE_OK;
 }

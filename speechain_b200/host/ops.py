@@ -263,8 +263,8 @@ class FrontendPlan:
 
     def chain(self, wav: torch.Tensor, wav_len: torch.Tensor, *, norm_mode: int, mean=None, std=None,
               clamp: float = 1e-10, use_mean=True, use_std=True, masks: Optional[DeviceMasks] = None,
-              len_host=None):
-        """frontend -> normalise -> masks in one library call (see sfe_chain_forward).  Lean on purpose:
+              len_host=None, warp=None):
+        """frontend -> normalise -> [time warp ->] masks in one library call (see sfe_chain_forward).  Lean on purpose:
         the caller has validated `wav` (B, T) or (B, T, 1) fp32 CUDA with unit stride along T and `wav_len` int64
         CUDA; `len_host` is the host copy of `wav_len` (contiguous numpy int64, or the address of B int64), or None."""
         B, T = wav.shape[0], wav.shape[1]  # (B, T) or (B, T, 1)
@@ -283,6 +283,10 @@ class FrontendPlan:
             ws, half = ent
             ent[1] = -1  # marks the scratch dirty until the call below has been enqueued completely
         ms = masks.struct() if masks is not None else None
+        wp = out2 = None
+        if warp is not None:  # the last pass runs out of place: a second buffer takes the result
+            wp = _lib.SfeWarp(int(warp[3]) if len(warp) > 3 else 1, int(warp[0]), int(warp[1]), int(warp[2]))
+            out2 = torch.empty((B, F, self.n_mels), dtype=torch.float32, device=dev)
         idx = dev.index
         prev = torch._C._cuda_getDevice()
         if idx is not None and idx != prev:
@@ -296,7 +300,8 @@ class FrontendPlan:
                 mean.data_ptr() if mean is not None else None, std.data_ptr() if std is not None else None,
                 clamp, int(use_mean), int(use_std), None, None, C.byref(ms) if ms is not None else None,
                 torch._C._cuda_getCurrentRawStream(idx),
-                len_host if isinstance(len_host, int) else _host_len_ptr(len_host, B))
+                len_host if isinstance(len_host, int) else _host_len_ptr(len_host, B),
+                C.byref(wp) if wp is not None else None, out2.data_ptr() if out2 is not None else None)
         finally:
             if idx != prev:
                 torch.cuda.set_device(prev)
@@ -304,7 +309,7 @@ class FrontendPlan:
             _lib.check(rc)
         if ws is not None:
             self._ws[B][1] = 1 - half
-        return mel, feat_len
+        return (out2 if out2 is not None else mel), feat_len
 
     def griffinlim(self, spec: torch.Tensor, feat_len: torch.Tensor, *, n_iter: int = 32, momentum: float = 0.99,
                    init_angles: Optional[torch.Tensor] = None, inv_preemph_taps: int = 0):

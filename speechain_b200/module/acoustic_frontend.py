@@ -94,11 +94,15 @@ class AcousticFrontend(Module):
                 return self._unfused(feat, feat_len, epoch, domain, drawn=(warp, masks))
         # masks ride in a kernel epilogue; a time warp needs one out-of-place gather pass, which also
         # carries the normalisation and the masks when the statistics are only known after the first pass
-        fused_masks = masks if warp is None else None
-        warp_done = warp is None
+        # (fp32 output: the library call carries the warp itself — frontend launch, then one warp + mask pass; a bf16
+        #  output keeps the separate last pass, which also converts)
+        in_call = warp is not None and not bf16
+        fused_masks = masks if (warp is None or in_call) else None
+        cwarp = warp if in_call else None
+        warp_done = warp is None or in_call
 
         if norm is None:
-            y, ylen = plan.chain(wav, len_dev, norm_mode=0, masks=fused_masks, len_host=len_host)
+            y, ylen = plan.chain(wav, len_dev, norm_mode=0, masks=fused_masks, len_host=len_host, warp=cwarp)
         else:
             kind = norm.norm_type
             if kind == "group":
@@ -113,10 +117,10 @@ class AcousticFrontend(Module):
                 mean = norm.get_buffer(f"{prefix}_mean") if norm.mean_norm else None
                 std = norm.get_buffer(f"{prefix}_std") if norm.std_norm else None
                 y, ylen = plan.chain(wav, len_dev, norm_mode=1, mean=mean, std=std, use_mean=norm.mean_norm,
-                                     use_std=norm.std_norm, masks=fused_masks, len_host=len_host)
-            elif not bf16 and warp is None and plan.mel_logging and (kind == "utterance" or (kind == "batch" and not norm.training)):
+                                     use_std=norm.std_norm, masks=fused_masks, len_host=len_host, warp=cwarp)
+            elif not bf16 and plan.mel_logging and (kind == "utterance" or (kind == "batch" and not norm.training)):
                 y, ylen = plan.chain(wav, len_dev, norm_mode=2, clamp=norm.clamp, use_mean=norm.mean_norm,
-                                     use_std=norm.std_norm, masks=fused_masks, len_host=len_host)
+                                     use_std=norm.std_norm, masks=fused_masks, len_host=len_host, warp=cwarp)
             else:
                 # raw rows + sums, then ONE pass: statistics (exchanged across ranks if needed), warp, masks
                 if wav.dim() == 3:
