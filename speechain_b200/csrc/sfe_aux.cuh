@@ -201,6 +201,79 @@ __device__ __forceinline__ void cubic_w(float t, float (&w)[4]) {
 #ifndef SFE_NORM_MINB
 #define SFE_NORM_MINB 4
 #endif
+// ---------------------------------------------------------------------------------------------
+// SpecAugment time warp IN PLACE, rows [0, minlen) only (+ time masks): the last launch of a training step whose
+// statistics were known up front.  The frontend kernel has already written every row normalised and frequency-
+// masked; rows at or past minlen are final (the warp and the time masks live below the batch's shortest length,
+// specaug.py:96-127,178-199), so this kernel touches minlen of F rows instead of reading and re-writing the tensor.
+// A CTA owns `cols` Mel bins of one utterance for ALL warped rows: it stages them in shared memory, then gathers the
+// four taps from there — no other CTA reads what it overwrites.  (A frequency-masked bin holds the constant fill 0
+// in every row, and any interpolation of zeros is zero: the frequency masks need not be applied again.)
+// ---------------------------------------------------------------------------------------------
+struct WarpInPlaceParams {
+  float* x;
+  int B;
+  long long F;
+  int D, cols;
+  int mode, center, pos, minlen;  // mode 1 bicubic, 2 bilinear (align_corners=True)
+  MaskDesc mk;                    // time masks only
+  float fill;
+};
+
+__global__ void __launch_bounds__(256) warp_inplace_kernel(const __grid_constant__ WarpInPlaceParams p) {
+  pdl_launch_dependents();
+  extern __shared__ __align__(16) float wsm[];  // [minlen][cols]
+  const int b = blockIdx.y, c0 = blockIdx.x * p.cols;
+  const int cols4 = min(p.cols, p.D - c0) / 4;
+  const int n_tmask = p.mk.n_tmask;
+  __shared__ int2 s_tiv[64];
+  if (p.mk.inl_on)
+    for (int q = threadIdx.x; q < n_tmask; q += blockDim.x)
+      s_tiv[q] = make_int2(p.mk.inl[b * n_tmask + q], max(p.mk.inl[p.B * n_tmask + b * n_tmask + q], 0));
+  pdl_wait();
+  if (!p.mk.inl_on)
+    for (int q = threadIdx.x; q < n_tmask; q += blockDim.x)
+      s_tiv[q] = make_int2(p.mk.tpos[b * n_tmask + q], max(p.mk.tlen[b * n_tmask + q], 0));
+  float* base = p.x + static_cast<long long>(b) * p.F * p.D + c0;
+  const int items = p.minlen * cols4;
+  float4* sm4 = reinterpret_cast<float4*>(wsm);
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int t = i / cols4, c = i - t * cols4;
+    sm4[i] = *(reinterpret_cast<const float4*>(base + static_cast<long long>(t) * p.D) + c);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int t = i / cols4, c = i - t * cols4;
+    int lo, in_len, out_len, t2;
+    if (t < p.pos) { lo = 0; in_len = p.center; out_len = p.pos; t2 = t; }
+    else { lo = p.center; in_len = p.minlen - p.center; out_len = p.minlen - p.pos; t2 = t - p.pos; }
+    const float scale = out_len > 1 ? static_cast<float>(in_len - 1) / static_cast<float>(out_len - 1) : 0.f;
+    const float real = scale * static_cast<float>(t2);
+    const int i0 = static_cast<int>(floorf(real));
+    float cw[4];
+    if (p.mode == 2) {
+      const float f = real - static_cast<float>(i0);
+      cw[0] = 0.f; cw[1] = 1.f - f; cw[2] = f; cw[3] = 0.f;
+    } else {
+      cubic_w(real - static_cast<float>(i0), cw);
+    }
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = lo + min(max(i0 - 1 + q, 0), in_len - 1);
+      const float4 v = sm4[idx * cols4 + c];
+      x.x = fmaf(cw[q], v.x, x.x); x.y = fmaf(cw[q], v.y, x.y); x.z = fmaf(cw[q], v.z, x.z); x.w = fmaf(cw[q], v.w, x.w);
+    }
+    bool tmask = false;
+    for (int q = 0; q < n_tmask; ++q) {
+      const int2 iv = s_tiv[q];
+      tmask |= static_cast<unsigned>(t - iv.x) < static_cast<unsigned>(iv.y);
+    }
+    if (tmask) x = make_float4(p.fill, p.fill, p.fill, p.fill);
+    *(reinterpret_cast<float4*>(base + static_cast<long long>(t) * p.D) + c) = x;
+  }
+}
+
 // WARP: the instance with the time-warp gather (more registers: 3 CTAs per SM); the plain instance keeps 4 per SM
 template <bool WARP>
 __global__ void __launch_bounds__(256, WARP ? SFE_NORM_MINB - 1 : SFE_NORM_MINB) normalize_kernel(const __grid_constant__ NormParams p) {

@@ -886,6 +886,68 @@ static int normalize_impl(const float* src, float* dst, const int64_t* feat_len,
   return SFE_OK;
 }
 
+// In-place time warp of rows [0, minlen) + time masks (warp_inplace_kernel): the tail of sfe_chain_forward's warp
+// schedules.  warp_tail_cols() says whether it applies (Mel bins per CTA, or 0) — to be asked BEFORE the launches in
+// front of it are issued.
+static int warp_tail_cols(int B, int D, const float* x, const sfe_warp* warp, const sfe_masks* masks) {
+  if (D % 4 != 0 || (reinterpret_cast<uintptr_t>(x) & 15)) return 0;
+  if (masks && (masks->fill != 0.f || masks->fill_dev)) return 0;  // (interpolating a masked bin must give the fill)
+  // about two CTAs per SM, and no more than 200 KB of shared memory to stage minlen rows
+  const int per_utt = (2 * cached_sm_count() + B - 1) / B;
+  int cols = ((D + per_utt - 1) / per_utt + 3) / 4 * 4;
+  const int fit = static_cast<int>((200 * 1024) / (static_cast<long long>(warp->minlen) * 4)) / 4 * 4;
+  if (cols > fit) cols = fit;
+  if (cols > D) cols = D;
+  return cols < 4 ? 0 : cols;
+}
+
+static int warp_tail(float* x, int32_t B, int64_t F, int D, int cols, const sfe_warp* warp, const sfe_masks* masks,
+                     void* stream) {
+  const size_t smem = static_cast<size_t>(warp->minlen) * cols * sizeof(float);
+  static std::mutex mu;
+  static bool raised = false;
+  if (smem > 48 * 1024) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!raised) {
+      SFE_CUDA(cudaFuncSetAttribute(warp_inplace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      raised = true;
+    }
+  }
+  WarpInPlaceParams P;
+  memset(&P, 0, sizeof(P));
+  P.x = x;
+  P.B = B;
+  P.F = F;
+  P.D = D;
+  P.cols = cols;
+  P.mode = warp->enabled == 2 ? 2 : 1;
+  P.center = warp->center;
+  P.pos = warp->pos;
+  P.minlen = warp->minlen;
+  if (masks && masks->n_time > 0) {
+    sfe_masks tm = *masks;  // time masks only
+    tm.n_freq = 0;
+    tm.freq_pos = tm.freq_len = nullptr;
+    float fill;
+    const float* fill_dev;
+    if (int rc = fill_masks(&tm, B, &P.mk, &fill, &fill_dev)) return rc;
+    P.fill = fill;
+  }
+  dim3 grid(static_cast<unsigned>((D + cols - 1) / cols), static_cast<unsigned>(B));
+  SFE_CUDA(launch_pdl<WarpInPlaceParams>(warp_inplace_kernel, grid, dim3(256), smem, static_cast<cudaStream_t>(stream), P));
+  SFE_CUDA(cudaGetLastError());
+  return SFE_OK;
+}
+
+// frequency masks only (the launch in front of warp_tail applies them to every row)
+static const sfe_masks* freq_only(const sfe_masks* masks, sfe_masks* tmp) {
+  if (!masks || masks->n_freq <= 0) return nullptr;
+  *tmp = *masks;
+  tmp->n_time = 0;
+  tmp->time_pos = tmp->time_len = nullptr;
+  return tmp;
+}
+
 extern "C" int sfe_chain_forward(const sfe_plan* pl, const float* wav, int64_t wav_pitch, const int64_t* wav_len,
                                  int32_t B, int64_t T_max, float* mel, int64_t* feat_len, int64_t* stats_ws,
                                  int32_t ws_half, int32_t norm_mode, const float* mean, const float* std, float clamp,
@@ -899,8 +961,24 @@ extern "C" int sfe_chain_forward(const sfe_plan* pl, const float* wav, int64_t w
     return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: a time warp needs warp_out, a second (B, F, n_mels) buffer");
   const int64_t F = sfe_plan_num_frames(pl, T_max);
   if (norm_mode == 0 || norm_mode == 1) {
-    // masks ride in the frontend kernel's epilogue — unless a time warp comes first (SpecAugment warps, then masks):
-    // then the kernel writes the (normalised) features and ONE more pass gathers the warp and applies the masks
+    // masks ride in the frontend kernel's epilogue — unless a time warp comes first (SpecAugment warps, then masks).
+    // Then: the kernel writes every row normalised and FREQUENCY-masked into warp_out, and a small kernel warps and
+    // time-masks rows [0, minlen) of it in place (warp_chain_in_place); where that is not possible (a fill value
+    // other than 0, a minlen too long to stage) the kernel writes `mel` and ONE more pass over the whole tensor
+    // gathers the warp and applies the masks.
+    if (warp_on) {
+      if (!(warp->center > 0 && warp->center < warp->minlen && warp->pos > 0 && warp->pos < warp->minlen && warp->minlen <= F))
+        return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: inconsistent warp descriptor");
+      if (const int cols = warp_tail_cols(B, pl->cfg.n_mels, warp_out, warp, masks)) {
+        sfe_masks fm;
+        if (int rc = sfe_frontend_forward(pl, wav, wav_pitch, wav_len, B, T_max, warp_out, nullptr, nullptr, feat_len,
+                                          nullptr, (norm_mode == 1 && use_mean) ? mean : nullptr,
+                                          (norm_mode == 1 && use_std) ? std : nullptr, freq_only(masks, &fm), 0, stream,
+                                          wav_len_host))
+          return rc;
+        return warp_tail(warp_out, B, F, pl->cfg.n_mels, cols, warp, masks, stream);
+      }
+    }
     if (int rc = sfe_frontend_forward(pl, wav, wav_pitch, wav_len, B, T_max, mel, nullptr, nullptr, feat_len, nullptr,
                                       (norm_mode == 1 && use_mean) ? mean : nullptr,
                                       (norm_mode == 1 && use_std) ? std : nullptr, warp_on ? nullptr : masks, 0, stream,
@@ -922,6 +1000,19 @@ extern "C" int sfe_chain_forward(const sfe_plan* pl, const float* wav, int64_t w
   if (int rc = frontend_forward_impl(pl, wav, wav_pitch, wav_len, B, T_max, mel, nullptr, nullptr, feat_len, cur,
                                      nullptr, nullptr, nullptr, 1, stream, false, wav_len_host))
     return rc;
+  if (warp_on) {
+    if (!(warp->center > 0 && warp->center < warp->minlen && warp->pos > 0 && warp->pos < warp->minlen && warp->minlen <= F))
+      return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: inconsistent warp descriptor");
+    if (const int cols = warp_tail_cols(B, pl->cfg.n_mels, warp_out, warp, masks)) {
+      // normalise + frequency masks into warp_out (every row), then warp + time masks on its rows [0, minlen) in place
+      sfe_masks fm;
+      if (int rc = normalize_impl(mel, warp_out, feat_len, B, F, pl->cfg.n_mels, cur, 1, clamp, use_mean, use_std, nullptr,
+                                  nullptr, 0, mean_out, std_out, 0, pl->proto.pad_mel, nullptr, freq_only(masks, &fm), stream,
+                                  other))
+        return rc;
+      return warp_tail(warp_out, B, F, pl->cfg.n_mels, cols, warp, masks, stream);
+    }
+  }
   // in place, or out of place into warp_out with the time-warp gather
   if (int rc = normalize_impl(mel, warp_on ? warp_out : mel, feat_len, B, F, pl->cfg.n_mels, cur, 1, clamp,
                               use_mean, use_std, nullptr, nullptr, 0, mean_out, std_out, 0, pl->proto.pad_mel,

@@ -569,6 +569,38 @@ def test_fused_chain_with_time_warp_vs_oracle(norm_type):
     assert_close(got, ref, what=f"warp chain {norm_type}")
 
 
+@pytest.mark.parametrize("mode", ["bicubic", "bilinear"])
+@pytest.mark.parametrize("n_fft", [None, 512])
+def test_frozen_global_statistics_with_recipe_specaug_vs_oracle(n_fft, mode):
+    """The ASR recipes' training step once the global statistics are frozen (normalize: True = global statistics
+    averaged over max_epoch_num epochs; their SpecAugment block leaves time_warp on): the frontend kernel writes every
+    row normalised and frequency-masked, a small kernel warps and time-masks rows [0, minlen) in place."""
+    g = torch.Generator().manual_seed(777)
+    lens = sorted(torch.randint(16000, 64001, (7,), generator=g).tolist(), reverse=True)
+    wav = _wave(23, lens, zero_seg=False)
+    conf = dict(n_mels=80, win_length=0.025, hop_length=0.010, sr=16000, preemphasis=0.97)
+    if n_fft:
+        conf["n_fft"] = n_fft
+    sconf = dict(freq_mask_width=15, freq_mask_num=4, time_mask_width=0.05, time_mask_num=5, time_warp_mode=mode)
+    chain = AcousticFrontend(frontend=dict(conf=conf), normalize=dict(norm_type="global", max_epoch_num=1), specaug=sconf).to(DEV)
+    chain.train()
+    x, xl = wav.to(DEV)[..., None], torch.tensor(lens, device=DEV)
+    torch.manual_seed(5)
+    chain(x, xl, epoch=1)                       # one averaging step fixes the statistics
+    torch.manual_seed(99)
+    y, yl = chain(x, xl, epoch=2)               # epoch > max_epoch_num: statistics known up front
+    feat, flen, _ = O.speech2mel(wav.numpy().astype(np.float64), lens, O.FrontendCfg(**conf))
+    ref = O.feat_norm_global([(feat, flen)], O.RunningStats(), 1)[0]   # the statistics of that one step
+    d = O.specaug_draw(O.TorchCpuRandint(99), len(lens), 80, flen, O.SpecAugCfg(**sconf))
+    assert d.warp is not None
+    ref = O.specaug_apply(ref, flen, d, feat_norm=True)
+    got = y.cpu().numpy()
+    assert np.array_equal(yl.cpu().numpy(), flen)
+    mask = O.specaug_mask(*got.shape, d)
+    assert (got[mask] == 0.0).all() and np.count_nonzero((got == 0.0) & ~mask) <= 2
+    assert_close(got, ref, what=f"frozen global statistics + warp ({mode}, n_fft {n_fft})")
+
+
 def test_c5_style_linear_and_mel_from_one_launch_with_running_global_norm():
     # BASELINE config 5 in miniature: magnitude linear spectrogram AND mel from one launch; mel -> global norm with
     # the running average over several batches (epoch=1) -> SpecAugment

@@ -36,3 +36,22 @@ for name, norm, aug, ep in (("utterance norm + masks, no warp (C2)", dict(norm_t
     host = (time.perf_counter() - t0) / 300 * 1e6
     torch.cuda.synchronize()
     print(f"{name:60s} {us:7.2f} us per step (host enqueue {host:5.1f} us)")
+
+# the library call alone (fixed draws): what the device needs
+chain = AcousticFrontend(frontend=dict(conf=w["frontend"]), normalize=dict(norm_type="global", max_epoch_num=1), specaug=recipe).to(dev)
+chain.train()
+for i in range(3): chain(batches[i], wl, epoch=1)
+fe = chain.frontend
+plan = fe.speech2linear._plan(dev, preemph=True, mel=fe.linear2mel.mel_conf())
+wl_dev = wl.to(dev)
+host = wl.numpy()
+flen_min = int((host.min() // 160) + 1)
+warp, masks = chain.specaug.draw_device(len(lens), 80, None, dev, minlen=flen_min)
+mean, std = chain.normalize.global_mean, chain.normalize.global_std
+print("warp", warp)
+for name, kw in (("chain mode 1 + masks", dict(norm_mode=1, mean=mean, std=std, masks=masks)),
+                 ("chain mode 1 + masks + warp", dict(norm_mode=1, mean=mean, std=std, masks=masks, warp=warp)),
+                 ("chain mode 2 + masks", dict(norm_mode=2, masks=masks)),
+                 ("chain mode 2 + masks + warp", dict(norm_mode=2, masks=masks, warp=warp))):
+    us = timeit(lambda i: plan.chain(batches[i % ring], wl_dev, len_host=host, **kw))
+    print(f"{name:52s} {us:7.2f} us per call")
