@@ -311,6 +311,28 @@ def measure_also(dev, world, rank, dist, peak, steps):
                               "frac": kb / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": kb}}
     del chain, fe, batches
 
+    # ---- the recipes' own training step on the C2 batch: `normalize: True` = global statistics, frozen after
+    #      max_epoch_num epochs (feat_norm.py:44-51), and the recipes' SpecAugment block, which leaves time_warp on
+    #      (recipes/asr/librispeech/train-clean-100/exp_cfg/*.yaml:188-194) ----
+    w = dict(WORKLOADS["c2"], normalize=dict(norm_type="global", max_epoch_num=1),
+             specaug=dict(freq_mask_width=15, freq_mask_num=4, time_mask_width=0.05, time_mask_num=5))
+    chain, fe, lens, batches, wl_dev, ring, F, D = build(w)
+    for i in range(3):
+        chain(batches[i % ring], wl_dev, epoch=1)      # averaging epoch: fixes the statistics
+    nr = max(50, min(steps, 300))
+    ms = timed(lambda i: chain(batches[i % ring], wl_dev, epoch=5), nr)
+    t0 = time.perf_counter()
+    for i in range(nr):
+        chain(batches[i % ring], wl_dev, epoch=5)
+    host_ms = (time.perf_counter() - t0) * 1e3 / nr
+    torch.cuda.synchronize()
+    out["c2_recipe"] = {"workload": "C2 batch through the recipes' own blocks: global statistics frozen (epoch > max_epoch_num) + "
+                                    "SpecAugment with time warp, 4 frequency and 5 time masks: frontend kernel (normalised, "
+                                    "frequency-masked rows) + in-place warp of rows [0, minlen)",
+                        "ms_per_step": ms, "value": world * sum(lens) / w["sr"] / (ms * 1e-3), "unit": "audio-s/s",
+                        "steps": nr, "host_enqueue_ms_per_step": host_ms, "gpu_launches_per_step": 2}
+    del chain, fe, batches
+
     # ---- C4: frontend + global normalisation (training, epoch=None): statistics all-reduce every step ----
     w = WORKLOADS["c4"]
     chain, fe, lens, batches, wl_dev, ring, F, D = build(w)
