@@ -770,3 +770,26 @@ def test_rows_past_each_length_are_written_by_the_frontend_kernel_itself():
         assert not torch.isnan(feat).any() and not torch.isnan(en).any()
         assert_close(feat.cpu().numpy(), ref, what="mel incl. padded rows")
         assert_close(en.cpu().numpy(), ren, what="energy incl. padded rows")
+
+
+def test_recipe_specaug_on_a_batch_beyond_the_inline_descriptor_block():
+    """2 * B * (4 + 5) mask descriptors of the recipes' SpecAugment block fit the kernel parameter block for up to 128
+    utterances; a larger batch uploads them (DeviceMasks, device arrays) — same masks, same features."""
+    B = 150
+    g = torch.Generator().manual_seed(150)
+    lens = sorted(torch.randint(3000, 12000, (B,), generator=g).tolist(), reverse=True)
+    wav = _wave(77, lens, zero_seg=False)
+    conf = dict(n_mels=80, n_fft=512, win_length=0.025, hop_length=0.010, sr=16000, preemphasis=0.97)
+    sconf = dict(freq_mask_width=15, freq_mask_num=4, time_mask_width=0.05, time_mask_num=5)
+    chain = AcousticFrontend(frontend=dict(conf=conf), normalize=dict(norm_type="utterance"), specaug=sconf).to(DEV)
+    chain.train()
+    torch.manual_seed(31)
+    y, yl = chain(wav.to(DEV)[..., None], torch.tensor(lens, device=DEV))
+    feat, flen, _ = O.speech2mel(wav.numpy().astype(np.float64), lens, O.FrontendCfg(**conf))
+    ref = O.feat_norm_utterance(feat, flen)
+    d = O.specaug_draw(O.TorchCpuRandint(31), B, 80, flen, O.SpecAugCfg(**sconf))
+    ref = O.specaug_apply(ref, flen, d, feat_norm=True)
+    got = y.cpu().numpy()
+    mask = O.specaug_mask(*got.shape, d)
+    assert (got[mask] == 0.0).all() and np.count_nonzero((got == 0.0) & ~mask) <= 2
+    assert_close(got, ref, what="recipe SpecAugment, B = 150")
