@@ -57,11 +57,16 @@ class AcousticFrontend(Module):
     def forward(self, feat: torch.Tensor, feat_len: torch.Tensor, epoch: int = None, domain=None):
         """feat (batch, T, 1) or (batch, T) fp32 CUDA waveforms, feat_len (batch,) int64 (CPU or CUDA).
         Returns (features (batch, F, n_mels), feature lengths (batch,) on the device)."""
-        fe = self.frontend
-        s2l = fe.speech2linear
-        norm: Optional[FeatureNormalization] = getattr(self, "normalize", None)
-        aug: Optional[SpecAugment] = getattr(self, "specaug", None) if self.training else None
-        bf16 = getattr(self, "out_dtype", None) == torch.bfloat16
+        # (submodules live in nn.Module._modules: every `self.x` is a __getattr__ round trip — look them up once)
+        fast = self.__dict__.get("_fast")
+        if fast is None:
+            fe = self.frontend
+            fast = self.__dict__["_fast"] = (fe, fe.speech2linear, fe.linear2mel, getattr(self, "normalize", None),
+                                             getattr(self, "specaug", None))
+        fe, s2l, l2m, norm, aug = fast
+        if not self.training:
+            aug = None
+        bf16 = self.__dict__.get("out_dtype") == torch.bfloat16
         if fe.delta_order is not None or fe.return_energy or s2l.pre_stft_norm is not None:
             if bf16:
                 raise NotImplementedError("out_dtype=bfloat16 is available for the fused log-Mel chain only")
@@ -82,7 +87,7 @@ class AcousticFrontend(Module):
         # if somebody asks for it (HostLengths.get on the returned lengths)
         flen_min = s2l._feat_len_of(int(len_host.min()))
         flen_host = None
-        plan = s2l._plan(wav.device, preemph=True, mel=fe.linear2mel.mel_conf())
+        plan = s2l._plan(wav.device, preemph=True, mel=l2m.mel_conf())
 
         # SpecAugment draws need only host-side lengths, so they happen before any launch
         warp = masks = None

@@ -50,7 +50,7 @@ class Speech2LinearSpec(Module):
     # ------------------------------------------------------------------------------------
     def _plan(self, device, preemph: bool = True, mel: Optional[dict] = None, plain_window: bool = False) -> FrontendPlan:
         # (a checkpoint load copies into the filterbank buffer in place: the version counter catches that)
-        key = (str(device), preemph, None if mel is None else (id(mel["weight"]), mel["weight"]._version), plain_window)
+        key = (device, preemph, None if mel is None else (id(mel["weight"]), mel["weight"]._version), plain_window)
         plan = self._plans.get(key)
         if plan is None:
             c = self.stft_config
