@@ -479,27 +479,7 @@ __global__ void __launch_bounds__(256, WARP ? SFE_NORM_MINB - 1 : SFE_NORM_MINB)
         for (int q = 0; q < 4; ++q) idx[q] = lo + min(max(i0 - 1 + q, 0), in_len - 1);
       }
       const bool is_pad = (t >= n_valid) && !p.src_has_pad;
-      if (vec) {
-        float4 x;
-        if (is_pad) x = make_float4(p.pad_value, p.pad_value, p.pad_value, p.pad_value);
-        else if (warped) {
-          x = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(src + static_cast<long long>(idx[q]) * D) + c);
-            x.x = fmaf(cw[q], v.x, x.x); x.y = fmaf(cw[q], v.y, x.y); x.z = fmaf(cw[q], v.z, x.z); x.w = fmaf(cw[q], v.w, x.w);
-          }
-        } else x = *(reinterpret_cast<const float4*>(src + t * D) + c);
-        float* xv = reinterpret_cast<float*>(&x);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float v = (xv[e] - mv[e]) * rv[e];
-          if (tmask || fv[e] != 0.f) v = fillv;
-          xv[e] = v;
-        }
-        if (dst16) *(reinterpret_cast<uint2*>(dst16 + t * D) + c) = bf16x4(x);
-        else *(reinterpret_cast<float4*>(dst + t * D) + c) = x;
-      } else {
+      {  // (scalar columns: feature widths that are not a multiple of four, or unaligned tensors)
         float v;
         if (is_pad) v = p.pad_value;
         else if (warped) {
