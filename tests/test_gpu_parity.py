@@ -737,6 +737,10 @@ def test_host_made_work_split_equals_the_kernels_own(skip_pad):
     assert torch.equal(a["stats"], b["stats"])
     assert torch.equal(a["mel"], b["mel"])
     # and the split really was the host's: lengths that disagree with the device's change what is computed
+    # (not under the A/B switches that take the host-made split or the tile kernel out of the picture)
+    import os
+    if os.environ.get("SFE_HOST_SPLIT") == "0" or os.environ.get("SFE_KERNEL", "").startswith("g"):
+        return
     wrong = host.copy()
     wrong[0] = 45000
     mel = torch.full((len(lens), F, 80), -7.0, device=DEV)
