@@ -69,5 +69,27 @@ def build(force: bool = False, verbose: bool = False, out: str = OUT) -> str:
     return out
 
 
+DRAW_DIR = os.path.join(HERE, "drawext")
+DRAW_NAME = "sfe_draw"
+
+
+def draw_ext_path() -> str:
+    return os.path.join(DRAW_DIR, DRAW_NAME + ".so")
+
+
+def build_draw_ext(force: bool = False) -> str:
+    """The host-side draw helper (sfe_draw.cpp: SpecAugment draws on torch's CPU generator in one call): a torch C++
+    extension, built in-tree with torch.utils.cpp_extension.  Optional — without it the module layer makes the same
+    draws with tensor ops."""
+    out, src = draw_ext_path(), os.path.join(HERE, "sfe_draw.cpp")
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+        return out
+    from torch.utils.cpp_extension import load
+    os.makedirs(DRAW_DIR, exist_ok=True)
+    load(name=DRAW_NAME, sources=[src], build_directory=DRAW_DIR, extra_cflags=["-O2"], verbose=False)
+    return out
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    build_draw_ext(force="--force" in sys.argv)

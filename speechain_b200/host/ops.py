@@ -135,6 +135,9 @@ class DeviceMasks:
             else:
                 self.views.append(None)
         assert sum(a.size for a in self._host) <= _lib.MASK_INLINE_MAX
+        # host addresses of (freq_pos, freq_len, time_pos, time_len), 0 where that kind of mask is off
+        it = iter(self._host)
+        self._addr = tuple(next(it).ctypes.data if n else 0 for n in (n_freq, n_freq, n_time, n_time))
         self._struct = None
         self._struct = self.struct()
         return self

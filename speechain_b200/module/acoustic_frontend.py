@@ -53,6 +53,11 @@ class AcousticFrontend(Module):
             self.specaug = SpecAugment(input_size=size, feat_norm=hasattr(self, "normalize"), **sconf)
         self.output_size = size
 
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d.pop("_fast", None)  # (looked-up submodules: rebuilt on the next call)
+        return d
+
     # ------------------------------------------------------------------------------------
     def forward(self, feat: torch.Tensor, feat_len: torch.Tensor, epoch: int = None, domain=None):
         """feat (batch, T, 1) or (batch, T) fp32 CUDA waveforms, feat_len (batch,) int64 (CPU or CUDA).

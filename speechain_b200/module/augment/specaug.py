@@ -15,6 +15,31 @@ from ...host.ops import DeviceMasks, HostLengths
 from ..abs import Module
 
 
+_DRAW = [False, None]  # [looked for, module]
+
+
+def _draw_helper():
+    """The optional host helper (csrc/sfe_draw.cpp, built by speechain_b200.csrc.build.build_draw_ext): the draws of a
+    step in one call on torch's default CPU generator.  None where it has not been built — the tensor-op path below
+    makes the same draws.  SFE_DRAW_HELPER=0 switches it off (A/B runs, tests of the tensor-op path)."""
+    if not _DRAW[0]:
+        _DRAW[0] = True
+        import os
+        if os.environ.get("SFE_DRAW_HELPER", "1") != "0":
+            try:
+                import importlib.util
+                from ...csrc import build as _b
+                path = _b.draw_ext_path()
+                if os.path.exists(path):
+                    spec = importlib.util.spec_from_file_location(_b.DRAW_NAME, path)
+                    mod = importlib.util.module_from_spec(spec)
+                    spec.loader.exec_module(mod)
+                    _DRAW[1] = mod
+            except Exception:  # noqa: BLE001  (host glue only: fall back to the tensor-op draws)
+                _DRAW[1] = None
+    return _DRAW[1]
+
+
 class SpecAugment(Module):
     def module_init(self, time_warp: bool = True, time_warp_window: int = 5, time_warp_mode: str = "bicubic",
                     freq_mask: bool = True, freq_mask_width: Union[int, List[int]] = 30, freq_mask_num: int = 2,
@@ -51,6 +76,13 @@ class SpecAugment(Module):
         self.time_mask_width = list(time_mask_width)
         self.time_mask_num = time_mask_num
         self.feat_norm = feat_norm
+
+    def __getstate__(self):
+        # the persistent descriptor arrays hold raw host addresses: never pickle / deepcopy them
+        d = self.__dict__.copy()
+        d.pop("_mask_cache", None)
+        d.pop("_warp_draw", None)
+        return d
 
     # ------------------------------------------------------------------------------------
     def draw(self, batch_size: int, feat_dim: int, time_minlen: int, generator: Optional[torch.Generator] = None):
@@ -111,6 +143,29 @@ class SpecAugment(Module):
         if masks is None:
             masks = cache[batch_size] = DeviceMasks.persistent(batch_size, nf, nt)
         masks.fill, masks.fill_dev = 0.0, None
+        if nf and self.feat_dim is None:
+            # latent bug of specaug.py:135-141, kept as the same error: feat_dim is never set lazily
+            assert self.feat_dim == feat_dim and self.freq_mask_width[1] < feat_dim, (
+                "The number of maximum frequency masking bins cannot be larger than the feature dimension! "
+                f"self.freq_mask_width[1]={self.freq_mask_width[1]} and feat_dim={feat_dim}.")
+        lo = hi = 0
+        if nt:
+            lo, hi = self.time_mask_width
+            if isinstance(lo, float):
+                lo = int(lo * minlen)
+            if isinstance(hi, float):
+                hi = int(hi * minlen)
+            hi = min(hi, minlen)
+        helper = _draw_helper()
+        if helper is not None:
+            # every draw of this step in ONE call on the same generator (csrc/sfe_draw.cpp)
+            ptr = masks._addr
+            center, pos = helper.specaug_draw(
+                batch_size, feat_dim, minlen, self.time_warp_window if self.time_warp else -1,
+                nf, self.freq_mask_width[0] if nf else 0, self.freq_mask_width[1] if nf else 0, ptr[0], ptr[1],
+                nt, lo, hi, ptr[2], ptr[3])
+            warp = (center, pos, minlen, 2 if self.time_warp_mode == "bilinear" else 1) if center >= 0 else None
+            return warp, masks
         warp = None
         if self.time_warp and minlen > 2 * self.time_warp_window + 1:
             # (the two scalar draws of specaug.py:98-108 — randint(size=(1,)) — in place on a persistent tensor)
@@ -123,20 +178,9 @@ class SpecAugment(Module):
             warp = (center, pos, minlen, 2 if self.time_warp_mode == "bilinear" else 1)
         t_fpos, t_flen, t_tpos, t_tlen = masks.views
         if nf:
-            if self.feat_dim is None:
-                # latent bug of specaug.py:135-141, kept as the same error: feat_dim is never set lazily
-                assert self.feat_dim == feat_dim and self.freq_mask_width[1] < feat_dim, (
-                    "The number of maximum frequency masking bins cannot be larger than the feature dimension! "
-                    f"self.freq_mask_width[1]={self.freq_mask_width[1]} and feat_dim={feat_dim}.")
             t_flen.random_(self.freq_mask_width[0], self.freq_mask_width[1] + 1)
             t_fpos.random_(0, max(1, feat_dim - int(masks._host[1].max())))
         if nt:
-            lo, hi = self.time_mask_width
-            if isinstance(lo, float):
-                lo = int(lo * minlen)
-            if isinstance(hi, float):
-                hi = int(hi * minlen)
-            hi = min(hi, minlen)
             t_tlen.random_(lo, hi + 1)
             t_tpos.random_(0, max(1, minlen - int(masks._host[-1].max())))
         return warp, masks

@@ -167,13 +167,22 @@ def test_upload_row_groups_bound_the_padding():
     assert valid <= ops.upload_bytes(lens) <= valid * 24 // 23 + 4
 
 
-def test_lean_draw_path_equals_reference_draw_sequence():
-    """draw_device's persistent-buffer path (int32 ``out=`` draws) consumes the CPU generator exactly like ``draw``
-    (the reference's call sequence): same warp, same intervals, step after step, for several configurations."""
+@pytest.mark.parametrize("helper", [False, True])
+def test_lean_draw_path_equals_reference_draw_sequence(helper, monkeypatch):
+    """draw_device's persistent-buffer path consumes the CPU generator exactly like ``draw`` (the reference's call
+    sequence): same warp, same intervals, step after step, for several configurations — with the tensor-op draws
+    (``Tensor.random_`` in place) and with the one-call helper (csrc/sfe_draw.cpp) where it is built."""
     import numpy as np
     import torch
 
+    from speechain_b200.module.augment import specaug as SA
     from speechain_b200.module.augment.specaug import SpecAugment
+    if helper:
+        monkeypatch.setattr(SA, "_DRAW", [False, None])
+        if SA._draw_helper() is None:
+            pytest.skip("draw helper not built")
+    else:
+        monkeypatch.setattr(SA, "_DRAW", [True, None])
     for conf in (dict(time_warp=False, freq_mask_width=30, freq_mask_num=2, time_mask_width=0.05, time_mask_num=2),
                  dict(time_warp=True, freq_mask_width=15, freq_mask_num=4, time_mask_width=20, time_mask_num=4),
                  dict(time_warp=True, freq_mask=False, time_mask_width=[2, 0.1], time_mask_num=3),
@@ -230,3 +239,44 @@ def test_host_length_cache_dies_with_its_tensor():
     # real tensors: the copy rides on the object
     t = torch.tensor([3, 2, 1])
     assert HostLengths.get(t).tolist() == [3, 2, 1]
+
+
+def test_draw_helper_makes_the_reference_draw_sequence():
+    """csrc/sfe_draw.cpp draws every mask of a step in one call on torch's default CPU generator: same values, same
+    generator state afterwards as the reference's torch.randint sequence (specaug.py:98-108,145-158,178-191) —
+    for the recipe block (time warp on), with and without each kind of mask, float and integer widths."""
+    import copy
+    from speechain_b200.csrc import build as B
+    from speechain_b200.module.augment import specaug as SA
+    try:
+        B.build_draw_ext()
+    except Exception as e:  # noqa: BLE001
+        pytest.skip(f"draw helper cannot be built here: {e}")
+    SA._DRAW[0], SA._DRAW[1] = False, None
+    assert SA._draw_helper() is not None
+    confs = [dict(freq_mask_width=15, freq_mask_num=4, time_mask_width=0.05, time_mask_num=5),
+             dict(time_warp=False, freq_mask_width=30, freq_mask_num=2, time_mask_width=0.05, time_mask_num=2),
+             dict(time_warp=True, freq_mask=False, time_mask_width=[3, 20], time_mask_num=3, time_warp_window=8),
+             dict(time_warp=False, time_mask=False, freq_mask_width=[2, 9], freq_mask_num=1),
+             dict(time_warp=True, freq_mask=False, time_mask=False)]
+    rng = np.random.default_rng(3)
+    for conf in confs:
+        a = SA.SpecAugment(input_size=80, **conf)
+        b = copy.deepcopy(a)  # (before the first draw: no persistent arrays yet)
+        for step in range(4):
+            fl = rng.integers(12 if step == 3 else 40, 400, size=16)
+            torch.manual_seed(100 + step)
+            w1, fpos, flen, tpos, tlen = a.draw(16, 80, int(fl.min()))
+            s1 = torch.get_rng_state()
+            torch.manual_seed(100 + step)
+            w2, m = b.draw_device(16, 80, fl, "cpu")
+            s2 = torch.get_rng_state()
+            assert torch.equal(s1, s2), "the generator must be left where the reference leaves it"
+            assert (w1 is None) == (w2 is None) and (w1 is None or tuple(w1[:3]) == tuple(w2[:3]))
+            got = iter(m._host) if m is not None else iter(())
+            for ref in (fpos, flen, tpos, tlen):
+                if ref is not None:
+                    assert np.array_equal(next(got), ref)
+    # a pickled / deep-copied module starts with fresh descriptor arrays (they hold raw host addresses)
+    c = copy.deepcopy(b)
+    assert "_mask_cache" not in c.__dict__
