@@ -797,3 +797,27 @@ def test_recipe_specaug_on_a_batch_beyond_the_inline_descriptor_block():
     mask = O.specaug_mask(*got.shape, d)
     assert (got[mask] == 0.0).all() and np.count_nonzero((got == 0.0) & ~mask) <= 2
     assert_close(got, ref, what="recipe SpecAugment, B = 150")
+
+
+def test_time_warp_over_more_rows_than_shared_memory_stages():
+    """The in-place warp stages rows [0, minlen) of a CTA's Mel bins in shared memory; where minlen rows do not fit
+    (here: > 12 800 frames, two utterances of over two minutes) the chain falls back to one out-of-place gather pass
+    over the whole tensor.  Same result either way."""
+    lens = [2_100_000, 2_090_000]
+    wav = _wave(91, lens, zero_seg=False)
+    conf = dict(n_mels=80, n_fft=512, win_length=0.025, hop_length=0.010, sr=16000, preemphasis=0.97)
+    sconf = dict(freq_mask_width=15, freq_mask_num=4, time_mask_width=0.05, time_mask_num=5)
+    chain = AcousticFrontend(frontend=dict(conf=conf), normalize=dict(norm_type="utterance"), specaug=sconf).to(DEV)
+    chain.train()
+    torch.manual_seed(17)
+    y, yl = chain(wav.to(DEV)[..., None], torch.tensor(lens, device=DEV))
+    feat, flen, _ = O.speech2mel(wav.numpy().astype(np.float64), lens, O.FrontendCfg(**conf))
+    assert int(flen.min()) * 16 > 200 * 1024
+    ref = O.feat_norm_utterance(feat, flen)
+    d = O.specaug_draw(O.TorchCpuRandint(17), len(lens), 80, flen, O.SpecAugCfg(**sconf))
+    assert d.warp is not None
+    ref = O.specaug_apply(ref, flen, d, feat_norm=True)
+    got = y.cpu().numpy()
+    mask = O.specaug_mask(*got.shape, d)
+    assert (got[mask] == 0.0).all()
+    assert_close(got, ref, what="warp fallback (long utterances)")
