@@ -821,3 +821,41 @@ def test_time_warp_over_more_rows_than_shared_memory_stages():
     mask = O.specaug_mask(*got.shape, d)
     assert (got[mask] == 0.0).all()
     assert_close(got, ref, what="warp fallback (long utterances)")
+
+
+def test_fresh_cuda_length_tensor_every_step_never_sees_the_previous_batch():
+    """What the real caller does (model/abs.py:329-352): a NEW CUDA length tensor with other contents every step, the
+    old one freed in between — so that the allocator hands out the same block and CPython the same id().  The host
+    copy of the lengths rides on the tensor object and dies with it: mask bounds, frame counts and the host-made work
+    split of every step must be those of THAT step's lengths (checked against the oracle step by step)."""
+    conf = dict(n_mels=80, n_fft=512, win_length=0.025, hop_length=0.010, sr=16000, preemphasis=0.97)
+    sconf = dict(time_warp=False, freq_mask_width=30, freq_mask_num=2, time_mask_width=0.05, time_mask_num=2)
+    chain = AcousticFrontend(frontend=dict(conf=conf), normalize=dict(norm_type="utterance"), specaug=sconf).to(DEV)
+    chain.train()
+    cfg = O.FrontendCfg(**conf)
+    g = torch.Generator().manual_seed(5150)
+    T = 40000
+    wav = 0.1 * torch.randn(6, T, generator=g)
+    x = wav.to(DEV)[..., None]
+    ptrs = set()
+    for step in range(6):
+        lens = torch.randint(4000, T + 1, (6,), generator=g).tolist()
+        lens[step % 6] = T
+        xl = torch.tensor(lens, dtype=torch.int64).to(DEV)   # fresh device tensor, no host copy remembered
+        ptrs.add(xl.data_ptr())
+        torch.manual_seed(900 + step)
+        y, yl = chain(x, xl)
+        w = wav.clone().numpy().astype(np.float64)
+        for i, n in enumerate(lens):
+            w[i, n:] = 0.0
+        feat, flen, _ = O.speech2mel(w, lens, cfg)
+        ref = O.feat_norm_utterance(feat, flen)
+        d = O.specaug_draw(O.TorchCpuRandint(900 + step), 6, 80, flen, O.SpecAugCfg(**sconf))
+        ref = O.specaug_apply(ref, flen, d, feat_norm=True)
+        got = y.cpu().numpy()
+        assert np.array_equal(yl.cpu().numpy(), flen), f"step {step}: frame counts"
+        mask = O.specaug_mask(*got.shape, d)
+        assert (got[mask] == 0.0).all() and np.count_nonzero((got == 0.0) & ~mask) <= 2, f"step {step}: mask pattern"
+        assert_close(got, ref, what=f"step {step}")
+        del xl, y, yl
+    assert len(ptrs) < 6, "the allocator was expected to reuse the length tensor's block (the stale-cache scenario)"
