@@ -253,6 +253,15 @@ int64_t sfe_upload_i16_stage_bytes(int32_t B, int64_t T);
 int sfe_upload_waveforms_i16(const int16_t* wav_host, int64_t host_pitch, const int64_t* len_host, int32_t B,
                              void* stage_dev, int64_t stage_bytes, float* wav_dev, int64_t dev_pitch, void* stream);
 
+/* Speech2LinearSpec with onesided=False (speech2linear.py:20-37,197-246: torch.stft returns all n_fft bins): `power`
+ * (B, F, n_fft/2+1) is the un-logged POWER spectrogram of sfe_frontend_forward (a plan without mag_spec / lin_logging;
+ * rows at or past feat_len are zero); `out` (B, F, n_fft) receives its mirror image |X[n_fft-k]| = |X[k]| after the
+ * reference's point-wise tail (sqrt for mag_spec, clamp + log / log_div), `energy` (B, F) or NULL the frame energy
+ * sqrt(max(sum over ALL n_fft bins, 1e-10)), zero at or past feat_len. */
+int sfe_twosided(const float* power, const int64_t* feat_len, int32_t B, int64_t F, int32_t K, int32_t n_fft,
+                 int32_t mag_spec, int32_t logging, float clamp, float log_div, float* out, float* energy,
+                 void* stream);
+
 /* DeltaFeature.forward (delta_feat.py:57-81): (B, F, D) -> (B, F, D*(order+1)). */
 int sfe_delta(const float* feat, int32_t B, int64_t F, int32_t D, int32_t order, int32_t N,
               float* out, void* stream);

@@ -59,6 +59,7 @@ class FrontendCfg:
     window: str = "hann"
     center: bool = True
     normalized: bool = False
+    onesided: bool = True
     mag_spec: bool = False
     return_energy: bool = False
     # linear-stage log (Speech2LinearSpec standalone)
@@ -181,6 +182,11 @@ def speech2linear(wav: np.ndarray, lens: Sequence[int], cfg: FrontendCfg):
     if cfg.pre_stft_norm is not None:
         wav = pre_stft_norm(wav, cfg.pre_stft_norm)
     spec = stft_power(wav, cfg)
+    if not cfg.onesided:
+        # torch.stft(onesided=False) returns all n_fft bins; for a real signal X[n_fft - k] = conj(X[k]), so the power
+        # of bins K .. n_fft-1 mirrors bins K-2 .. 1 (odd n_fft: K-1 .. 1).  speech2linear.py:197-198
+        K = spec.shape[-1]
+        spec = np.concatenate([spec, spec[..., cfg.n_fft - K:0:-1]], axis=-1)
     flen = feat_lengths(lens, cfg.n_fft, cfg.hop_length, cfg.center)
     energy = None
     if cfg.return_energy:

@@ -71,6 +71,7 @@ SYMBOLS = {
     "sfe_upload_bytes": (C.c_int64, [_vp, _i32]),
     "sfe_upload_i16_stage_bytes": (C.c_int64, [_i32, _i64]),
     "sfe_upload_waveforms_i16": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _i64, _vp, _i64, _vp]),
+    "sfe_twosided": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp]),
     "sfe_delta": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _i32, _vp, _vp]),
     "sfe_mean_all": (C.c_int, [_vp, _i64, _vp, _vp]),
     "sfe_mel2linear": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _i32, _f32, _i64, _f32, _vp, _vp]),

@@ -497,6 +497,37 @@ __global__ void __launch_bounds__(256, WARP ? SFE_NORM_MINB - 1 : SFE_NORM_MINB)
 }
 
 // ---------------------------------------------------------------------------------------------
+// two-sided linear spectrogram (torch.stft(onesided=False), speech2linear.py:197-246): the one-sided POWER spectrum
+// of the frontend kernel mirrored to n_fft bins (|X[n_fft - k]| = |X[k]| for a real signal), the frame energy over
+// all n_fft bins, then the reference's point-wise tail (sqrt for mag_spec, clamp + log) — rows at or past feat_len
+// hold zero power already, which is what the reference feeds to that tail.  One warp per row.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) twosided_kernel(const float* __restrict__ power, const long long* __restrict__ flen,
+                                                       long long rows, long long F, int K, int n_fft, int mag, int logging,
+                                                       float clampv, float lmul, float* __restrict__ out,
+                                                       float* __restrict__ energy) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  for (long long r = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
+    const float* src = power + r * K;
+    float* dst = out + r * n_fft;
+    float sum = 0.f;
+    for (int k = lane; k < n_fft; k += 32) {
+      float x = src[k < K ? k : n_fft - k];
+      sum += x;
+      if (mag) x = sqrtf(x);
+      if (logging) x = fast_log(x, clampv, lmul);
+      dst[k] = x;
+    }
+    if (energy) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == 0) energy[r] = ((r % F) < flen[r / F]) ? sqrtf(fmaxf(sum, 1e-10f)) : 0.f;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // delta / delta-delta                                                      delta_feat.py:57-81
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) delta_kernel(const float* __restrict__ x, int B, long long F, int D, int order,

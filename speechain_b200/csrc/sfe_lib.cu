@@ -1171,6 +1171,22 @@ extern "C" int sfe_delta(const float* feat, int32_t B, int64_t F, int32_t D, int
   return SFE_OK;
 }
 
+extern "C" int sfe_twosided(const float* power, const int64_t* feat_len, int32_t B, int64_t F, int32_t K, int32_t n_fft,
+                            int32_t mag_spec, int32_t logging, float clamp, float log_div, float* out, float* energy,
+                            void* stream) {
+  if (!power || !feat_len || !out) return fail(SFE_ERR_BAD_ARG, "sfe_twosided: NULL argument");
+  if (B <= 0 || F <= 0 || n_fft < 2 || K != n_fft / 2 + 1) return fail(SFE_ERR_BAD_ARG, "sfe_twosided: bad shape");
+  if (logging && !(clamp >= 1.17549435e-38f)) return fail(SFE_ERR_BAD_ARG, "sfe_twosided: clamp must be a normal positive number");
+  const long long rows = static_cast<long long>(B) * F;
+  long long blocks = (rows + 7) / 8;
+  if (blocks > cached_sm_count() * 16LL) blocks = cached_sm_count() * 16LL;
+  twosided_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      power, reinterpret_cast<const long long*>(feat_len), rows, F, K, n_fft, mag_spec, logging, clamp,
+      0.69314718055994530942f / log_div, out, energy);
+  SFE_CUDA(cudaGetLastError());
+  return SFE_OK;
+}
+
 // scratch accumulator for sfe_mean_all lives with the library (one word per device context)
 extern "C" int sfe_mean_all(const float* x, int64_t n, float* out, void* stream) {
   if (!x || !out || n <= 0) return fail(SFE_ERR_BAD_ARG, "sfe_mean_all: bad argument");

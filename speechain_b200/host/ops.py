@@ -445,6 +445,22 @@ def prestft_norm(wav: torch.Tensor, wav_len: torch.Tensor, *, preemphasis: Optio
     return out
 
 
+def twosided(power: torch.Tensor, feat_len: torch.Tensor, n_fft: int, *, mag_spec: bool, logging: bool, clamp: float,
+             log_base: Optional[float], want_energy: bool):
+    """One-sided power spectrogram (B, F, n_fft//2+1) -> (two-sided spectrogram (B, F, n_fft) after the reference's
+    point-wise tail, frame energy (B, F) over all n_fft bins or None); see sfe_twosided."""
+    _need_cuda(power, "feat")
+    power = power.contiguous()
+    B, F, K = power.shape
+    out = torch.empty((B, F, n_fft), dtype=torch.float32, device=power.device)
+    energy = torch.empty((B, F), dtype=torch.float32, device=power.device) if want_energy else None
+    with _on_device(power.device):
+        _lib.check(_lib.load().sfe_twosided(_ptr(power), _ptr(feat_len), B, F, K, int(n_fft), int(mag_spec), int(logging),
+                                            float(clamp), float(math.log(log_base)) if log_base is not None else 1.0,
+                                            _ptr(out), _ptr(energy), _stream()))
+    return out, energy
+
+
 def delta(feat: torch.Tensor, order: int, N: int) -> torch.Tensor:
     _need_cuda(feat, "feat")
     feat = feat.contiguous()

@@ -27,12 +27,11 @@ class Speech2LinearSpec(Module):
         win_length = to_samples(win_length, sr)
         if n_fft is None:
             n_fft = win_length  # speech2linear.py:93-94
-        if not onesided:
-            raise NotImplementedError("onesided=False is not supported by the B200 frontend (no recipe uses it; "
-                                      "LinearSpec2MelSpec needs n_fft//2+1 bins anyway).")
         if pre_stft_norm not in (None, "mean_std", "min_max"):
             raise ValueError(f"pre_stft_norm must be None, 'mean_std' or 'min_max', got {pre_stft_norm!r}")
-        self.output_size = n_fft // 2 + 1
+        # (two-sided: all n_fft bins of torch.stft(onesided=False); LinearSpec2MelSpec cannot consume those)
+        self.onesided = bool(onesided)
+        self.output_size = n_fft // 2 + 1 if onesided else n_fft
         self.win_length, self.hop_length, self.n_fft, self.sr = win_length, hop_length, n_fft, sr
         self.preemphasis = as_float(preemphasis, "preemphasis")
         if self.preemphasis is not None:
@@ -48,17 +47,18 @@ class Speech2LinearSpec(Module):
         self._plans = {}
 
     # ------------------------------------------------------------------------------------
-    def _plan(self, device, preemph: bool = True, mel: Optional[dict] = None, plain_window: bool = False) -> FrontendPlan:
+    def _plan(self, device, preemph: bool = True, mel: Optional[dict] = None, plain_window: bool = False,
+              raw_power: bool = False) -> FrontendPlan:
         # (a checkpoint load copies into the filterbank buffer in place: the version counter catches that)
-        key = (device, preemph, None if mel is None else (id(mel["weight"]), mel["weight"]._version), plain_window)
+        key = (device, preemph, None if mel is None else (id(mel["weight"]), mel["weight"]._version), plain_window, raw_power)
         plan = self._plans.get(key)
         if plan is None:
             c = self.stft_config
             # (Griffin-Lim in the reference always runs un-normalised STFTs, whatever `normalized` says)
             win = make_window(c["window"], self.win_length, self.n_fft, c["normalized"] and not plain_window)
             kw = dict(n_fft=self.n_fft, win_length=self.win_length, hop_length=self.hop_length, center=c["center"],
-                      preemphasis=self.preemphasis if preemph else None, mag_spec=self.mag_spec,
-                      lin_logging=self.logging, lin_clamp=self.clamp, lin_log_base=self.log_base, window=win,
+                      preemphasis=self.preemphasis if preemph else None, mag_spec=self.mag_spec and not raw_power,
+                      lin_logging=self.logging and not raw_power, lin_clamp=self.clamp, lin_log_base=self.log_base, window=win,
                       device=device)
             if mel is not None:
                 kw.update(n_mels=mel["n_mels"], mel_logging=mel["logging"], mel_clamp=mel["clamp"],
@@ -91,7 +91,7 @@ class Speech2LinearSpec(Module):
         samples beyond a length as zero.)"""
         return len_dev if in_kernel else torch.full_like(len_dev, wav.size(1))
 
-    def _fix_padded_rows(self, out, len_dev, in_kernel, plan):
+    def _fix_padded_rows(self, out, len_dev, in_kernel, plan, raw_power: bool = False):
         """Rare pre_stft_norm path: the kernel ran with full-row lengths, so rows t >= feat_len still hold
         spectra of the padding; reset them like speech2linear.py:226-233 / linear2mel.py:177-187 do."""
         if in_kernel:
@@ -103,7 +103,7 @@ class Speech2LinearSpec(Module):
         if out.get("lin") is not None:
             import math
             pad_lin = 0.0
-            if self.logging:
+            if self.logging and not raw_power:
                 pad_lin = math.log(self.clamp) / (math.log(self.log_base) if self.log_base is not None else 1.0)
             ops.normalize(out["lin"], feat_len, use_mean=False, use_std=False, src_has_pad=False, pad_value=pad_lin)
         if out.get("energy") is not None:
@@ -133,12 +133,19 @@ class Speech2LinearSpec(Module):
         Returns (linear_spec (batch, F, n_fft//2+1), feat_len) or, with ``return_energy``,
         (linear_spec, feat_len, energy (batch, F), energy_len)."""
         wav, len_dev, len_host, in_kernel = self._prepare(speech, speech_len)
-        plan = self._plan(wav.device, preemph=in_kernel)
+        two = not getattr(self, "onesided", True)
+        # (two-sided: the kernel delivers the plain power spectrum, one more pass mirrors it, sums the energy over all
+        #  n_fft bins and applies the point-wise tail)
+        plan = self._plan(wav.device, preemph=in_kernel, raw_power=two)
         out = plan.forward(wav, self._kernel_lengths(wav, len_dev, in_kernel), want_mel=False, want_lin=True,
-                           want_energy=self.return_energy)
-        self._fix_padded_rows(out, len_dev, in_kernel, plan)
+                           want_energy=self.return_energy and not two)
+        self._fix_padded_rows(out, len_dev, in_kernel, plan, raw_power=two)
         feat_len = out["feat_len"]
         HostLengths.remember(feat_len, self._feat_len_host(len_host))
+        if two:
+            out["lin"], out["energy"] = ops.twosided(out["lin"], feat_len, self.n_fft, mag_spec=self.mag_spec,
+                                                     logging=self.logging, clamp=self.clamp, log_base=self.log_base,
+                                                     want_energy=self.return_energy)
         if self.return_energy:
             return out["lin"], feat_len, out["energy"], feat_len
         return out["lin"], feat_len
@@ -157,6 +164,9 @@ class Speech2LinearSpec(Module):
             raise RuntimeError("speechain_b200 frontend: `feat` must be a CUDA tensor — there is no CPU path.")
         assert self.pre_stft_norm is None, "waveform pre-stft normalization cannot be recovered for TTS synthesis."
         B, F, K = feat.shape
+        if K != self.n_fft // 2 + 1:
+            raise ValueError(f"recover() needs the one-sided spectrogram (n_fft // 2 + 1 = {self.n_fft // 2 + 1} bins), "
+                             f"got {K} (torchaudio's GriffinLim rejects it the same way)")
         len_host = HostLengths.get(feat_len)
         assert int(len_host.max()) == F, "Something wrong happens when calculating the length of synthetic utterances."
         len_dev = feat_len if feat_len.is_cuda else feat_len.to(feat.device, non_blocking=True)

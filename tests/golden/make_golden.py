@@ -150,7 +150,11 @@ def main():
     wav, wl = make_wave(1250, [7000, 4100, 2000])
     for nm, conf in [("lin_mag_log", dict(sr=22050, win_length=1024, hop_length=256, mag_spec=True, logging=True, clamp=1e-5)),
                      ("lin_pow", dict(sr=16000, win_length=400, hop_length=160, n_fft=512, return_energy=True)),
-                     ("lin_pow_log10", dict(sr=16000, win_length=400, hop_length=160, preemphasis=0.97, logging=True, log_base=10.0))]:
+                     ("lin_pow_log10", dict(sr=16000, win_length=400, hop_length=160, preemphasis=0.97, logging=True, log_base=10.0)),
+                     # all n_fft bins (torch.stft(onesided=False)); the energy then sums the mirrored half too
+                     ("lin_twosided", dict(sr=16000, win_length=400, hop_length=160, n_fft=512, onesided=False, return_energy=True)),
+                     ("lin_twosided_mag_log", dict(sr=16000, win_length=400, hop_length=160, onesided=False, mag_spec=True,
+                                                   logging=True, clamp=1e-5, return_energy=True))]:
         m = Speech2LinearSpec(**conf)
         out = m(wav.clone(), wl.clone())
         extra = dict(energy=out[2]) if len(out) == 4 else {}

@@ -76,6 +76,9 @@ def test_speech2mel_2d_input_and_unaligned_view(name):
     ("lin_mag_log", dict(sr=22050, win_length=1024, hop_length=256, mag_spec=True, logging=True, clamp=1e-5)),
     ("lin_pow", dict(sr=16000, win_length=400, hop_length=160, n_fft=512, return_energy=True)),
     ("lin_pow_log10", dict(sr=16000, win_length=400, hop_length=160, preemphasis=0.97, logging=True, log_base=10.0)),
+    ("lin_twosided", dict(sr=16000, win_length=400, hop_length=160, n_fft=512, onesided=False, return_energy=True)),
+    ("lin_twosided_mag_log", dict(sr=16000, win_length=400, hop_length=160, onesided=False, mag_spec=True, logging=True,
+                                  clamp=1e-5, return_energy=True)),
 ])
 def test_speech2linear_golden(name, conf):
     g = load_golden(name)
@@ -87,13 +90,35 @@ def test_speech2linear_golden(name, conf):
         # single bins at the fp32 noise floor: compare in the power domain (see test_oracle_golden.py)
         p, pref = 10.0 ** spec.astype(np.float64), 10.0 ** g["spec"].astype(np.float64)
         assert_close(p, pref, rtol=1e-4, atol=1e-6 * pref.max(), what=name)
-    elif name == "lin_mag_log":
+    elif name in ("lin_mag_log", "lin_twosided_mag_log"):
         p, pref = np.exp(spec.astype(np.float64)), np.exp(g["spec"].astype(np.float64))
         assert_close(p, pref, rtol=1e-4, atol=1e-5 * pref.max(), what=name)
     else:
         assert_close(spec, g["spec"], what=name)
     if "energy" in g:
         assert_close(out[2].cpu().numpy(), g["energy"], what=name + " energy")
+
+
+def test_twosided_spectrogram_with_waveform_normalisation_and_no_recovery():
+    """onesided=False on the rare pre_stft_norm path against the oracle, and recover() refusing all-n_fft-bin input."""
+    conf = dict(sr=16000, win_length=400, hop_length=160, n_fft=512, onesided=False, return_energy=True, logging=True,
+                pre_stft_norm="min_max")
+    g = torch.Generator().manual_seed(77)
+    lens = np.array([4000, 2600, 900])
+    wav = torch.randn(3, 4000, generator=g) * 0.1
+    for i, n in enumerate(lens):
+        wav[i, n:] = 0
+    m = Speech2LinearSpec(**conf).to(DEV)
+    spec, flen, energy, _ = m(wav.to(DEV)[..., None], cu(lens))
+    cfg = O.FrontendCfg(sr=16000, win_length=400, hop_length=160, n_fft=512, onesided=False, return_energy=True,
+                        lin_logging=True, pre_stft_norm="min_max")
+    ref, rlen, renergy = O.speech2linear(wav.numpy().astype(np.float64), lens, cfg)
+    assert spec.shape[-1] == 512 and np.array_equal(flen.cpu().numpy(), rlen)
+    p, pref = np.exp(spec.cpu().numpy().astype(np.float64)), np.exp(ref)
+    assert_close(p, pref, rtol=1e-4, atol=1e-6 * pref.max(), what="two-sided prenorm")
+    assert_close(energy.cpu().numpy(), renergy, what="two-sided prenorm energy")
+    with pytest.raises(ValueError):
+        Speech2LinearSpec(sr=16000, win_length=400, hop_length=160, n_fft=512, onesided=False).to(DEV).recover(spec, flen)
 
 
 def test_linear2mel_golden():

@@ -64,6 +64,9 @@ def test_mel_filterbank(name):
     ("lin_mag_log", dict(sr=22050, win_length=1024, hop_length=256, mag_spec=True, lin_logging=True, lin_clamp=1e-5)),
     ("lin_pow", dict(sr=16000, win_length=400, hop_length=160, n_fft=512, return_energy=True)),
     ("lin_pow_log10", dict(sr=16000, win_length=400, hop_length=160, preemphasis=0.97, lin_logging=True, lin_log_base=10.0)),
+    ("lin_twosided", dict(sr=16000, win_length=400, hop_length=160, n_fft=512, onesided=False, return_energy=True)),
+    ("lin_twosided_mag_log", dict(sr=16000, win_length=400, hop_length=160, onesided=False, mag_spec=True, lin_logging=True,
+                                  lin_clamp=1e-5, return_energy=True)),
 ])
 def test_speech2linear(name, cfg):
     g = load_golden(name)
@@ -75,6 +78,10 @@ def test_speech2linear(name, cfg):
         # 2.4e-3 away from fp64 there).  Compare in the power domain against the frame's scale.
         p, pref = 10.0 ** spec, 10.0 ** g["spec"].astype(np.float64)
         assert_close(p, pref, rtol=1e-4, atol=1e-6 * pref.max(), what=name)
+    elif name == "lin_twosided_mag_log":
+        assert spec.shape[-1] == 400
+        p, pref = np.exp(spec), np.exp(g["spec"].astype(np.float64))
+        assert_close(p, pref, rtol=1e-4, atol=1e-5 * pref.max(), what=name)
     else:
         # power spectra of 0.1*randn reach ~1e2: compare with the north-star tolerance
         assert_close(spec, g["spec"], what=name)
