@@ -11,8 +11,7 @@ import sys
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-HEADERS = ["sfe_fft.cuh", "sfe_fused.cuh", "sfe_aux.cuh", "sfe_gl.cuh", "sfe_registry.h",
-           os.path.join("..", "..", "include", "sfe.h")]
+HEADERS = sorted(f for f in os.listdir(HERE) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "sfe.h")]
 SOURCES = ["sfe_lib.cu", "sfe_plans.cu"]
 OUT = os.path.join(HERE, "libsfe.so")
 OBJ = os.path.join(HERE, "build")

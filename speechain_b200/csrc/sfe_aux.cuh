@@ -287,6 +287,26 @@ __global__ void __launch_bounds__(256, WARP ? SFE_NORM_MINB - 1 : SFE_NORM_MINB)
   // this utterance's time-mask intervals [lo, hi) -> shared memory (n_tmask <= 64)
   __shared__ int s_tlo[64], s_thi[64];
   __shared__ int2 s_tiv[64];  // {first frame, length}: one unsigned compare per interval in the streaming loop
+  // the same intervals as one bit per row of this CTA's slice of the time axis: the streaming loop tests a bit instead
+  // of walking the intervals (slices longer than 32 * NORM_TB_WORDS rows walk them)
+  constexpr int NORM_TB_WORDS = 128;
+  __shared__ unsigned s_tbits[NORM_TB_WORDS];
+  const int t0i = static_cast<int>(blockIdx.x) * static_cast<int>(p.frames_per_cta);
+  const bool tb_on = p.frames_per_cta <= 32 * NORM_TB_WORDS;
+  auto fill_bits = [&](const int* tpos, const int* tlen) {
+    if (!tb_on) return;
+    const int nw = (static_cast<int>(p.frames_per_cta) + 31) >> 5;
+    for (int w = threadIdx.x; w < nw; w += blockDim.x) {
+      unsigned bits = 0u;
+      const int base = t0i + 32 * w;
+      for (int q = 0; q < n_tmask; ++q) {
+        const int ps = tpos[b * n_tmask + q], ln = tlen[b * n_tmask + q];
+        const int lo = max(ps - base, 0), hi = min(ps + ln - base, 32);
+        if (hi > lo) bits |= (hi - lo >= 32 ? 0xffffffffu : ((1u << (hi - lo)) - 1u)) << lo;
+      }
+      s_tbits[w] = bits;
+    }
+  };
   if (p.mk.inl_on) {
     // descriptors that travel in the parameter block need nothing from the previous kernel: before the wait
     const int* m_fpos = p.mk.inl;
@@ -307,6 +327,7 @@ __global__ void __launch_bounds__(256, WARP ? SFE_NORM_MINB - 1 : SFE_NORM_MINB)
       s_thi[q] = ps + m_tlen[b * n_tmask + q];
       s_tiv[q] = make_int2(ps, max(m_tlen[b * n_tmask + q], 0));
     }
+    fill_bits(m_tpos, m_tlen);
   }
   pdl_wait();
   const long long n_valid = min(p.flen[b], p.F);
@@ -348,6 +369,7 @@ __global__ void __launch_bounds__(256, WARP ? SFE_NORM_MINB - 1 : SFE_NORM_MINB)
       s_thi[q] = ps + p.mk.tlen[b * n_tmask + q];
       s_tiv[q] = make_int2(ps, max(p.mk.tlen[b * n_tmask + q], 0));
     }
+    fill_bits(p.mk.tpos, p.mk.tlen);
   }
   __syncthreads();
   const float fillv = p.fill_dev ? *p.fill_dev : p.fill;
@@ -383,9 +405,14 @@ __global__ void __launch_bounds__(256, WARP ? SFE_NORM_MINB - 1 : SFE_NORM_MINB)
       float4* dp = reinterpret_cast<float4*>(dst) + c;
       auto finish = [&](int t, float4 x) {
         bool tmask = false;
-        for (int q = 0; q < n_tmask; ++q) {
-          const int2 iv = s_tiv[q];
-          tmask |= static_cast<unsigned>(t - iv.x) < static_cast<unsigned>(iv.y);
+        if (tb_on) {
+          const int r = t - t0i;
+          tmask = ((s_tbits[r >> 5] >> (r & 31)) & 1u) != 0u;
+        } else {
+          for (int q = 0; q < n_tmask; ++q) {
+            const int2 iv = s_tiv[q];
+            tmask |= static_cast<unsigned>(t - iv.x) < static_cast<unsigned>(iv.y);
+          }
         }
         float* xv = reinterpret_cast<float*>(&x);
 #pragma unroll

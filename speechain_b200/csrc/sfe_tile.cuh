@@ -184,6 +184,9 @@ constexpr int T2_CTRL_BYTES(int TS) { return 96 + T2_MAX_NPB * TS * 16; }
 
 // try_wait with a suspend-time hint: the warp sleeps in hardware until the phase flips (or ~1 us passes) — it
 // neither eats the issue slots of the warps it waits for nor adds a polling interval to the hand-over
+#ifndef SFE_T2_FULLBAR
+#define SFE_T2_FULLBAR 1
+#endif
 #ifndef SFE_T2_WAIT  // tuning experiments: 0 plain try_wait loop, 1 sleep between polls, 2 hardware suspend hint
 #define SFE_T2_WAIT 2
 #endif
@@ -248,6 +251,10 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
   constexpr int pre1 = PRE ? 1 : 0;
   constexpr int EDGE_SHIFT = 4;
   const int p2_floats = 2 * TS * PP;
+  // hand-over of a full tile through a hardware named barrier (TS arriving pair warps + the buffer's Mel warps) instead
+  // of an mbarrier the Mel warps poll
+  constexpr int FULLBAR_ID0 = 1 + 3 * T2_MAX_NPB;
+  constexpr bool FULLBAR = (SFE_T2_FULLBAR != 0) && (FULLBAR_ID0 + NPB <= 16) && (TS + TileCfg<PL>::MS <= TileCfg<PL>::NW);
 
   // ---- one-time set-up ----
   if (tid == 0) {
@@ -403,7 +410,8 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
     SFE_PF_DECL
     for (int j = pb; j < ntiles; j += NPB) {
       SFE_PF(4)
-      mbar_wait_hint(pfull0 + 8 * pb, static_cast<uint32_t>((j / NPB) & 1));
+      if (FULLBAR) named_sync(FULLBAR_ID0 + pb, 32 * TS + 32 * MS);
+      else mbar_wait_hint(pfull0 + 8 * pb, static_cast<uint32_t>((j / NPB) & 1));
       SFE_PF(0)
       SFE_TR(10, j);
       const int nsl = min(TS, npairs - j * TS);
@@ -749,7 +757,11 @@ __global__ void __launch_bounds__(TileCfg<PL>::NW * 32, 1) tile_frontend_kernel(
         T2Row rd;
         rd.b = b; rd.tA = tA; rd.flen = flen; rd.kind = kind;
         rows[pb * TS + s] = rd;
-        mbar_arrive(pfull0 + 8 * pb);  // (release: rows and descriptor are visible to the Mel warp)
+        if (!FULLBAR) mbar_arrive(pfull0 + 8 * pb);  // (release: rows and descriptor are visible to the Mel warp)
+      }
+      if (FULLBAR) {
+        __syncwarp();
+        named_arrive(FULLBAR_ID0 + pb, 32 * TS + 32 * TileCfg<PL>::MS);
       }
     };
     if (kind == U_DONE || kind == U_PAD || SFE_T2_ABLATE >= 2) {  // (U_DONE: padding of the CTA's last tile)
