@@ -156,6 +156,12 @@ int sfe_frontend_forward(const sfe_plan* plan, const float* wav, int64_t wav_pit
  *                by the caller between calls; ws_half (0/1) names the half this call accumulates into
  *                and must alternate from call to call on the same scratch; after a failed call zero
  *                the scratch again.
+ *   norm_mode 3  batch / global statistics that are still being averaged (training, epoch <= max_epoch_num;
+ *                feat_norm.py:232-266, 455-508): launch 1 as in mode 2 but into ONE (B, n_mels, 2) stats_ws that the
+ *                call zeroes itself (ws_half is ignored), launch 2 reduces the per-utterance statistics to the packed
+ *                [sum_i mean_i | sum_i std_i | B] of sfe_stats_finalize, written to `mean_out` (2 n_mels + 1 floats).
+ *                `mel` holds the RAW valid rows afterwards; the caller all-reduces the packed sums when it runs
+ *                data-parallel (one collective) and finishes with sfe_running_normalize.  masks / warp are ignored.
  * mean_out/std_out (B, n_mels), optional: the per-utterance statistics of norm_mode 2.
  * wav_len_host: as in sfe_frontend_forward (optional host copy of wav_len).
  * warp / warp_out: NULL, or the SpecAugment time warp (specaug.py:89-127: the warp comes BEFORE the masks) and a second
@@ -169,6 +175,19 @@ int sfe_chain_forward(const sfe_plan* plan, const float* wav, int64_t wav_pitch,
                       const float* std, float clamp, int32_t use_mean, int32_t use_std,
                       float* mean_out, float* std_out, const sfe_masks* masks, void* stream,
                       const int64_t* wav_len_host, const sfe_warp* warp, float* warp_out);
+
+/* Second half of the averaging step (feat_norm.py:250,265,455-508, 327-336, then specaug.py:73-206): the running
+ * average of register_mean_std_batch from the (all-reduced) packed sums — run = first ? batch : weight*batch +
+ * (1-weight)*run, weight = 1/count in fp32 — written to run_mean / run_std (n_mels,; either may be NULL: mean_norm /
+ * std_norm off), `count` stored into the `{prefix}_batch` buffer `counter` (int64 on the device, or NULL), and then
+ * (feat - run_mean) / run_std in place over feat (B, F, D) with the rows at or past feat_len synthesised from
+ * pad_value when src_has_pad == 0, the SpecAugment masks, and — with warp / warp_out — the time warp in front of the
+ * masks, result in warp_out (as in sfe_chain_forward).  Two launches (three with a warp). */
+int sfe_running_normalize(const float* packed, int32_t D, float weight, int32_t first, float* run_mean,
+                          float* run_std, int64_t* counter, int64_t count, float* feat,
+                          const int64_t* feat_len, int32_t B, int64_t F, int32_t src_has_pad,
+                          float pad_value, const sfe_masks* masks, void* stream, const sfe_warp* warp,
+                          float* warp_out);
 
 /* LinearSpec2MelSpec.forward on an existing linear spectrogram (linear2mel.py:163-189).
  * lin (B*F, n_fft/2+1) -> mel (B*F, n_mels). */

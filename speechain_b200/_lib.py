@@ -58,6 +58,8 @@ SYMBOLS = {
                                        C.POINTER(SfeMasks), _i32, _vp, _vp]),
     "sfe_chain_forward": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _f32, _i32, _i32,
                                     _vp, _vp, C.POINTER(SfeMasks), _vp, _vp, C.POINTER(SfeWarp), _vp]),
+    "sfe_running_normalize": (C.c_int, [_vp, _i32, _f32, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _i64, _i32, _f32,
+                                        C.POINTER(SfeMasks), _vp, C.POINTER(SfeWarp), _vp]),
     "sfe_linear2mel_forward": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "sfe_stats_accumulate": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp]),
     "sfe_stats_finalize": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),

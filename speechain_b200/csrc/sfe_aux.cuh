@@ -136,8 +136,10 @@ __global__ void stats_finalize_kernel(const void* __restrict__ stats, int fixed,
 // batch statistics + running average                                       feat_norm.py:250,265,483-508
 __global__ void running_update_kernel(const float* __restrict__ packed, int D, float w, int first, int update,
                                       float* __restrict__ run_mean, float* __restrict__ run_std,
-                                      float* __restrict__ bmean, float* __restrict__ bstd) {
+                                      float* __restrict__ bmean, float* __restrict__ bstd,
+                                      long long* __restrict__ counter, long long count) {
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d == 0 && counter) *counter = count;  // the `{prefix}_batch` buffer (feat_norm.py:469-480)
   if (d >= D) return;
   const float n = packed[2 * D];
   const float m = packed[d] / n, s = packed[D + d] / n;

@@ -782,7 +782,7 @@ extern "C" int sfe_running_update(const float* packed, int32_t D, float weight, 
                                   void* stream) {
   if (!packed || D <= 0) return fail(SFE_ERR_BAD_ARG, "sfe_running_update: bad argument");
   running_update_kernel<<<(D + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      packed, D, weight, first, update, run_mean, run_std, batch_mean_out, batch_std_out);
+      packed, D, weight, first, update, run_mean, run_std, batch_mean_out, batch_std_out, nullptr, 0);
   SFE_CUDA(cudaGetLastError());
   return SFE_OK;
 }
@@ -988,9 +988,20 @@ extern "C" int sfe_chain_forward(const sfe_plan* pl, const float* wav, int64_t w
     return normalize_impl(mel, warp_out, feat_len, B, F, pl->cfg.n_mels, nullptr, 0, clamp, 0, 0, nullptr, nullptr, 0,
                           nullptr, nullptr, 1, 0.f, warp, masks, stream, nullptr);
   }
-  if (norm_mode != 2) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: norm_mode must be 0, 1 or 2");
-  if (!stats_ws) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: norm_mode 2 needs stats_ws");
-  if (!pl->cfg.mel_logging) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: norm_mode 2 needs a log-mel plan");
+  if (norm_mode != 2 && norm_mode != 3) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: norm_mode must be 0, 1, 2 or 3");
+  if (!stats_ws) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: norm_mode 2 / 3 needs stats_ws");
+  if (!pl->cfg.mel_logging) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: norm_mode 2 / 3 needs a log-mel plan");
+  if (norm_mode == 3) {
+    // batch / global statistics that are still being averaged: raw rows + sums (the launch zeroes stats_ws itself:
+    // ONE (B, n_mels, 2) buffer, ws_half is ignored), then the packed [sum of means | sum of stds | B] of
+    // sfe_stats_finalize into mean_out.  The caller all-reduces those 2 n_mels + 1 floats when it runs data-parallel
+    // and finishes with sfe_running_normalize.
+    if (!mean_out) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: norm_mode 3 writes the packed sums to mean_out");
+    if (int rc = frontend_forward_impl(pl, wav, wav_pitch, wav_len, B, T_max, mel, nullptr, nullptr, feat_len, stats_ws,
+                                       nullptr, nullptr, nullptr, 1, stream, true, wav_len_host))
+      return rc;
+    return sfe_stats_finalize(stats_ws, 1, feat_len, B, pl->cfg.n_mels, clamp, nullptr, nullptr, mean_out, stream);
+  }
   // stats_ws holds TWO (B, n_mels, 2) buffers, both zero before the first call: this call accumulates into half
   // `ws_half` and its normalise launch clears the other half for the next call (which must pass 1 - ws_half),
   // so no memset launch is needed
@@ -1019,6 +1030,34 @@ extern "C" int sfe_chain_forward(const sfe_plan* pl, const float* wav, int64_t w
                               warp_on ? warp : nullptr, masks, stream, other))
     return rc;
   return SFE_OK;
+}
+
+extern "C" int sfe_running_normalize(const float* packed, int32_t D, float weight, int32_t first, float* run_mean,
+                                     float* run_std, int64_t* counter, int64_t count, float* feat,
+                                     const int64_t* feat_len, int32_t B, int64_t F, int32_t src_has_pad, float pad_value,
+                                     const sfe_masks* masks, void* stream, const sfe_warp* warp, float* warp_out) {
+  if (!packed || D <= 0 || (!run_mean && !run_std))
+    return fail(SFE_ERR_BAD_ARG, "sfe_running_normalize: bad argument");
+  const bool warp_on = warp && warp->enabled;
+  if (warp_on && (!warp_out || warp_out == feat))
+    return fail(SFE_ERR_BAD_ARG, "sfe_running_normalize: a time warp needs warp_out, a second (B, F, D) buffer");
+  running_update_kernel<<<(D + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      packed, D, weight, first, 1, run_mean, run_std, nullptr, nullptr, reinterpret_cast<long long*>(counter), count);
+  SFE_CUDA(cudaGetLastError());
+  if (warp_on) {
+    if (!(warp->center > 0 && warp->center < warp->minlen && warp->pos > 0 && warp->pos < warp->minlen && warp->minlen <= F))
+      return fail(SFE_ERR_BAD_ARG, "sfe_running_normalize: inconsistent warp descriptor");
+    if (const int cols = warp_tail_cols(B, D, warp_out, warp, masks)) {
+      // normalise + frequency masks into warp_out (every row), then warp + time masks on its rows [0, minlen) in place
+      sfe_masks fm;
+      if (int rc = normalize_impl(feat, warp_out, feat_len, B, F, D, nullptr, 0, 0.f, 0, 0, run_mean, run_std, 0, nullptr,
+                                  nullptr, src_has_pad, pad_value, nullptr, freq_only(masks, &fm), stream, nullptr))
+        return rc;
+      return warp_tail(warp_out, B, F, D, cols, warp, masks, stream);
+    }
+  }
+  return normalize_impl(feat, warp_on ? warp_out : feat, feat_len, B, F, D, nullptr, 0, 0.f, 0, 0, run_mean, run_std, 0,
+                        nullptr, nullptr, src_has_pad, pad_value, warp_on ? warp : nullptr, masks, stream, nullptr);
 }
 
 // Row groups of the ragged upload: [b, e) travels as one pitched copy of width w (see include/sfe.h).

@@ -210,6 +210,7 @@ class FrontendPlan:
         self._lib = lib
         self._ws = {}   # per-batch-size scratch for the fixed-point sums (stream-ordered reuse)
         self._frames = {}  # padded length -> frame count
+        self._ws3 = {}  # per-batch-size sums of the averaging step (zeroed by the call itself)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -314,6 +315,40 @@ class FrontendPlan:
             self._ws[B][1] = 1 - half
         return (out2 if out2 is not None else mel), feat_len
 
+    def chain_sums(self, wav: torch.Tensor, wav_len: torch.Tensor, *, clamp: float = 1e-10, len_host=None):
+        """First half of a step whose batch / global statistics are still being averaged (sfe_chain_forward, norm_mode
+        3): raw valid rows + the packed [sum of means | sum of stds | B] of the batch.  Same lean contract as `chain`.
+        Returns (mel, feat_len, packed (2 n_mels + 1,) fp32)."""
+        B, T = wav.shape[0], wav.shape[1]
+        dev = wav.device
+        F = self._frames.get(T)
+        if F is None:
+            F = self._frames[T] = self.num_frames(T)
+        mel = torch.empty((B, F, self.n_mels), dtype=torch.float32, device=dev)
+        feat_len = torch.empty((B,), dtype=torch.int64, device=dev)
+        packed = torch.empty((2 * self.n_mels + 1,), dtype=torch.float32, device=dev)
+        ws = self._ws3.get(B)
+        if ws is None:
+            ws = self._ws3[B] = torch.empty((B, self.n_mels, 2), dtype=torch.int64, device=dev)
+        idx = dev.index
+        prev = torch._C._cuda_getDevice()
+        if idx is not None and idx != prev:
+            torch.cuda.set_device(idx)
+        else:
+            idx = prev
+        try:
+            rc = self._lib.sfe_chain_forward(
+                self._h, wav.data_ptr(), wav.stride(0), wav_len.data_ptr(), B, T, mel.data_ptr(), feat_len.data_ptr(),
+                ws.data_ptr(), 0, 3, None, None, clamp, 1, 1, packed.data_ptr(), None, None,
+                torch._C._cuda_getCurrentRawStream(idx),
+                len_host if isinstance(len_host, int) else _host_len_ptr(len_host, B), None, None)
+        finally:
+            if idx != prev:
+                torch.cuda.set_device(prev)
+        if rc:
+            _lib.check(rc)
+        return mel, feat_len, packed
+
     def griffinlim(self, spec: torch.Tensor, feat_len: torch.Tensor, *, n_iter: int = 32, momentum: float = 0.99,
                    init_angles: Optional[torch.Tensor] = None, inv_preemph_taps: int = 0):
         """(B, F, K) power/magnitude spectrogram -> (waveform (B, hop*(F-1)), wav_len (B,)); see sfe_griffinlim.
@@ -383,6 +418,29 @@ def running_update(packed: torch.Tensor, D: int, weight: float, first: bool, upd
         _lib.check(_lib.load().sfe_running_update(_ptr(packed), D, float(weight), int(first), int(update), _ptr(run_mean),
                                                   _ptr(run_std), _ptr(bm), _ptr(bs), _stream()))
     return bm, bs
+
+
+def running_normalize(packed: torch.Tensor, weight: float, first: bool, run_mean, run_std, counter, count: int,
+                      feat: torch.Tensor, feat_len: torch.Tensor, *, src_has_pad: bool, pad_value: float,
+                      masks: Optional["DeviceMasks"] = None, warp=None):
+    """Second half of the averaging step (sfe_running_normalize): running average of the statistics from the packed
+    sums, `count` into the counter buffer, then (x - mean) / std [+ time warp] [+ masks] over `feat` — in place, or
+    into a new tensor when a warp is requested.  Returns the result tensor."""
+    B, F, D = feat.shape
+    dev = feat.device
+    wp = out2 = None
+    if warp is not None:
+        wp = _lib.SfeWarp(int(warp[3]) if len(warp) > 3 else 1, int(warp[0]), int(warp[1]), int(warp[2]))
+        out2 = torch.empty_like(feat)
+    ms = masks.struct() if masks is not None else None
+    with _on_device(dev):
+        _lib.check(_lib.load().sfe_running_normalize(
+            packed.data_ptr(), D, float(weight), int(first), run_mean.data_ptr() if run_mean is not None else None,
+            run_std.data_ptr() if run_std is not None else None, counter.data_ptr() if counter is not None else None,
+            int(count), feat.data_ptr(), feat_len.data_ptr(), B, F, int(src_has_pad), float(pad_value),
+            C.byref(ms) if ms is not None else None, _stream(), C.byref(wp) if wp is not None else None,
+            out2.data_ptr() if out2 is not None else None))
+    return out2 if out2 is not None else feat
 
 
 def normalize(src: torch.Tensor, feat_len: torch.Tensor, *, dst: Optional[torch.Tensor] = None, stats=None,

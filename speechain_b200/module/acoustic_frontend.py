@@ -131,6 +131,11 @@ class AcousticFrontend(Module):
             elif not bf16 and plan.mel_logging and (kind == "utterance" or (kind == "batch" and not norm.training)):
                 y, ylen = plan.chain(wav, len_dev, norm_mode=2, clamp=norm.clamp, use_mean=norm.mean_norm,
                                      use_std=norm.std_norm, masks=fused_masks, len_host=len_host, warp=cwarp)
+            elif (not bf16 and plan.mel_logging and not isinstance(domain, torch.Tensor)
+                  and norm.averaging(prefix, epoch)):
+                # statistics still being averaged: two library calls with the (2 D + 1)-float exchange between them
+                y, ylen = norm.average_step(plan, wav, len_dev, len_host, prefix, epoch, masks=masks, warp=warp)
+                warp_done = True
             else:
                 # raw rows + sums, then ONE pass: statistics (exchanged across ranks if needed), warp, masks
                 if wav.dim() == 3:

@@ -5,6 +5,7 @@ normalisation is one read + one write, and the DDP exchange is ONE all-reduce of
 (2·D+1)-float buffer instead of the reference's three all_gathers (feat_norm.py:146-266)."""
 from typing import Dict, Optional
 
+import numpy as np
 import torch
 
 from ...host import ops
@@ -78,6 +79,57 @@ class FeatureNormalization(Module):
         else:  # one of the two buffers pre-exists (partial checkpoint)
             ops.running_update(packed, D, weight, first_m, True, run_mean, None)
             ops.running_update(packed, D, weight, first_s, True, None, run_std)
+
+    def averaging(self, prefix: Optional[str], epoch: Optional[int]) -> bool:
+        """True when a training step on `prefix` ("global" or a group name) updates the running statistics and both
+        buffers are in the same state (both missing or both present) — the case AcousticFrontend runs as two library
+        calls (`average_step`).  Everything else takes `forward`."""
+        if not self.training or prefix is None or self.norm_type not in ("global", "group"):
+            return False
+        if not (epoch is None or epoch <= self.max_epoch_num):
+            return False
+        if self.mean_norm and self.std_norm:
+            return hasattr(self, f"{prefix}_mean") == hasattr(self, f"{prefix}_std")
+        return True
+
+    def average_step(self, plan, wav, len_dev, len_host, prefix: str, epoch: Optional[int], masks=None, warp=None):
+        """The step of feat_norm.py:232-266, 455-508, 327-336 while the statistics are being averaged, straight from
+        the waveforms: frontend launch with sums + packed batch statistics (one library call), the all-reduce of the
+        2 D + 1 floats under DDP, then running average + counter + normalise [+ warp] [+ masks] (one more call)."""
+        D = plan.n_mels
+        dev = wav.device
+        count = self._counter(prefix)
+        count = 1 if (epoch is None or count is None) else count + 1
+        self._batch_host[prefix] = count
+        bufs = self._buffers
+        counter = bufs.get(f"{prefix}_batch")
+        if counter is None or counter.device != dev:
+            self.register_buffer(f"{prefix}_batch", torch.empty((1,), dtype=torch.int64, device=dev))
+            counter = bufs[f"{prefix}_batch"]
+        run_mean = run_std = None
+        first = False
+        for name in (f"{prefix}_mean", f"{prefix}_std"):  # (a checkpoint loaded on another device)
+            t = bufs.get(name)
+            if t is not None and (t.device != dev or t.dtype != torch.float32 or not t.is_contiguous()):
+                bufs[name] = t.to(dev, torch.float32).contiguous()
+        if self.mean_norm:
+            run_mean = bufs.get(f"{prefix}_mean")
+            if run_mean is None:
+                first = True
+                self.register_buffer(f"{prefix}_mean", torch.empty(D, dtype=torch.float32, device=dev))
+                run_mean = bufs[f"{prefix}_mean"]
+        if self.std_norm:
+            run_std = bufs.get(f"{prefix}_std")
+            if run_std is None:
+                first = True
+                self.register_buffer(f"{prefix}_std", torch.empty(D, dtype=torch.float32, device=dev))
+                run_std = bufs[f"{prefix}_std"]
+        weight = float(np.float32(1.0) / np.float32(count))  # fp32 1/count like `1 / LongTensor`
+        mel, ylen, packed = plan.chain_sums(wav, len_dev, clamp=self.clamp, len_host=len_host)
+        packed = self._all_reduce(packed)
+        y = ops.running_normalize(packed, weight, first, run_mean, run_std, counter, count, mel, ylen,
+                                  src_has_pad=False, pad_value=plan.pad_mel, masks=masks, warp=warp)
+        return y, ylen
 
     # ------------------------------------------------------------------------------------
     def forward(self, feat: torch.Tensor, feat_len: torch.Tensor, group_ids=None, epoch: int = None,

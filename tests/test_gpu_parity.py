@@ -626,6 +626,65 @@ def test_frozen_global_statistics_with_recipe_specaug_vs_oracle(n_fft, mode):
     assert_close(got, ref, what=f"frozen global statistics + warp ({mode}, n_fft {n_fft})")
 
 
+@pytest.mark.parametrize("stats", ["both", "mean_only", "std_only"])
+def test_averaging_epochs_through_the_chain_vs_oracle(stats):
+    """The ASR recipes' training step during the first max_epoch_num epochs (normalize: True = global statistics, still
+    averaged; SpecAugment with time warp): frontend launch with sums + packed batch statistics, running average with
+    the counter, normalise + warp + masks — against the oracle step by step, buffers and counter included, then the
+    state dict into a fresh module (the counter must continue) and a step with epoch=None (count restarts at 1)."""
+    conf = dict(n_mels=80, n_fft=512, win_length=0.025, hop_length=0.010, sr=16000, preemphasis=0.97)
+    sconf = dict(freq_mask_width=15, freq_mask_num=4, time_mask_width=0.05, time_mask_num=5)
+    nconf = dict(norm_type="global", mean_norm=stats != "std_only", std_norm=stats != "mean_only")
+    chain = AcousticFrontend(frontend=dict(conf=conf), normalize=nconf, specaug=sconf).to(DEV)
+    chain.train()
+    st = O.RunningStats()
+    g = torch.Generator().manual_seed(4321)
+
+    def step(chain, k, epoch):
+        lens = sorted(torch.randint(16000, 56001, (6,), generator=g).tolist(), reverse=True)
+        wav = _wave(60 + k, lens, zero_seg=False)
+        torch.manual_seed(100 + k)
+        y, yl = chain(wav.to(DEV)[..., None], torch.tensor(lens, device=DEV), epoch=epoch)
+        feat, flen, _ = O.speech2mel(wav.numpy().astype(np.float64), lens, O.FrontendCfg(**conf))
+        ms, ss = O.utterance_stats(feat, flen, 1e-10)
+        bm, bs = O.batch_stats([ms], [ss])
+        st.register(bm, bs, epoch)
+        ref = feat
+        if nconf["mean_norm"]:
+            ref = ref - st.mean
+        if nconf["std_norm"]:
+            ref = ref / st.std
+        d = O.specaug_draw(O.TorchCpuRandint(100 + k), len(lens), 80, flen, O.SpecAugCfg(**sconf))
+        assert d.warp is not None
+        ref = O.specaug_apply(ref, flen, d, feat_norm=True)
+        got = y.cpu().numpy()
+        assert np.array_equal(yl.cpu().numpy(), flen)
+        mask = O.specaug_mask(*got.shape, d)
+        assert (got[mask] == 0.0).all()
+        assert_close(got, ref, what=f"averaging step {k} ({stats})")
+        n = chain.normalize
+        if nconf["mean_norm"]:
+            assert_close(n.global_mean.cpu().numpy(), st.mean, what=f"global_mean {k}")
+        else:
+            assert not hasattr(n, "global_mean")
+        if nconf["std_norm"]:
+            assert_close(n.global_std.cpu().numpy(), st.std, what=f"global_std {k}")
+        else:
+            assert not hasattr(n, "global_std")
+        return n
+
+    for k in range(3):
+        n = step(chain, k, epoch=1 + k)
+        assert int(n.global_batch.item()) == k + 1
+    fresh = AcousticFrontend(frontend=dict(conf=conf), normalize=nconf, specaug=sconf).to(DEV)
+    fresh.load_state_dict(chain.state_dict())
+    fresh.train()
+    n = step(fresh, 3, epoch=4)
+    assert int(n.global_batch.item()) == 4
+    n = step(fresh, 4, epoch=None)  # feat_norm.py:469-472: no epoch -> the counter restarts, the average is the batch
+    assert int(n.global_batch.item()) == 1
+
+
 def test_c5_style_linear_and_mel_from_one_launch_with_running_global_norm():
     # BASELINE config 5 in miniature: magnitude linear spectrogram AND mel from one launch; mel -> global norm with
     # the running average over several batches (epoch=1) -> SpecAugment
