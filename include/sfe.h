@@ -157,9 +157,10 @@ int sfe_frontend_forward(const sfe_plan* plan, const float* wav, int64_t wav_pit
  *                and must alternate from call to call on the same scratch; after a failed call zero
  *                the scratch again.
  *   norm_mode 3  batch / global statistics that are still being averaged (training, epoch <= max_epoch_num;
- *                feat_norm.py:232-266, 455-508): launch 1 as in mode 2 but into ONE (B, n_mels, 2) stats_ws that the
- *                call zeroes itself (ws_half is ignored), launch 2 reduces the per-utterance statistics to the packed
- *                [sum_i mean_i | sum_i std_i | B] of sfe_stats_finalize, written to `mean_out` (2 n_mels + 1 floats).
+ *                feat_norm.py:232-266, 455-508): launch 1 as in mode 2 (same stats_ws / ws_half protocol; the two
+ *                modes may share one scratch), launch 2 reduces the per-utterance statistics to the packed
+ *                [sum_i mean_i | sum_i std_i | B] of sfe_stats_finalize, written to `mean_out` (2 n_mels + 1 floats),
+ *                and clears the other half.
  *                `mel` holds the RAW valid rows afterwards; the caller all-reduces the packed sums when it runs
  *                data-parallel (one collective) and finishes with sfe_running_normalize.  masks / warp are ignored.
  * mean_out/std_out (B, n_mels), optional: the per-utterance statistics of norm_mode 2.

@@ -100,7 +100,10 @@ __device__ __forceinline__ void moments_to_mean_std(double s1, double s2, long l
 // column)); the slices' partial sums are combined in slice order, so the result does not depend on timing.
 __global__ void stats_finalize_kernel(const void* __restrict__ stats, int fixed, const long long* __restrict__ flen,
                                       int B, int D, int Dc, int S, float clamp, float* __restrict__ mean,
-                                      float* __restrict__ sd, float* __restrict__ packed) {
+                                      float* __restrict__ sd, float* __restrict__ packed,
+                                      long long* __restrict__ zero_sums) {
+  pdl_launch_dependents();
+  pdl_wait();  // (a no-op unless launched with programmatic stream serialisation)
   extern __shared__ float fin_red[];  // [S][Dc][2]
   const int sl = threadIdx.x / Dc, dl = threadIdx.x - sl * Dc;
   const int d = blockIdx.x * Dc + dl;
@@ -109,6 +112,10 @@ __global__ void stats_finalize_kernel(const void* __restrict__ stats, int fixed,
     for (int b = sl; b < B; b += S) {
       float m, s;
       double s1, s2;
+      if (zero_sums) {  // the other half of the double-buffered sums, for the next call (sfe_chain_forward)
+        zero_sums[(static_cast<long long>(b) * D + d) * 2] = 0;
+        zero_sums[(static_cast<long long>(b) * D + d) * 2 + 1] = 0;
+      }
       load_moments(stats, fixed, static_cast<long long>(b) * D + d, s1, s2);
       moments_to_mean_std(s1, s2, flen[b], clamp, m, s);
       if (mean) mean[static_cast<long long>(b) * D + d] = m;
@@ -138,6 +145,8 @@ __global__ void running_update_kernel(const float* __restrict__ packed, int D, f
                                       float* __restrict__ run_mean, float* __restrict__ run_std,
                                       float* __restrict__ bmean, float* __restrict__ bstd,
                                       long long* __restrict__ counter, long long count) {
+  pdl_launch_dependents();
+  pdl_wait();  // (a no-op unless launched with programmatic stream serialisation)
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d == 0 && counter) *counter = count;  // the `{prefix}_batch` buffer (feat_norm.py:469-480)
   if (d >= D) return;

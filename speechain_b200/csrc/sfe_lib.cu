@@ -128,6 +128,28 @@ static cudaError_t launch_pdl(void (*fn)(const Params), dim3 grid, dim3 block, s
   return cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(fn), args);
 }
 
+// (the same for kernels that take their arguments one by one)
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl_args(void (*fn)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  static const bool on = [] {
+    const char* ev = getenv("SFE_PDL");
+    return !(ev && ev[0] == '0');
+  }();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at;
+  memset(&at, 0, sizeof(at));
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, fn, static_cast<KArgs>(args)...);
+}
+
 // SM count of the current device, looked up once per device (hot host path: no driver query per call)
 static int cached_sm_count() {
   static std::mutex mu;
@@ -761,8 +783,9 @@ extern "C" int sfe_stats_accumulate(const float* feat, const int64_t* feat_len, 
   return SFE_OK;
 }
 
-extern "C" int sfe_stats_finalize(const void* stats, int32_t stats_fixed, const int64_t* feat_len, int32_t B, int32_t D,
-                                  float clamp, float* mean, float* std, float* packed, void* stream) {
+static int stats_finalize_impl(const void* stats, int32_t stats_fixed, const int64_t* feat_len, int32_t B, int32_t D,
+                               float clamp, float* mean, float* std, float* packed, void* stream, int64_t* zero_sums,
+                               bool pdl) {
   if (!stats || !feat_len) return fail(SFE_ERR_BAD_ARG, "sfe_stats_finalize: NULL argument");
   if (B <= 0 || D <= 0) return fail(SFE_ERR_BAD_ARG, "sfe_stats_finalize: bad shape");
   // one CTA per 1024 columns; inside it the utterances are cut into interleaved slices (1024 / Dc of them)
@@ -770,11 +793,24 @@ extern "C" int sfe_stats_finalize(const void* stats, int32_t stats_fixed, const 
   int S = 1024 / Dc;
   if (S > B) S = B;
   const int threads = ((S * Dc + 31) / 32) * 32;
-  stats_finalize_kernel<<<(D + Dc - 1) / Dc, threads, static_cast<size_t>(S) * Dc * 2 * sizeof(float),
-                          static_cast<cudaStream_t>(stream)>>>(
-      stats, stats_fixed, reinterpret_cast<const long long*>(feat_len), B, D, Dc, S, clamp, mean, std, packed);
+  const dim3 grid((D + Dc - 1) / Dc), block(threads);
+  const size_t smem = static_cast<size_t>(S) * Dc * 2 * sizeof(float);
+  const long long* fl = reinterpret_cast<const long long*>(feat_len);
+  long long* zs = reinterpret_cast<long long*>(zero_sums);
+  if (pdl)
+    SFE_CUDA(launch_pdl_args(stats_finalize_kernel, grid, block, smem, static_cast<cudaStream_t>(stream), stats,
+                             static_cast<int>(stats_fixed), fl, static_cast<int>(B), static_cast<int>(D), Dc, S, clamp, mean,
+                             std, packed, zs));
+  else
+    stats_finalize_kernel<<<grid, block, smem, static_cast<cudaStream_t>(stream)>>>(stats, stats_fixed, fl, B, D, Dc, S,
+                                                                                    clamp, mean, std, packed, zs);
   SFE_CUDA(cudaGetLastError());
   return SFE_OK;
+}
+
+extern "C" int sfe_stats_finalize(const void* stats, int32_t stats_fixed, const int64_t* feat_len, int32_t B, int32_t D,
+                                  float clamp, float* mean, float* std, float* packed, void* stream) {
+  return stats_finalize_impl(stats, stats_fixed, feat_len, B, D, clamp, mean, std, packed, stream, nullptr, false);
 }
 
 extern "C" int sfe_running_update(const float* packed, int32_t D, float weight, int32_t first, int32_t update,
@@ -992,15 +1028,19 @@ extern "C" int sfe_chain_forward(const sfe_plan* pl, const float* wav, int64_t w
   if (!stats_ws) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: norm_mode 2 / 3 needs stats_ws");
   if (!pl->cfg.mel_logging) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: norm_mode 2 / 3 needs a log-mel plan");
   if (norm_mode == 3) {
-    // batch / global statistics that are still being averaged: raw rows + sums (the launch zeroes stats_ws itself:
-    // ONE (B, n_mels, 2) buffer, ws_half is ignored), then the packed [sum of means | sum of stds | B] of
-    // sfe_stats_finalize into mean_out.  The caller all-reduces those 2 n_mels + 1 floats when it runs data-parallel
-    // and finishes with sfe_running_normalize.
+    // batch / global statistics that are still being averaged: raw rows + sums into one half of stats_ws (the
+    // protocol of norm_mode 2), then the packed [sum of means | sum of stds | B] of sfe_stats_finalize into mean_out
+    // by a launch that also clears the other half.  The caller all-reduces those 2 n_mels + 1 floats when it runs
+    // data-parallel and finishes with sfe_running_normalize.
     if (!mean_out) return fail(SFE_ERR_BAD_ARG, "sfe_chain_forward: norm_mode 3 writes the packed sums to mean_out");
-    if (int rc = frontend_forward_impl(pl, wav, wav_pitch, wav_len, B, T_max, mel, nullptr, nullptr, feat_len, stats_ws,
-                                       nullptr, nullptr, nullptr, 1, stream, true, wav_len_host))
+    const size_t half3 = static_cast<size_t>(B) * pl->cfg.n_mels * 2;
+    int64_t* cur3 = stats_ws + (ws_half ? half3 : 0);
+    int64_t* other3 = stats_ws + (ws_half ? 0 : half3);
+    if (int rc = frontend_forward_impl(pl, wav, wav_pitch, wav_len, B, T_max, mel, nullptr, nullptr, feat_len, cur3,
+                                       nullptr, nullptr, nullptr, 1, stream, false, wav_len_host))
       return rc;
-    return sfe_stats_finalize(stats_ws, 1, feat_len, B, pl->cfg.n_mels, clamp, nullptr, nullptr, mean_out, stream);
+    return stats_finalize_impl(cur3, 1, feat_len, B, pl->cfg.n_mels, clamp, nullptr, nullptr, mean_out, stream, other3,
+                               true);
   }
   // stats_ws holds TWO (B, n_mels, 2) buffers, both zero before the first call: this call accumulates into half
   // `ws_half` and its normalise launch clears the other half for the next call (which must pass 1 - ws_half),
@@ -1041,8 +1081,10 @@ extern "C" int sfe_running_normalize(const float* packed, int32_t D, float weigh
   const bool warp_on = warp && warp->enabled;
   if (warp_on && (!warp_out || warp_out == feat))
     return fail(SFE_ERR_BAD_ARG, "sfe_running_normalize: a time warp needs warp_out, a second (B, F, D) buffer");
-  running_update_kernel<<<(D + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      packed, D, weight, first, 1, run_mean, run_std, nullptr, nullptr, reinterpret_cast<long long*>(counter), count);
+  SFE_CUDA(launch_pdl_args(running_update_kernel, dim3((D + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream),
+                           packed, static_cast<int>(D), weight, static_cast<int>(first), 1, run_mean, run_std,
+                           static_cast<float*>(nullptr), static_cast<float*>(nullptr), reinterpret_cast<long long*>(counter),
+                           static_cast<long long>(count)));
   SFE_CUDA(cudaGetLastError());
   if (warp_on) {
     if (!(warp->center > 0 && warp->center < warp->minlen && warp->pos > 0 && warp->pos < warp->minlen && warp->minlen <= F))

@@ -210,7 +210,6 @@ class FrontendPlan:
         self._lib = lib
         self._ws = {}   # per-batch-size scratch for the fixed-point sums (stream-ordered reuse)
         self._frames = {}  # padded length -> frame count
-        self._ws3 = {}  # per-batch-size sums of the averaging step (zeroed by the call itself)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -327,9 +326,12 @@ class FrontendPlan:
         mel = torch.empty((B, F, self.n_mels), dtype=torch.float32, device=dev)
         feat_len = torch.empty((B,), dtype=torch.int64, device=dev)
         packed = torch.empty((2 * self.n_mels + 1,), dtype=torch.float32, device=dev)
-        ws = self._ws3.get(B)
-        if ws is None:
-            ws = self._ws3[B] = torch.empty((B, self.n_mels, 2), dtype=torch.int64, device=dev)
+        # double-buffered fixed-point sums, shared with norm_mode 2 (same protocol: see `chain`)
+        ent = self._ws.get(B)
+        if ent is None or ent[1] < 0:
+            ent = self._ws[B] = [torch.zeros((2, B, self.n_mels, 2), dtype=torch.int64, device=dev), 0]
+        ws, half = ent
+        ent[1] = -1  # marks the scratch dirty until the call below has been enqueued completely
         idx = dev.index
         prev = torch._C._cuda_getDevice()
         if idx is not None and idx != prev:
@@ -339,7 +341,7 @@ class FrontendPlan:
         try:
             rc = self._lib.sfe_chain_forward(
                 self._h, wav.data_ptr(), wav.stride(0), wav_len.data_ptr(), B, T, mel.data_ptr(), feat_len.data_ptr(),
-                ws.data_ptr(), 0, 3, None, None, clamp, 1, 1, packed.data_ptr(), None, None,
+                ws.data_ptr(), half, 3, None, None, clamp, 1, 1, packed.data_ptr(), None, None,
                 torch._C._cuda_getCurrentRawStream(idx),
                 len_host if isinstance(len_host, int) else _host_len_ptr(len_host, B), None, None)
         finally:
@@ -347,6 +349,7 @@ class FrontendPlan:
                 torch.cuda.set_device(prev)
         if rc:
             _lib.check(rc)
+        self._ws[B][1] = 1 - half
         return mel, feat_len, packed
 
     def griffinlim(self, spec: torch.Tensor, feat_len: torch.Tensor, *, n_iter: int = 32, momentum: float = 0.99,
