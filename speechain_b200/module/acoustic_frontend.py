@@ -136,6 +136,9 @@ class AcousticFrontend(Module):
                 # statistics still being averaged: two library calls with the (2 D + 1)-float exchange between them
                 y, ylen = norm.average_step(plan, wav, len_dev, len_host, prefix, epoch, masks=masks, warp=warp)
                 warp_done = True
+            elif not bf16 and plan.mel_logging and kind == "batch" and norm.training:
+                y, ylen = norm.batch_step(plan, wav, len_dev, len_host, masks=masks, warp=warp)
+                warp_done = True
             else:
                 # raw rows + sums, then ONE pass: statistics (exchanged across ranks if needed), warp, masks
                 if wav.dim() == 3:

@@ -131,6 +131,19 @@ class FeatureNormalization(Module):
                                   src_has_pad=False, pad_value=plan.pad_mel, masks=masks, warp=warp)
         return y, ylen
 
+    def batch_step(self, plan, wav, len_dev, len_host, masks=None, warp=None):
+        """``norm_type='batch'`` in training (feat_norm.py:232-299) straight from the waveforms, as the same two library
+        calls as `average_step`: the batch statistics (all-reduced under DDP) land in a scratch pair of vectors
+        instead of running buffers."""
+        D = plan.n_mels
+        mel, ylen, packed = plan.chain_sums(wav, len_dev, clamp=self.clamp, len_host=len_host)
+        packed = self._all_reduce(packed)
+        tmp = torch.empty((2, D), dtype=torch.float32, device=wav.device)
+        y = ops.running_normalize(packed, 1.0, True, tmp[0] if self.mean_norm else None,
+                                  tmp[1] if self.std_norm else None, None, 0, mel, ylen,
+                                  src_has_pad=False, pad_value=plan.pad_mel, masks=masks, warp=warp)
+        return y, ylen
+
     # ------------------------------------------------------------------------------------
     def forward(self, feat: torch.Tensor, feat_len: torch.Tensor, group_ids=None, epoch: int = None,
                 masks: Optional[DeviceMasks] = None, inplace: bool = False, src_has_pad: bool = True,

@@ -685,6 +685,29 @@ def test_averaging_epochs_through_the_chain_vs_oracle(stats):
     assert int(n.global_batch.item()) == 1
 
 
+@pytest.mark.parametrize("warp", [False, True])
+def test_batch_statistics_in_training_through_the_chain_vs_oracle(warp):
+    """norm_type='batch' in training (feat_norm.py:232-299): the batch's own statistics, nothing kept between steps."""
+    conf = dict(n_mels=80, n_fft=512, win_length=0.025, hop_length=0.010, sr=16000, preemphasis=0.97)
+    sconf = dict(time_warp=warp, freq_mask_width=20, freq_mask_num=2, time_mask_width=0.05, time_mask_num=3)
+    chain = AcousticFrontend(frontend=dict(conf=conf), normalize=dict(norm_type="batch"), specaug=sconf).to(DEV)
+    chain.train()
+    g = torch.Generator().manual_seed(99)
+    for k in range(2):
+        lens = sorted(torch.randint(12000, 50001, (5,), generator=g).tolist(), reverse=True)
+        wav = _wave(80 + k, lens, zero_seg=False)
+        torch.manual_seed(40 + k)
+        y, yl = chain(wav.to(DEV)[..., None], torch.tensor(lens, device=DEV), epoch=1)
+        feat, flen, _ = O.speech2mel(wav.numpy().astype(np.float64), lens, O.FrontendCfg(**conf))
+        ref = O.feat_norm_batch([(feat, flen)], training=True)[0]
+        d = O.specaug_draw(O.TorchCpuRandint(40 + k), len(lens), 80, flen, O.SpecAugCfg(**sconf))
+        assert (d.warp is not None) == warp
+        ref = O.specaug_apply(ref, flen, d, feat_norm=True)
+        assert np.array_equal(yl.cpu().numpy(), flen)
+        assert_close(y.cpu().numpy(), ref, what=f"batch statistics, step {k}, warp {warp}")
+    assert not [n for n, _ in chain.normalize.named_buffers()]  # nothing is remembered
+
+
 def test_c5_style_linear_and_mel_from_one_launch_with_running_global_norm():
     # BASELINE config 5 in miniature: magnitude linear spectrogram AND mel from one launch; mel -> global norm with
     # the running average over several batches (epoch=1) -> SpecAugment

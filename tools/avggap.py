@@ -14,9 +14,10 @@ ring = 5
 batches = [bench.make_batch(w, lens, 7 + i, dev) for i in range(ring)]
 wl = torch.tensor(lens, dtype=torch.int64)
 recipe = dict(freq_mask_width=15, freq_mask_num=4, time_mask_width=0.05, time_mask_num=5)
-for name, aug in (("averaging epoch, no SpecAugment", None), ("averaging epoch + bench masks", w["specaug"]),
-                  ("averaging epoch + recipe SpecAugment (time warp)", recipe)):
-    chain = AcousticFrontend(frontend=dict(conf=w["frontend"]), normalize=dict(norm_type="global"), specaug=aug).to(dev)
+for name, aug, kind in (("averaging epoch, no SpecAugment", None, "global"), ("averaging epoch + bench masks", w["specaug"], "global"),
+                        ("averaging epoch + recipe SpecAugment (time warp)", recipe, "global"),
+                        ("batch statistics (training) + bench masks", w["specaug"], "batch")):
+    chain = AcousticFrontend(frontend=dict(conf=w["frontend"]), normalize=dict(norm_type=kind), specaug=aug).to(dev)
     chain.train()
     for i in range(5): chain(batches[i % ring], wl, epoch=1)
     torch.cuda.synchronize()
