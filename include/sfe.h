@@ -181,14 +181,15 @@ int sfe_chain_forward(const sfe_plan* plan, const float* wav, int64_t wav_pitch,
  * average of register_mean_std_batch from the (all-reduced) packed sums — run = first ? batch : weight*batch +
  * (1-weight)*run, weight = 1/count in fp32 — written to run_mean / run_std (n_mels,; either may be NULL: mean_norm /
  * std_norm off), `count` stored into the `{prefix}_batch` buffer `counter` (int64 on the device, or NULL), and then
- * (feat - run_mean) / run_std in place over feat (B, F, D) with the rows at or past feat_len synthesised from
- * pad_value when src_has_pad == 0, the SpecAugment masks, and — with warp / warp_out — the time warp in front of the
- * masks, result in warp_out (as in sfe_chain_forward).  Two launches (three with a warp). */
+ * out = (feat - run_mean) / run_std over (B, F, D) — `out` may be `feat` itself (in place) — with the rows at or past
+ * feat_len synthesised from pad_value when src_has_pad == 0, the SpecAugment masks, and — with `warp` — the time warp
+ * in front of the masks (then `out` must be a second buffer, as in sfe_chain_forward).  Two launches (three with a
+ * warp). */
 int sfe_running_normalize(const float* packed, int32_t D, float weight, int32_t first, float* run_mean,
-                          float* run_std, int64_t* counter, int64_t count, float* feat,
+                          float* run_std, int64_t* counter, int64_t count, const float* feat,
                           const int64_t* feat_len, int32_t B, int64_t F, int32_t src_has_pad,
                           float pad_value, const sfe_masks* masks, void* stream, const sfe_warp* warp,
-                          float* warp_out);
+                          float* out);
 
 /* LinearSpec2MelSpec.forward on an existing linear spectrogram (linear2mel.py:163-189).
  * lin (B*F, n_fft/2+1) -> mel (B*F, n_mels). */

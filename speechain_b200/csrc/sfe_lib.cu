@@ -1073,14 +1073,15 @@ extern "C" int sfe_chain_forward(const sfe_plan* pl, const float* wav, int64_t w
 }
 
 extern "C" int sfe_running_normalize(const float* packed, int32_t D, float weight, int32_t first, float* run_mean,
-                                     float* run_std, int64_t* counter, int64_t count, float* feat,
+                                     float* run_std, int64_t* counter, int64_t count, const float* feat,
                                      const int64_t* feat_len, int32_t B, int64_t F, int32_t src_has_pad, float pad_value,
-                                     const sfe_masks* masks, void* stream, const sfe_warp* warp, float* warp_out) {
+                                     const sfe_masks* masks, void* stream, const sfe_warp* warp, float* out) {
   if (!packed || D <= 0 || (!run_mean && !run_std))
     return fail(SFE_ERR_BAD_ARG, "sfe_running_normalize: bad argument");
+  if (!out) return fail(SFE_ERR_BAD_ARG, "sfe_running_normalize: NULL destination");
   const bool warp_on = warp && warp->enabled;
-  if (warp_on && (!warp_out || warp_out == feat))
-    return fail(SFE_ERR_BAD_ARG, "sfe_running_normalize: a time warp needs warp_out, a second (B, F, D) buffer");
+  if (warp_on && out == feat)
+    return fail(SFE_ERR_BAD_ARG, "sfe_running_normalize: the time warp cannot run in place");
   SFE_CUDA(launch_pdl_args(running_update_kernel, dim3((D + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream),
                            packed, static_cast<int>(D), weight, static_cast<int>(first), 1, run_mean, run_std,
                            static_cast<float*>(nullptr), static_cast<float*>(nullptr), reinterpret_cast<long long*>(counter),
@@ -1089,17 +1090,17 @@ extern "C" int sfe_running_normalize(const float* packed, int32_t D, float weigh
   if (warp_on) {
     if (!(warp->center > 0 && warp->center < warp->minlen && warp->pos > 0 && warp->pos < warp->minlen && warp->minlen <= F))
       return fail(SFE_ERR_BAD_ARG, "sfe_running_normalize: inconsistent warp descriptor");
-    if (const int cols = warp_tail_cols(B, D, warp_out, warp, masks)) {
-      // normalise + frequency masks into warp_out (every row), then warp + time masks on its rows [0, minlen) in place
+    if (const int cols = warp_tail_cols(B, D, out, warp, masks)) {
+      // normalise + frequency masks into `out` (every row), then warp + time masks on its rows [0, minlen) in place
       sfe_masks fm;
-      if (int rc = normalize_impl(feat, warp_out, feat_len, B, F, D, nullptr, 0, 0.f, 0, 0, run_mean, run_std, 0, nullptr,
+      if (int rc = normalize_impl(feat, out, feat_len, B, F, D, nullptr, 0, 0.f, 0, 0, run_mean, run_std, 0, nullptr,
                                   nullptr, src_has_pad, pad_value, nullptr, freq_only(masks, &fm), stream, nullptr))
         return rc;
-      return warp_tail(warp_out, B, F, D, cols, warp, masks, stream);
+      return warp_tail(out, B, F, D, cols, warp, masks, stream);
     }
   }
-  return normalize_impl(feat, warp_on ? warp_out : feat, feat_len, B, F, D, nullptr, 0, 0.f, 0, 0, run_mean, run_std, 0,
-                        nullptr, nullptr, src_has_pad, pad_value, warp_on ? warp : nullptr, masks, stream, nullptr);
+  return normalize_impl(feat, out, feat_len, B, F, D, nullptr, 0, 0.f, 0, 0, run_mean, run_std, 0, nullptr, nullptr,
+                        src_has_pad, pad_value, warp_on ? warp : nullptr, masks, stream, nullptr);
 }
 
 // Row groups of the ragged upload: [b, e) travels as one pitched copy of width w (see include/sfe.h).

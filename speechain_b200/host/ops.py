@@ -425,16 +425,19 @@ def running_update(packed: torch.Tensor, D: int, weight: float, first: bool, upd
 
 def running_normalize(packed: torch.Tensor, weight: float, first: bool, run_mean, run_std, counter, count: int,
                       feat: torch.Tensor, feat_len: torch.Tensor, *, src_has_pad: bool, pad_value: float,
-                      masks: Optional["DeviceMasks"] = None, warp=None):
+                      masks: Optional["DeviceMasks"] = None, warp=None, dst: Optional[torch.Tensor] = None):
     """Second half of the averaging step (sfe_running_normalize): running average of the statistics from the packed
-    sums, `count` into the counter buffer, then (x - mean) / std [+ time warp] [+ masks] over `feat` — in place, or
-    into a new tensor when a warp is requested.  Returns the result tensor."""
+    sums, `count` into the counter buffer, then (x - mean) / std [+ time warp] [+ masks] over `feat` into `dst` — in
+    place when `dst` is None and no warp is requested (a warp always gets a new tensor).  Returns the result tensor."""
     B, F, D = feat.shape
     dev = feat.device
-    wp = out2 = None
+    wp = None
     if warp is not None:
         wp = _lib.SfeWarp(int(warp[3]) if len(warp) > 3 else 1, int(warp[0]), int(warp[1]), int(warp[2]))
-        out2 = torch.empty_like(feat)
+        if dst is None or dst is feat:
+            dst = torch.empty_like(feat)
+    elif dst is None:
+        dst = feat
     ms = masks.struct() if masks is not None else None
     with _on_device(dev):
         _lib.check(_lib.load().sfe_running_normalize(
@@ -442,8 +445,8 @@ def running_normalize(packed: torch.Tensor, weight: float, first: bool, run_mean
             run_std.data_ptr() if run_std is not None else None, counter.data_ptr() if counter is not None else None,
             int(count), feat.data_ptr(), feat_len.data_ptr(), B, F, int(src_has_pad), float(pad_value),
             C.byref(ms) if ms is not None else None, _stream(), C.byref(wp) if wp is not None else None,
-            out2.data_ptr() if out2 is not None else None))
-    return out2 if out2 is not None else feat
+            dst.data_ptr()))
+    return dst
 
 
 def normalize(src: torch.Tensor, feat_len: torch.Tensor, *, dst: Optional[torch.Tensor] = None, stats=None,

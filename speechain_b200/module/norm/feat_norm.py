@@ -92,12 +92,9 @@ class FeatureNormalization(Module):
             return hasattr(self, f"{prefix}_mean") == hasattr(self, f"{prefix}_std")
         return True
 
-    def average_step(self, plan, wav, len_dev, len_host, prefix: str, epoch: Optional[int], masks=None, warp=None):
-        """The step of feat_norm.py:232-266, 455-508, 327-336 while the statistics are being averaged, straight from
-        the waveforms: frontend launch with sums + packed batch statistics (one library call), the all-reduce of the
-        2 D + 1 floats under DDP, then running average + counter + normalise [+ warp] [+ masks] (one more call)."""
-        D = plan.n_mels
-        dev = wav.device
+    def _advance(self, prefix: str, epoch: Optional[int], D: int, dev):
+        """Host side of register_mean_std_batch (feat_norm.py:455-508) for a step that updates the running average:
+        the counter, the fp32 weight 1/count, and the buffers (created on first use) the kernels write."""
         count = self._counter(prefix)
         count = 1 if (epoch is None or count is None) else count + 1
         self._batch_host[prefix] = count
@@ -125,6 +122,23 @@ class FeatureNormalization(Module):
                 self.register_buffer(f"{prefix}_std", torch.empty(D, dtype=torch.float32, device=dev))
                 run_std = bufs[f"{prefix}_std"]
         weight = float(np.float32(1.0) / np.float32(count))  # fp32 1/count like `1 / LongTensor`
+        return count, weight, first, run_mean, run_std, counter
+
+    def frozen(self, prefix: Optional[str], epoch: Optional[int]) -> bool:
+        """True when a training step can no longer change the statistics of `prefix` (epoch > max_epoch_num) and the
+        buffers it normalises with exist: the batch statistics — and their all-reduce — would be computed for nothing
+        (the reference computes them and drops them, feat_norm.py:483-486)."""
+        if prefix is None or epoch is None or epoch <= self.max_epoch_num:
+            return False
+        bufs = self._buffers
+        return (f"{prefix}_batch" in bufs and (not self.mean_norm or f"{prefix}_mean" in bufs)
+                and (not self.std_norm or f"{prefix}_std" in bufs))
+
+    def average_step(self, plan, wav, len_dev, len_host, prefix: str, epoch: Optional[int], masks=None, warp=None):
+        """The step of feat_norm.py:232-266, 455-508, 327-336 while the statistics are being averaged, straight from
+        the waveforms: frontend launch with sums + packed batch statistics (one library call), the all-reduce of the
+        2 D + 1 floats under DDP, then running average + counter + normalise [+ warp] [+ masks] (one more call)."""
+        count, weight, first, run_mean, run_std, counter = self._advance(prefix, epoch, plan.n_mels, wav.device)
         mel, ylen, packed = plan.chain_sums(wav, len_dev, clamp=self.clamp, len_host=len_host)
         packed = self._all_reduce(packed)
         y = ops.running_normalize(packed, weight, first, run_mean, run_std, counter, count, mel, ylen,
@@ -190,12 +204,13 @@ class FeatureNormalization(Module):
             out, _, _ = ops.normalize(feat, feat_len, dst=dst, **common)
             return (out.squeeze(-1) if squeeze else out), feat_len
 
-        sums = self._sums(feat, feat_len)
         if self.norm_type == "utterance" or (self.norm_type == "batch" and not self.training):
             # feat_norm.py:137-139, 288-299: statistics are resolved inside the normalise kernel
+            sums = self._sums(feat, feat_len)
             out, _, _ = ops.normalize(feat, feat_len, dst=dst, stats=sums, clamp=self.clamp, use_mean=self.mean_norm,
                                       use_std=self.std_norm, **common)
         elif self.norm_type == "group" and isinstance(group_ids, torch.Tensor):
+            sums = self._sums(feat, feat_len) if self.training else None
             out = self._forward_group_tensor(feat, feat_len, dst, sums, group_ids, epoch, common)
         elif self.norm_type in ("batch", "global", "group"):
             if self.norm_type == "group":
@@ -203,7 +218,19 @@ class FeatureNormalization(Module):
                     f"If all the utterances in a single batch belong to the same group, "
                     f"you should give group_ids as a string or integer. But got type(group_ids)={type(group_ids)}.")
             mean = std = None
-            if self.training:
+            prefix = None if self.norm_type == "batch" else ("global" if self.norm_type == "global" else str(group_ids))
+            training = self.training and not self.frozen(prefix, epoch)
+            # (evaluation and frozen statistics need no sums: without the frontend kernel's they would cost a pass)
+            sums = self._sums(feat, feat_len) if training else None
+            if training and not bf16 and self.averaging(prefix, epoch):
+                # statistics still being averaged: running average + counter + normalise in one library call
+                _, _, packed = ops.stats_finalize(sums, feat_len, self.clamp, want_packed=True)
+                packed = self._all_reduce(packed)
+                count, weight, first, run_mean, run_std, counter = self._advance(prefix, epoch, D, feat.device)
+                out = ops.running_normalize(packed, weight, first, run_mean, run_std, counter, count, feat, feat_len,
+                                            src_has_pad=src_has_pad, pad_value=pad_value, masks=masks, warp=warp, dst=dst)
+                return (out.squeeze(-1) if squeeze else out), feat_len
+            if training:
                 _, _, packed = ops.stats_finalize(sums, feat_len, self.clamp, want_packed=True)
                 packed = self._all_reduce(packed)
                 if self.norm_type == "batch":
@@ -211,9 +238,8 @@ class FeatureNormalization(Module):
                     mean = mean if self.mean_norm else None
                     std = std if self.std_norm else None
             if self.norm_type != "batch":
-                prefix = "global" if self.norm_type == "global" else group_ids
-                if self.training:
-                    self.register_mean_std_batch(packed, D, str(prefix), epoch)
+                if training:
+                    self.register_mean_std_batch(packed, D, prefix, epoch)
                 mean = self.get_buffer(f"{prefix}_mean") if self.mean_norm else None
                 std = self.get_buffer(f"{prefix}_std") if self.std_norm else None
             out, _, _ = ops.normalize(feat, feat_len, dst=dst, mean=mean, std=std, per_utt=False, **common)
