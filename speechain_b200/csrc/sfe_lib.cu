@@ -1082,10 +1082,12 @@ extern "C" int sfe_running_normalize(const float* packed, int32_t D, float weigh
   const bool warp_on = warp && warp->enabled;
   if (warp_on && out == feat)
     return fail(SFE_ERR_BAD_ARG, "sfe_running_normalize: the time warp cannot run in place");
-  SFE_CUDA(launch_pdl_args(running_update_kernel, dim3((D + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream),
-                           packed, static_cast<int>(D), weight, static_cast<int>(first), 1, run_mean, run_std,
-                           static_cast<float*>(nullptr), static_cast<float*>(nullptr), reinterpret_cast<long long*>(counter),
-                           static_cast<long long>(count)));
+  // A plain launch on purpose.  With programmatic serialisation here as well, the whole chain frontend -> finalise ->
+  // this -> normalise launches early, and the normalise CTAs take the SMs the frontend kernel frees FIRST, four per
+  // SM: a grid that does not fill every slot (C4: 512 CTAs for 592) then leaves SMs idle for the whole pass
+  // (C4 step 606 us against 574 with the chain broken here; C2-sized steps lose 1 us to the launch gap).
+  running_update_kernel<<<(D + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      packed, D, weight, first, 1, run_mean, run_std, nullptr, nullptr, reinterpret_cast<long long*>(counter), count);
   SFE_CUDA(cudaGetLastError());
   if (warp_on) {
     if (!(warp->center > 0 && warp->center < warp->minlen && warp->pos > 0 && warp->pos < warp->minlen && warp->minlen <= F))
