@@ -280,3 +280,34 @@ def test_draw_helper_makes_the_reference_draw_sequence():
     # a pickled / deep-copied module starts with fresh descriptor arrays (they hold raw host addresses)
     c = copy.deepcopy(b)
     assert "_mask_cache" not in c.__dict__
+
+
+def test_which_training_steps_average_and_which_are_frozen():
+    """Host-side schedule choice of FeatureNormalization (feat_norm.py:455-508): a training step updates the running
+    statistics while epoch <= max_epoch_num (or no epoch is given); afterwards the statistics are frozen — but only
+    once all the buffers the step needs exist, otherwise the reference's own path (and its error) is taken."""
+    n = FeatureNormalization(input_size=4, norm_type="global", max_epoch_num=2)
+    n.train()
+    assert n.averaging("global", None) and n.averaging("global", 1) and n.averaging("global", 2)
+    assert not n.averaging("global", 3) and not n.averaging(None, 1)
+    assert not n.frozen("global", 3)                       # nothing registered yet
+    n.register_buffer("global_mean", torch.zeros(4))
+    assert not n.averaging("global", 1)                    # one of the two buffers only: the general path
+    n.register_buffer("global_std", torch.ones(4))
+    assert n.averaging("global", 1)
+    assert not n.frozen("global", 3)                       # no counter yet
+    n.register_buffer("global_batch", torch.tensor([7]))
+    assert n.frozen("global", 3) and not n.frozen("global", 2) and not n.frozen("global", None)
+    n.eval()
+    assert not n.averaging("global", 1)
+    b = FeatureNormalization(input_size=4, norm_type="batch")
+    b.train()
+    assert not b.averaging(None, 1) and not b.frozen(None, 9)
+    m = FeatureNormalization(input_size=4, norm_type="group", std_norm=False, max_epoch_num=2)
+    m.train()
+    assert m.averaging("spk3", 1)
+    m.register_buffer("spk3_mean", torch.zeros(4))
+    m.register_buffer("spk3_batch", torch.tensor([1]))
+    assert m.averaging("spk3", 2) and m.frozen("spk3", 3) and not m.frozen("spk4", 3)
+    # the host mirror of the counter: restored from the buffer once, then advanced without a sync
+    assert n._counter("global") == 7
