@@ -4,7 +4,7 @@ The path shards by utterance with no data-path collective; the only exchange is 
 (2·D+1)-float [sum of per-utterance means | sum of per-utterance stds | utterance count] buffer of
 batch/global normalisation, all-reduced once per batch (the reference issues three all_gathers,
 feat_norm.py:146-150,239-266)."""
-from typing import List, Sequence
+from typing import List
 
 import torch
 

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-from typing import Dict, Optional
+from typing import Optional
 
 import numpy as np
 import torch

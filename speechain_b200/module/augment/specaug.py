@@ -7,7 +7,6 @@ bytes) go to the device, where one kernel applies the time warp (4-tap cubic gat
 masks in a single read + write."""
 from typing import List, Optional, Union
 
-import numpy as np
 import torch
 
 from ...host import ops

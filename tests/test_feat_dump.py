@@ -1,5 +1,4 @@
 """Offline feature dumper (SURVEY §8 f4 iii): host logic on the CPU, end-to-end parity on the GPU."""
-import os
 import wave
 
 import numpy as np

@@ -5,7 +5,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import bench
-from speechain_b200.module.acoustic_frontend import AcousticFrontend
 from speechain_b200.module.frontend.speech2mel import Speech2MelSpec
 from speechain_b200.module.norm.feat_norm import FeatureNormalization
 from speechain_b200.module.augment.specaug import SpecAugment
