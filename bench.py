@@ -2,13 +2,16 @@
 """Benchmark of the acoustic-frontend hot path (BASELINE.json metric: log-Mel audio-seconds per
 second; HBM GB/s vs the measured peak; reference CPU path timed beside it).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4|c5] [--impl reference]
 
 One "step" = one pass of the hot path over one synthetic batch of the named workload.
   value  : audio-s/s with the waveforms already resident in HBM (CUDA events, max over ranks)
   e2e    : same metric through the public module API with PINNED HOST waveforms — the H2D copy
            of every step's batch and the D2H read of its result lengths are inside the timed region
-  roofline / cpu_baseline : see DESIGN.md §Measurement
+  roofline / cpu_baseline : see DESIGN.md §5
+  also   : (default workload only) the C1 kernel, the recipes' own blocks on the C2 batch — global statistics frozen
+           (c2_recipe) and still averaged (c2_recipe_averaging) with SpecAugment's time warp — and C4 with its
+           statistics all-reduce, each timed like `value`
 Inputs cycle through a ring of distinct batches whose total footprint exceeds 3x the 126 MB L2,
 so no step finds its input or output lines in cache.
 """
